@@ -1,0 +1,289 @@
+// Head-side small kernels: trunk tail (split-K reduce + bias + LayerNorm + tanh) and its
+// backward, the clipped TruncatedNormal sample, TD target / critic loss, actor loss.
+// Reference: drqv2.py:74-75,88-92,177-228; utils.py:105-126.
+#include "common.cuh"
+
+namespace drq {
+
+constexpr int kMaxFPerLane = 8;  // F <= 256
+
+// one warp per row
+__global__ void __launch_bounds__(128)
+ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_stride,
+                   const float* __restrict__ bias, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ h_out, long long ld_h,
+                   float* __restrict__ xhat, float* __restrict__ rstd_out, int B, int F, float eps) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float z[kMaxFPerLane];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxFPerLane; ++i) {
+        const int f = lane + 32 * i;
+        float v = 0.f;
+        if (f < F) {
+            for (int s = 0; s < S; ++s) v += partial[s * split_stride + (long long)row * F + f];
+            v += bias[f];
+        }
+        z[i] = v;
+        sum += v;
+    }
+    const float mean = warp_sum(sum) / (float)F;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxFPerLane; ++i) {
+        const int f = lane + 32 * i;
+        const float d = (f < F) ? z[i] - mean : 0.f;
+        sq += d * d;
+    }
+    const float var = warp_sum(sq) / (float)F;   // biased, as nn.LayerNorm
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxFPerLane; ++i) {
+        const int f = lane + 32 * i;
+        if (f < F) {
+            const float xh = (z[i] - mean) * rstd;
+            const float y = xh * gamma[f] + beta[f];
+            h_out[(long long)row * ld_h + f] = tanhf(y);
+            if (xhat) xhat[(long long)row * F + f] = xh;
+        }
+    }
+    if (rstd_out && lane == 0) rstd_out[row] = rstd;
+}
+
+// per row: dy = dh*(1-h^2); dxhat = dy*gamma; dz = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)).
+// dy and dy*xhat are staged in dz_tmp-style buffers for the column reduction below.
+__global__ void __launch_bounds__(128)
+ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const float* __restrict__ h,
+                       long long ld_h, const float* __restrict__ xhat,
+                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                       float* __restrict__ dz, float* __restrict__ dy_out, int B, int F) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float dxh[kMaxFPerLane], xh[kMaxFPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxFPerLane; ++i) {
+        const int f = lane + 32 * i;
+        dxh[i] = 0.f; xh[i] = 0.f;
+        if (f < F) {
+            const float hv = h[(long long)row * ld_h + f];
+            const float dy = dh[(long long)row * ld_dh + f] * (1.0f - hv * hv);
+            dy_out[(long long)row * F + f] = dy;
+            xh[i] = xhat[(long long)row * F + f];
+            dxh[i] = dy * gamma[f];
+            s1 += dxh[i];
+            s2 += dxh[i] * xh[i];
+        }
+    }
+    const float m1 = warp_sum(s1) / (float)F, m2 = warp_sum(s2) / (float)F;
+    const float r = rstd[row];
+#pragma unroll
+    for (int i = 0; i < kMaxFPerLane; ++i) {
+        const int f = lane + 32 * i;
+        if (f < F) dz[(long long)row * F + f] = r * (dxh[i] - m1 - xh[i] * m2);
+    }
+}
+
+// one block per feature: dgamma[f] = sum_b dy*xhat, dbeta[f] = sum_b dy (fixed-order tree)
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int F) {
+    __shared__ float sg[256], sb[256];
+    const int f = blockIdx.x;
+    float g = 0.f, b = 0.f;
+    for (int r = threadIdx.x; r < B; r += 256) {
+        const float d = dy[(long long)r * F + f];
+        g += d * xhat[(long long)r * F + f];
+        b += d;
+    }
+    sg[threadIdx.x] = g; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sg[threadIdx.x] += sg[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { dgamma[f] = sg[0]; dbeta[f] = sb[0]; }
+}
+
+// block-wide fixed-order sum of per-thread values (blockDim = 256)
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    const float r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// single block; thread t handles rows t, t+256, ...
+__global__ void __launch_bounds__(256)
+actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ eps,
+                    const float* __restrict__ std_dev, float clip, float* __restrict__ action_out,
+                    long long ld_a, float* __restrict__ mu_out, float* __restrict__ metrics, int B,
+                    int A) {
+    __shared__ float sh[256];
+    const float std = std_dev ? *std_dev : 0.f;
+    const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;  // utils.py:113 (python: -1.0 + 1e-6 -> fp32)
+    const float log_std = logf(std);
+    float lp_sum = 0.f;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float lp = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float mu = tanhf(mu_pre[(long long)b * A + j]);   // drqv2.py:89
+            float a = mu;
+            if (eps) {
+                float e = __fmul_rn(eps[(long long)b * A + j], std);      // utils.py:120
+                if (clip > 0.f) e = fminf(fmaxf(e, -clip), clip);         // utils.py:121-122
+                const float x = __fadd_rn(mu, e);                          // utils.py:123
+                a = fminf(fmaxf(x, lo), hi);                               // utils.py:113-116 (value)
+                // Normal.log_prob(a): -((a-mu)^2)/(2 var) - log(std) - log(sqrt(2 pi))
+                const float d = a - mu;
+                lp += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
+            }
+            action_out[(long long)b * ld_a + j] = a;
+            if (mu_out) mu_out[(long long)b * A + j] = mu;
+        }
+        lp_sum += lp;
+    }
+    if (metrics && gridDim.x == 1) {
+        const float t = block_sum_256(lp_sum, sh);
+        if (threadIdx.x == 0) {
+            metrics[0] = t / (float)B;                                         // actor_logprob
+            metrics[1] = (float)A * (0.5f + 0.9189385332046727f + log_std);    // actor_ent
+        }
+    }
+}
+
+__global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long ld_da,
+                                        const float* __restrict__ mu, float* __restrict__ dmu_pre,
+                                        int B, int A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * A) return;
+    const int b = i / A, j = i - b * A;
+    const float m = mu[i];
+    dmu_pre[i] = da[(long long)b * ld_da + j] * (1.0f - m * m);
+}
+
+__global__ void __launch_bounds__(256)
+critic_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
+                   const float* __restrict__ tq1, const float* __restrict__ tq2,
+                   const float* __restrict__ reward, const float* __restrict__ discount,
+                   float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ tq_out,
+                   float* __restrict__ metrics, int B) {
+    __shared__ float sh[256];
+    float s_r = 0.f, s_t = 0.f, s_1 = 0.f, s_2 = 0.f, s_l1 = 0.f, s_l2 = 0.f;
+    const float scale = 2.0f / (float)B;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const float tv = fminf(tq1[b], tq2[b]);                                  // drqv2.py:185
+        const float tq = __fadd_rn(reward[b], __fmul_rn(discount[b], tv));       // drqv2.py:186
+        const float e1 = q1[b] - tq, e2 = q2[b] - tq;
+        dq1[b] = scale * e1;   // d/dq mean((q - tq)^2)
+        dq2[b] = scale * e2;
+        if (tq_out) tq_out[b] = tq;
+        s_r += reward[b]; s_t += tq; s_1 += q1[b]; s_2 += q2[b];
+        s_l1 += e1 * e1; s_l2 += e2 * e2;
+    }
+    const float r = block_sum_256(s_r, sh), t = block_sum_256(s_t, sh);
+    const float a = block_sum_256(s_1, sh), c = block_sum_256(s_2, sh);
+    const float l1 = block_sum_256(s_l1, sh), l2 = block_sum_256(s_l2, sh);
+    if (metrics && threadIdx.x == 0) {
+        const float inv = 1.0f / (float)B;
+        metrics[0] = r * inv;               // batch_reward       drqv2.py:249
+        metrics[1] = t * inv;               // critic_target_q    drqv2.py:192
+        metrics[2] = a * inv;               // critic_q1
+        metrics[3] = c * inv;               // critic_q2
+        metrics[4] = l1 * inv + l2 * inv;   // critic_loss        drqv2.py:189
+    }
+}
+
+__global__ void __launch_bounds__(256)
+actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
+                  float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ metrics,
+                  int B) {
+    __shared__ float sh[256];
+    float s = 0.f;
+    const float g = -1.0f / (float)B;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const float a = q1[b], c = q2[b];
+        s += fminf(a, c);
+        dq1[b] = a < c ? g : (a == c ? 0.5f * g : 0.f);
+        dq2[b] = c < a ? g : (a == c ? 0.5f * g : 0.f);
+    }
+    const float t = block_sum_256(s, sh);
+    if (metrics && threadIdx.x == 0) metrics[0] = -(t / (float)B);   // drqv2.py:216
+}
+
+}  // namespace drq
+
+using namespace drq;
+
+extern "C" {
+
+int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
+                    const float* gamma, const float* beta, float* h_out, int64_t ld_h, float* xhat,
+                    float* rstd, int B, int F, float eps, void* stream) {
+    DRQ_REQUIRE(partial && bias && gamma && beta && h_out, "ln_tanh_fwd: null pointer");
+    DRQ_REQUIRE(B >= 0 && F > 0 && F <= 32 * kMaxFPerLane && S >= 1, "ln_tanh_fwd: bad dims (F<=256)");
+    if (B == 0) return DRQ_OK;
+    ln_tanh_fwd_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(
+        partial, S, split_stride, bias, gamma, beta, h_out, ld_h, xhat, rstd, B, F, eps);
+    return check_launch("ln_tanh_fwd_kernel");
+}
+
+int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, const float* xhat,
+                    const float* rstd, const float* gamma, float* dz, float* dgamma, float* dbeta,
+                    int B, int F, void* stream) {
+    DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && dgamma && dbeta, "ln_tanh_bwd: null pointer");
+    DRQ_REQUIRE(B > 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_bwd: bad dims (F<=256)");
+    // dy = dh * tanh' is staged in the second half of the caller's 2*B*F buffer
+    float* dy = dz + (long long)B * F;
+    ln_tanh_bwd_row_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(dh, ld_dh, h, ld_h, xhat, rstd,
+                                                                      gamma, dz, dy, B, F);
+    if (int rc = check_launch("ln_tanh_bwd_row_kernel")) return rc;
+    ln_param_grad_kernel<<<F, 256, 0, as_stream(stream)>>>(dy, xhat, dgamma, dbeta, B, F);
+    return check_launch("ln_param_grad_kernel");
+}
+
+int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev, float clip,
+                     float* action_out, int64_t ld_a, float* mu_out, float* metrics, int B, int A,
+                     void* stream) {
+    DRQ_REQUIRE(mu_pre && action_out, "actor_sample: null pointer");
+    DRQ_REQUIRE(!(eps && !std_dev), "actor_sample: eps without std");
+    DRQ_REQUIRE(B > 0 && A > 0, "actor_sample: bad dims");
+    actor_sample_kernel<<<1, 256, 0, as_stream(stream)>>>(mu_pre, eps, std_dev, clip, action_out, ld_a,
+                                                          mu_out, metrics, B, A);
+    return check_launch("actor_sample_kernel");
+}
+
+int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre, int B,
+                         int A, void* stream) {
+    DRQ_REQUIRE(daction && mu && dmu_pre && B > 0 && A > 0, "actor_sample_bwd: bad args");
+    actor_sample_bwd_kernel<<<(B * A + 255) / 256, 256, 0, as_stream(stream)>>>(daction, ld_da, mu,
+                                                                                dmu_pre, B, A);
+    return check_launch("actor_sample_bwd_kernel");
+}
+
+int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                    const float* reward, const float* discount, float* dq1, float* dq2,
+                    float* target_q_out, float* metrics, int B, void* stream) {
+    DRQ_REQUIRE(q1 && q2 && tq1 && tq2 && reward && discount && dq1 && dq2, "critic_loss: null pointer");
+    DRQ_REQUIRE(B > 0, "critic_loss: bad dims");
+    critic_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(q1, q2, tq1, tq2, reward, discount, dq1, dq2,
+                                                         target_q_out, metrics, B);
+    return check_launch("critic_loss_kernel");
+}
+
+int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, float* metrics, int B,
+                   void* stream) {
+    DRQ_REQUIRE(q1 && q2 && dq1 && dq2 && B > 0, "actor_loss: bad args");
+    actor_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(q1, q2, dq1, dq2, metrics, B);
+    return check_launch("actor_loss_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// GPU-resident replay ring: n-step gather, device-side sampler, per-update RNG draws.
+// Reference arithmetic: replay_buffer.py:142-160 (sample), dmc.py:86-109 (frame stack).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace drq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return DRQ_ERR_CUDA;
+    }
+    return DRQ_OK;
+}
+
+int ensure_smem(const void* kernel, size_t bytes, const char* what) {
+    static const void* seen_fn[64];
+    static size_t seen_bytes[64];
+    static int n_seen = 0;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen_fn[i] == kernel && seen_bytes[i] >= bytes) return DRQ_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%zu): %s", what, bytes, cudaGetErrorString(e));
+        return DRQ_ERR_CUDA;
+    }
+    int slot = -1;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen_fn[i] == kernel) slot = i;
+    if (slot < 0 && n_seen < 64) slot = n_seen++;
+    if (slot >= 0) { seen_fn[slot] = kernel; seen_bytes[slot] = bytes; }
+    return DRQ_OK;
+}
+
+// grid (B, 2*stack + 1).  y < 2*stack: copy one frame of obs / next_obs with 16-byte
+// vectors; y == 2*stack: action copy + the un-fused fp32 n-step chain.
+__global__ void __launch_bounds__(256)
+ring_gather_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ action,
+                   const float* __restrict__ reward, const float* __restrict__ discount,
+                   long long capacity, int frame_bytes, int stack, int A,
+                   const int* __restrict__ ep_start, const int* __restrict__ idx, int nstep,
+                   float gamma, uint8_t* __restrict__ obs_out, uint8_t* __restrict__ next_out,
+                   float* __restrict__ action_out, float* __restrict__ reward_out,
+                   float* __restrict__ discount_out) {
+    const int b = blockIdx.x;
+    const int y = blockIdx.y;
+    const long long start = ep_start[b];
+    const int row = idx[b];
+    if (y < 2 * stack) {
+        const bool is_next = y >= stack;
+        const int j = is_next ? y - stack : y;
+        const int t = is_next ? row + nstep - 1 : row - 1;  // replay_buffer.py:151,153
+        int r = t - (stack - 1 - j);                        // dmc.py:98-109: deque of last `stack` frames
+        r = r < 0 ? 0 : r;                                  // reset repeats the first frame
+        const long long slot = (start + r) % capacity;
+        const int4* src = reinterpret_cast<const int4*>(frames + slot * (long long)frame_bytes);
+        uint8_t* dst_base = (is_next ? next_out : obs_out) +
+                            ((long long)b * stack + j) * (long long)frame_bytes;
+        int4* dst = reinterpret_cast<int4*>(dst_base);
+        const int nvec = frame_bytes >> 4;
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
+        // tail (frame_bytes % 16 != 0 never happens for 3x84x84 but stay general)
+        for (int i = (nvec << 4) + threadIdx.x; i < frame_bytes; i += blockDim.x)
+            dst_base[i] = frames[slot * (long long)frame_bytes + i];
+    } else {
+        const long long s0 = (start + row) % capacity;
+        for (int a = threadIdx.x; a < A; a += blockDim.x)
+            action_out[(long long)b * A + a] = action[s0 * A + a];  // replay_buffer.py:152
+        if (threadIdx.x == 0) {
+            float rew = 0.f, disc = 1.f;  // replay_buffer.py:154-155
+            for (int i = 0; i < nstep; ++i) {
+                const long long s = (start + row + i) % capacity;
+                rew = __fadd_rn(rew, __fmul_rn(disc, reward[s]));             // :158
+                disc = __fmul_rn(disc, __fmul_rn(discount[s], gamma));        // :159
+            }
+            reward_out[b] = rew;
+            discount_out[b] = disc;
+        }
+    }
+}
+
+__global__ void ring_sample_kernel(const int* __restrict__ ep_table, int E, int nstep,
+                                   unsigned long long seed, const unsigned long long* counter,
+                                   int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint32_t r[4];
+    Philox::gen(seed, (*counter << 3) | 0ull, (uint64_t)b, r);
+    // unbiased enough for E, len << 2^32: multiply-shift range reduction
+    const int e = (int)(((uint64_t)r[0] * (uint64_t)E) >> 32);
+    const int start = ep_table[2 * e], len = ep_table[2 * e + 1];
+    const int span = len - nstep + 1;  // np.random.randint(0, len - nstep + 1) + 1
+    const int i = (int)(((uint64_t)r[1] * (uint64_t)span) >> 32) + 1;
+    ep_start_out[b] = start;
+    idx_out[b] = i;
+}
+
+// stream ids: 1 shift_obs, 2 shift_next, 3 eps_critic, 4 eps_actor
+__global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned long long* counter,
+                                        int pad, int* __restrict__ shift_obs,
+                                        int* __restrict__ shift_next, float* __restrict__ eps_c,
+                                        float* __restrict__ eps_a, int B, int A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long c = *counter;
+    const unsigned range = 2 * pad + 1;
+    if (i < B) {
+        uint32_t r[4];
+        Philox::gen(seed, (c << 3) | 1ull, (uint64_t)i, r);
+        shift_obs[2 * i] = (int)(((uint64_t)r[0] * range) >> 32);
+        shift_obs[2 * i + 1] = (int)(((uint64_t)r[1] * range) >> 32);
+        shift_next[2 * i] = (int)(((uint64_t)r[2] * range) >> 32);
+        shift_next[2 * i + 1] = (int)(((uint64_t)r[3] * range) >> 32);
+    }
+    const int n = B * A;
+    // Box-Muller: 4 words -> 2 pairs -> 4 normals; element i uses pair (i>>1) of stream 3/4.
+    if (i < n) {
+        uint32_t r[4];
+        Philox::gen(seed, (c << 3) | 3ull, (uint64_t)(i >> 1), r);
+        {
+            const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float s, co;
+            sincospif(2.0f * u2, &s, &co);
+            eps_c[i] = (i & 1) ? rad * s : rad * co;
+        }
+        {
+            const float u1 = ((float)(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float u2 = ((float)(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float s, co;
+            sincospif(2.0f * u2, &s, &co);
+            eps_a[i] = (i & 1) ? rad * s : rad * co;
+        }
+    }
+}
+
+__global__ void counter_advance_kernel(unsigned long long* counter) { *counter += 1ull; }
+
+// out[n,c,r,col] = in[n,c,clamp(r+sy-pad),clamp(col+sx-pad)]
+__global__ void random_shift_f32_kernel(const float* __restrict__ in, const int* __restrict__ shift,
+                                        float* __restrict__ out, int C, int H, int W, int pad) {
+    const int n = blockIdx.y;
+    const int sx = shift[2 * n], sy = shift[2 * n + 1];
+    const long long per = (long long)C * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % W);
+        const int r = (int)((i / W) % H);
+        const int c = (int)(i / ((long long)W * H));
+        const int sr = clampi(r + sy - pad, 0, H - 1), sc = clampi(col + sx - pad, 0, W - 1);
+        out[n * per + i] = in[n * per + ((long long)c * H + sr) * W + sc];
+    }
+}
+
+}  // namespace drq
+
+using namespace drq;
+
+extern "C" {
+
+int drq_abi_version(void) { return DRQ_ABI_VERSION; }
+const char* drq_last_error(void) { return drq::g_err; }
+
+int drq_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const float* reward,
+                          const float* discount, int64_t capacity, int frame_c, int stack, int A,
+                          const int32_t* ep_start, const int32_t* idx, int B, int nstep, float gamma,
+                          uint8_t* obs_out, uint8_t* next_obs_out, float* action_out,
+                          float* reward_out, float* discount_out, void* stream) {
+    DRQ_REQUIRE(frames && action && reward && discount && ep_start && idx, "ring_gather: null input");
+    DRQ_REQUIRE(obs_out && next_obs_out && action_out && reward_out && discount_out,
+                "ring_gather: null output");
+    DRQ_REQUIRE(capacity > 0 && frame_c > 0 && stack > 0 && A > 0 && nstep > 0, "ring_gather: bad dims");
+    if (B == 0) return DRQ_OK;
+    DRQ_REQUIRE(B > 0, "ring_gather: negative batch");
+    const int frame_bytes = frame_c * kImg * kImg;
+    DRQ_REQUIRE(frame_bytes % 16 == 0 && ((uintptr_t)frames % 16) == 0 &&
+                    ((uintptr_t)obs_out % 16) == 0 && ((uintptr_t)next_obs_out % 16) == 0,
+                "ring_gather: frames must be 16-byte aligned");
+    dim3 grid(B, 2 * stack + 1);
+    ring_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+        frames, action, reward, discount, (long long)capacity, frame_bytes, stack, A, ep_start, idx,
+        nstep, gamma, obs_out, next_obs_out, action_out, reward_out, discount_out);
+    return check_launch("ring_gather_kernel");
+}
+
+int drq_ring_sample(const int32_t* ep_table, int E, int nstep, uint64_t seed, const uint64_t* counter,
+                    int32_t* ep_start_out, int32_t* idx_out, int B, void* stream) {
+    DRQ_REQUIRE(ep_table && counter && ep_start_out && idx_out, "ring_sample: null pointer");
+    DRQ_REQUIRE(E > 0 && nstep > 0 && B > 0, "ring_sample: bad dims");
+    ring_sample_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(
+        ep_table, E, nstep, (unsigned long long)seed, (const unsigned long long*)counter,
+        ep_start_out, idx_out, B);
+    return check_launch("ring_sample_kernel");
+}
+
+int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_t* shift_obs,
+                         int32_t* shift_next, float* eps_critic, float* eps_actor, int B, int A,
+                         void* stream) {
+    DRQ_REQUIRE(counter && shift_obs && shift_next && eps_critic && eps_actor, "rng: null pointer");
+    DRQ_REQUIRE(B > 0 && A > 0 && pad >= 0, "rng: bad dims");
+    const int n = B * A > B ? B * A : B;
+    rng_update_draws_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+        (unsigned long long)seed, (const unsigned long long*)counter, pad, shift_obs, shift_next,
+        eps_critic, eps_actor, B, A);
+    return check_launch("rng_update_draws_kernel");
+}
+
+int drq_counter_advance(uint64_t* counter, void* stream) {
+    DRQ_REQUIRE(counter, "counter_advance: null pointer");
+    counter_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long*)counter);
+    return check_launch("counter_advance_kernel");
+}
+
+int drq_random_shift_f32(const float* in, const int32_t* shift, float* out, int N, int C, int H,
+                         int W, int pad, void* stream) {
+    DRQ_REQUIRE(in && shift && out, "random_shift: null pointer");
+    DRQ_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "random_shift: bad dims");
+    DRQ_REQUIRE(H == W, "random_shift: h != w (drqv2.py:21)");
+    if (N == 0) return DRQ_OK;
+    const long long per = (long long)C * H * W;
+    int gx = (int)((per + 255) / 256);
+    if (gx > 64) gx = 64;
+    random_shift_f32_kernel<<<dim3(gx, N), 256, 0, as_stream(stream)>>>(in, shift, out, C, H, W, pad);
+    return check_launch("random_shift_f32_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+/*
+ * drqv2_b200.h — C ABI of libdrqv2_b200.so: the DrQ-v2 agent-update hot path
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (johannah/drqv2) is pure Python/PyTorch and has no FFI of its
+ * own; its plug-in point is the duck-typed agent class named in
+ * cfgs/config.yaml:35 (`_target_: drqv2.DrQV2Agent`).  This header is the
+ * boundary a maintainer binds (ctypes) to replace the ATen
+ * library kernels that drqv2.py / utils.py / replay_buffer.py launch.  Every
+ * entry point cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in `_host`.  The caller owns all memory.
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as
+ *     void*) and returns immediately: no sync, no allocation, no host reads.
+ *     All entry points are CUDA-graph capturable.
+ *   - return value: 0 = ok; non-zero = error, text via drq_last_error().
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with DRQ_ERR_CUDA.
+ *
+ * Layouts
+ *   - parameters, gradients and Adam state are fp32 in the reference's own
+ *     layouts (conv [Cout,Cin,3,3]; linear [out,in]), so state_dict tensors
+ *     can alias them.
+ *   - encoder activations use the "wide plane" layout: [N][32][DRQ_PLANE]
+ *     with a fixed row stride of DRQ_PW = 41 elements for every layer (conv1's
+ *     true output width).  Layer l's valid region is rows/cols < 41,39,37,35;
+ *     other positions are don't-care in forward buffers and exactly zero in
+ *     gradient buffers.  A 3x3 stride-1 tap (ky,kx) is then the constant
+ *     offset ky*41+kx, which makes forward and dgrad the same shifted GEMM.
+ *   - features handed to the heads are compact NCHW-flattened [N][39200],
+ *     exactly drqv2.py:66 `h.view(h.shape[0], -1)`.
+ */
+#ifndef DRQV2_B200_H
+#define DRQV2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRQ_ABI_VERSION 1
+
+#define DRQ_OK 0
+#define DRQ_ERR_INVALID 1 /* bad argument */
+#define DRQ_ERR_CUDA 2    /* CUDA runtime / launch failure */
+
+#define DRQ_IMG 84          /* input frame height = width (dmc.py pixels wrapper) */
+#define DRQ_PW 41           /* wide-plane row stride */
+#define DRQ_PLANE 1696      /* wide-plane stride per channel (41*41=1681, padded) */
+#define DRQ_CONV_CH 32      /* drqv2.py:55 */
+#define DRQ_REPR_DIM 39200  /* drqv2.py:53 32*35*35 */
+
+/* GEMM epilogues (drq_gemm_f32) */
+#define DRQ_EPI_NONE 0       /* C = acc (+bias) */
+#define DRQ_EPI_RELU 1       /* C = relu(acc + bias)            nn.ReLU in drqv2.py:77-81,103-111 */
+#define DRQ_EPI_MASK 2       /* C = acc * (mask > 0)            ReLU backward */
+#define DRQ_EPI_MASK_WIDE 3  /* as MASK, N index = compact feature k -> scatter into wide plane */
+
+int drq_abi_version(void);
+const char* drq_last_error(void);
+/* number of SMs of the current device (0 if none) — used to size persistent grids */
+int drq_device_sm_count(void);
+
+/* ------------------------------------------------------------------ replay */
+
+/* n-step gather from the GPU-resident uint8 ring.
+ * Replaces ReplayBuffer._sample (replay_buffer.py:142-160) + default-collate +
+ * utils.to_torch (utils.py:48-49).
+ * Ring: one slot per environment step; slot s holds the newest frame
+ * frames[s] u8[frame_c,84,84], action[s] f32[A], reward[s], discount[s].  An episode occupies
+ * consecutive slots modulo `capacity`, row 0 being the reset step.
+ * Sample i is (ep_start[i], idx[i]): first slot of its episode and the row
+ * `idx` of replay_buffer.py:150.  Produces
+ *   obs[i]      = stack of rows max(idx-1-(S-1-j),0), j=0..S-1   (dmc.py:86-109)
+ *   next_obs[i] = same for row idx+nstep-1
+ *   action[i]   = action[idx];  reward/discount = the fp32 chain of
+ *                 replay_buffer.py:154-159, un-fused (bit-exact).
+ * frame_c = channels per frame (3), stack = frames per observation (3). */
+int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const float* reward,
+                          const float* discount, int64_t capacity, int frame_c, int stack, int A,
+                          const int32_t* ep_start, const int32_t* idx, int B, int nstep,
+                          float gamma, uint8_t* obs_out, uint8_t* next_obs_out,
+                          float* action_out, float* reward_out, float* discount_out,
+                          void* stream);
+
+/* Device-side sampler: episode ~ U{0..E-1} then idx ~ U{1..len-nstep+1}
+ * (replay_buffer.py:96-98,150).  ep_table is int32 [E][2] = (start slot, len)
+ * with len = transitions in the episode (rows-1).  Philox4x32-10 keyed by
+ * (seed, *counter); the kernel does not advance the counter. */
+int drq_ring_sample(const int32_t* ep_table, int E, int nstep, uint64_t seed,
+                    const uint64_t* counter, int32_t* ep_start_out, int32_t* idx_out, int B,
+                    void* stream);
+
+/* ------------------------------------------------------------------ RNG */
+
+/* Per-update random draws, in the reference's order (drqv2.py:241-242 shifts,
+ * utils.py:119 noise x2): shift_obs/shift_next int32 [B][2] = (x, y) in
+ * [0, 2*pad], eps_critic/eps_actor f32 [B][A] ~ N(0,1).  Keyed by
+ * (seed, *counter); `counter` is advanced by drq_counter_advance. */
+int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_t* shift_obs,
+                         int32_t* shift_next, float* eps_critic, float* eps_actor, int B, int A,
+                         void* stream);
+int drq_counter_advance(uint64_t* counter, void* stream);
+
+/* ------------------------------------------------------------------ augmentation */
+
+/* RandomShiftsAug as an exact integer shift (drqv2.py:19-45 in intent):
+ * out[n,c,r,col] = in[n,c,clamp(r+sy-pad,0,H-1),clamp(col+sx-pad,0,W-1)],
+ * shift[n] = (sx, sy).  Stand-alone (materialising) form used by the
+ * RandomShiftsAug module; the update path uses the fused conv1 loader. */
+int drq_random_shift_f32(const float* in, const int32_t* shift, float* out, int N, int C, int H,
+                         int W, int pad, void* stream);
+
+/* ------------------------------------------------------------------ encoder, fp32 */
+
+/* conv1 of drqv2.py:55 (Cin->32, k3, stride 2) + ReLU, with RandomShiftsAug
+ * (integer shift, pad 4) and `obs / 255.0 - 0.5` (drqv2.py:64) fused into the
+ * loader.  obs u8 [N][cin][84][84]; shift int32 [N][2] (x,y) or NULL for no
+ * augmentation (act path).  out: wide plane [N][32][DRQ_PLANE]. */
+int drq_conv1_fwd_f32(const uint8_t* obs, const int32_t* shift, const float* w, const float* b,
+                      float* out, int N, int cin, int pad, void* stream);
+
+/* weight/bias gradient of conv1: dw [32][cin][3][3], db [32] from
+ * dpre (wide, gradient w.r.t. the pre-ReLU output).  partial: workspace of
+ * drq_conv_wgrad_ws_floats(cin) floats. */
+int drq_conv1_wgrad_f32(const uint8_t* obs, const int32_t* shift, const float* dpre,
+                        float* partial, float* dw, float* db, int N, int cin, int pad,
+                        void* stream);
+
+/* conv2..4 of drqv2.py:56-59 (32->32, k3, stride 1) + ReLU.
+ * in: wide plane; hout = valid output rows = cols (39, 37 or 35).
+ * compact_out != 0: write out as [N][32][hout][hout] (the flattened features
+ * of drqv2.py:66) instead of the wide plane. */
+int drq_conv3x3_fwd_f32(const float* in, const float* w, const float* b, float* out, int N,
+                        int hout, int compact_out, void* stream);
+
+/* data gradient: din_pre[ci][q] = relu'(act_in[ci][q]) * sum_{co,tap} w[co][ci][tap] dout[co][q-off].
+ * dout: wide, gradient w.r.t. this layer's PRE-ReLU output (zero outside the
+ * valid hout x hout region).  act_in: this layer's input activation (post-ReLU
+ * output of the layer below), used as the ReLU mask.  din: wide, gradient
+ * w.r.t. the layer below's pre-ReLU output, zero outside (hout+2)^2. */
+int drq_conv3x3_dgrad_f32(const float* dout, const float* w, const float* act_in, float* din,
+                          int N, int hout, void* stream);
+
+/* weight/bias gradient of a 32->32 layer.  in: wide input activation, dpre:
+ * wide gradient w.r.t. pre-ReLU output.  partial: workspace of
+ * drq_conv_wgrad_ws_floats(32) floats. */
+int drq_conv3x3_wgrad_f32(const float* in, const float* dpre, float* partial, float* dw,
+                          float* db, int N, int hout, void* stream);
+int64_t drq_conv_wgrad_ws_floats(int cin);
+
+/* ------------------------------------------------------------------ dense, fp32 */
+
+/* C[z][m][n] = epi( sum_k A[z](m,k) * B[z](k,n) + bias[z][n] ), general strides.
+ * A(m,k) = A[m*sa_m + k*sa_k], B(k,n) = B[k*sb_k + n*sb_n], C row stride ldc.
+ * batch > 1: independent problems at pointer strides (bs_a, bs_b, bs_c,
+ * bs_bias, bs_mask) — the twin Q heads of drqv2.py:103-111.
+ * splitk > 1 (batch must be 1): K is cut in `splitk` chunks and chunk s writes
+ * its raw partial sum to C + s*bs_c (bias/epilogue ignored) — reduced in fixed
+ * order by drq_ln_tanh_fwd / drq_splitk_reduce.
+ * accumulate != 0: C += result (after epilogue).  mask has C's shape/ld. */
+int drq_gemm_f32(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
+                 int64_t sb_n, float* C, int64_t ldc, const float* bias, const float* mask,
+                 int64_t ldmask, int M, int N, int K, int epilogue, int accumulate, int batch,
+                 int64_t bs_a, int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask,
+                 int splitk, void* stream);
+
+/* out[n] (+)= sum_s partial[s][n]  (fixed order; used for split-K and bias grads) */
+int drq_splitk_reduce(const float* partial, int S, int64_t stride, float* out, int64_t n,
+                      void* stream);
+
+/* out[z][n] = sum_m X[z][m*ld + n]  — bias gradients. */
+int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,
+                   int64_t bs_out, void* stream);
+
+/* trunk tail: z = sum_s partial[s] + bias; LayerNorm(F, eps) affine; tanh
+ * (drqv2.py:74-75,100-101).  h written at h_out[b*ld_h + f] (so it can land in
+ * the [h, action] concat buffer of drqv2.py:117).  xhat [B][F] and rstd [B]
+ * are saved for backward when non-NULL. */
+int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
+                    const float* gamma, const float* beta, float* h_out, int64_t ld_h,
+                    float* xhat, float* rstd, int B, int F, float eps, void* stream);
+
+/* backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
+ * output), dgamma[F], dbeta[F].  h is the saved tanh output (ld_h).
+ * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) is scratch. */
+int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h,
+                    const float* xhat, const float* rstd, const float* gamma, float* dz,
+                    float* dgamma, float* dbeta, int B, int F, void* stream);
+
+/* ------------------------------------------------------------------ heads */
+
+/* Actor tail (drqv2.py:88-92 + utils.py:112-126): mu = tanh(mu_pre);
+ * e = eps*std; if clip > 0: e = clamp(e,-clip,clip); a = clamp(mu+e, -1+1e-6, 1-1e-6).
+ * std is read from the device scalar *std_dev.  eps == NULL -> a = mu (eval
+ * mode mean).  Writes a at action_out[b*ld_a + j] and mu at mu_out (nullable).
+ * metrics (nullable) [2]: mean_b sum_j log_prob, mean_b sum_j entropy
+ * (drqv2.py:212,226). */
+int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev, float clip,
+                     float* action_out, int64_t ld_a, float* mu_out, float* metrics, int B, int A,
+                     void* stream);
+
+/* d(mu_pre) = d(action) * (1 - mu^2)   (straight-through clamp, utils.py:113-116) */
+int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
+                         int B, int A, void* stream);
+
+/* TD target + critic loss (drqv2.py:185-189): tq = r + d*min(tq1,tq2);
+ * loss = mean((q1-tq)^2) + mean((q2-tq)^2); dq1 = 2(q1-tq)/B, dq2 likewise.
+ * metrics [5]: batch_reward, critic_target_q, critic_q1, critic_q2, critic_loss
+ * (drqv2.py:192-195,249).  target_q_out nullable [B]. */
+int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                    const float* reward, const float* discount, float* dq1, float* dq2,
+                    float* target_q_out, float* metrics, int B, void* stream);
+
+/* actor loss (drqv2.py:213-216): L = -mean(min(q1,q2)); dq1/dq2 = -1/B on the
+ * smaller head (split evenly on exact ties, as torch.minimum's backward).
+ * metrics [1]: actor_loss. */
+int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, float* metrics,
+                   int B, void* stream);
+
+/* ------------------------------------------------------------------ optimiser */
+
+/* scalars (device, float[8]): [0] 1-beta1, [1] beta2, [2] 1-beta2,
+ * [3] sqrt(1-beta2^t), [4] eps, [5] -lr/(1-beta1^t)  — computed on the host in
+ * float64 exactly as torch/optim/adam.py:531-547 and cast to fp32.
+ * One launch updates the contiguous range p[0..n): torch.optim.Adam x3 of
+ * drqv2.py:148-150,201-202,221 over the flat parameter arena. */
+int drq_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* scalars,
+                  void* stream);
+
+/* soft target update (utils.py:42-45): tp = tau*p + (1-tau)*tp, two rounded
+ * multiplies then an add (bit-exact). */
+int drq_soft_update(const float* p, float* tp, int64_t n, float tau, float one_minus_tau,
+                    void* stream);
+
+/* fused: Adam over p[0..n_adam) and soft update of target from src[0..n_ema)
+ * in one launch (K17+K18 of SURVEY §2.1). */
+int drq_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n_adam,
+                      const float* scalars, const float* ema_src, float* ema_dst, int64_t n_ema,
+                      float tau, float one_minus_tau, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRQV2_B200_H */
