@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the DrQ-v2 agent update (BASELINE.json metric: updates/sec at batch 256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one DrQV2Agent.update (critic + actor + soft target update) on a fresh
+batch of the walker_walk shape (B=256, 9x84x84 uint8 stacks, A=6, F=50, H=1024, n-step 3).
+
+ours      : `value` = updates/s with the replay ring resident in HBM (sample + n-step
+            gather + update captured in one CUDA graph, timed with CUDA events);
+            `e2e` = the same update through the public API fed from HOST batches
+            (pinned memory -> H2D inside the timed region, metrics read back D2H).
+reference : the CPU restatement of the reference's update (oracle/ port; the reference is
+            pure PyTorch, there is nothing to compile) on the host cores, bounded sample.
+Multi-GPU : one process per GPU (torchrun); independent agents (ensemble members) with no
+            collective, value = sum over ranks / max-over-ranks time, scaling "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCHED = "linear(1.0,0.1,100000)"
+E_F, E_B = 84_561_984, 160_409_664     # encoder fwd / bwd FLOP per sample
+CONV_MACS = {39: 14_017_536, 37: 12_616_704, 35: 11_289_600}
+
+
+def update_flops(B, A, F, H):
+    T = 2 * 39200 * F
+    Q = 2 * ((F + A) * H + H * H + H)
+    P = 2 * (F * H + H * H + H * A)
+    return B * (2 * E_F + E_B + 8 * T + (2 * P + 6 * Q) + (6 * Q + 2 * P))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fill_ring(loader_dir, A, episodes, rows, device, seed=1):
+    """SURVEY §8d synthetic replay: E episodes x rows steps of uniform u8 frames, action~U(-1,1),
+    reward~U(0,1), discount 1; row 0 is the reset dummy.  Written straight into the ring."""
+    from drqv2_b200 import replay_buffer as rb
+    cap = episodes * rows
+    ring = rb.GpuRing(cap, 3, 3, A, device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    ring.frames.copy_(torch.randint(0, 256, ring.frames.shape, dtype=torch.uint8, device=device, generator=g))
+    ring.action.copy_(torch.rand(cap, A, device=device, generator=g) * 2 - 1)
+    ring.reward.copy_(torch.rand(cap, device=device, generator=g))
+    ring.discount.fill_(1.0)
+    starts = torch.arange(episodes, device=device) * rows
+    ring.action[starts] = 0
+    ring.reward[starts] = 0
+    ring.episodes = [(int(e * rows), rows) for e in range(episodes)]
+    ring.head = 0
+    ring._upload_table()
+    rb._RINGS[str(loader_dir)] = dict(ring=ring, capacity=cap, storage=None)
+    return ring
+
+
+def time_kernel(fn, iters=20):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def run_ours(args, rank, world):
+    from drqv2_b200 import DrQV2Agent, _lib, make_replay_loader
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    torch.manual_seed(rank)                       # ensemble member = independent seed
+    np.random.seed(7 + rank)
+    agent = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
+                       use_cuda_graph=True, seed=rank)
+    key = f"/bench/ring{rank}"
+    fill_ring(key, A, args.episodes, 501, dev, seed=1 + rank)
+    loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
+    it = iter(loader)
+
+    # count kernel launches of one update (eager pass == what the graph replays)
+    n_calls = [0]
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        n_calls[0] += 1
+        return orig_call(name, *a)
+
+    import drqv2_b200.drqv2 as D
+    import drqv2_b200.replay_buffer as R
+    D.call = R.call = counting_call
+    step = 0
+    agent.update(it, step); step += 2             # eager warm-up (counts launches)
+    launches_per_update = n_calls[0] + 1          # + the H2D scalar copy node is not a kernel; +1 = none
+    launches_per_update = n_calls[0]
+    D.call = R.call = orig_call
+    # conv wgrad entry points launch 2 kernels each (partial + reduce)
+    launches_per_update += 4
+    for _ in range(max(args.warmup, 3)):
+        agent.update(it, step); step += 2
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        agent.update(it, step); step += 2
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- e2e: public API fed from host batches (pinned), metrics read back
+    agent.use_tb = True
+    g = torch.Generator().manual_seed(100 + rank)
+    nhost = 4
+    host_batches = []
+    for _ in range(nhost):
+        host_batches.append(tuple(t.pin_memory() for t in (
+            torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g),
+            torch.rand(B, A, generator=g) * 2 - 1, torch.rand(B, 1, generator=g),
+            torch.full((B, 1), 0.970299065), torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g))))
+
+    def host_iter():
+        i = 0
+        while True:
+            yield host_batches[i % nhost]
+            i += 1
+
+    hit = host_iter()
+    for _ in range(4):
+        agent.update(hit, step); step += 2
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        m = agent.update(hit, step); step += 2
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_value = world * 1e3 / (e2e_ms / args.steps)
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0]) + 64
+    d2h = 8 * 4
+    assert np.isfinite(m["critic_loss"])
+    agent.use_tb = False
+
+    out = None
+    if rank == 0:
+        hbm, tf_burst, tf_sust, src = peaks()
+        flops = update_flops(B, A, Fd, H)
+        # ---- dominant kernel, timed alone with CUDA events on its launch stream
+        ws = agent.workspace(B)
+        s = torch.cuda.current_stream().cuda_stream
+        pe = lambda k: agent._p("encoder", k)
+        ge = lambda k: agent._g("encoder", k)
+        acts = [a.data_ptr() for a in ws.acts]
+        d = [t.data_ptr() for t in ws.dpre]
+        cand = {
+            "conv3x3_fwd_f32(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_f32", acts[0], pe("convnet.2.weight"), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, s),
+                                              2 * CONV_MACS[39] * 2 * B),
+            "conv3x3_dgrad_f32(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_f32", d[1], pe("convnet.2.weight"), acts[0], d[0], B, 39, s),
+                                              2 * CONV_MACS[39] * B),
+            "conv3x3_wgrad_f32(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_f32", acts[0], d[1], ws.wgrad_ws.data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
+                                              2 * CONV_MACS[39] * B),
+        }
+        kt = {k: (time_kernel(fn), fl) for k, (fn, fl) in cand.items()}
+        # share of the step: fwd x3 layers x(2B), dgrad x3, wgrad x3 are of the same class
+        dom = max(kt, key=lambda k: kt[k][0])
+        dt, fl = kt[dom]
+        roof = {"bound": "tensor", "kernel": dom, "achieved": fl / dt / 1e12, "peak": tf_burst,
+                "unit": "TFLOP/s", "frac": fl / dt / 1e12 / tf_burst, "traffic": None, "peak_source": src,
+                "kernel_ms": dt * 1e3,
+                "all_kernels_ms": {k: v[0] * 1e3 for k, v in kt.items()},
+                "whole_update": {"flop": flops, "achieved": flops * value / world / 1e12,
+                                 "frac_of_sustained": flops * value / world / 1e12 / tf_sust}}
+        cpu = cpu_baseline(args, steps=2)
+        out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic",
+               "config": {"workload": f"configs[1]: walker_walk-shape agent.update, B={B}, 9x84x84 u8 stacks, A={A}, "
+                                      f"F={Fd}, H={H}, n-step 3, GPU-resident replay ring ({args.episodes} episodes x 501 "
+                                      "rows), CUDA-graphed, fp32 parity mode" + (f"; {world} independent agents (ensemble), one per GPU" if world > 1 else ""),
+                          "l2": "inputs larger than L2: each step gathers a fresh 32.5 MB batch from a "
+                                f"{args.episodes * 501 * 21168 / 1e6:.0f} MB ring and streams ~700 MB of activations",
+                          "mode": "fp32"},
+               "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches_per_update * args.steps, "launches_per_update": launches_per_update,
+               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    return out
+
+
+def cpu_baseline(args, steps=2, warm=1):
+    """The oracle port of the reference's update (torch CPU, all host threads) on a bounded
+    sample: `steps` updates of the same B=256 workload."""
+    from oracle import drq_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    params = O.synthetic_params(9, A, Fd, H, seed=0)
+    agent = O.OracleAgent(params, 1e-4, 0.01, SCHED, 0.3, dtype=torch.float32, aug="grid")
+    b = O.synthetic_batch(B, A, seed=1)
+    a = (b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])
+    k = (b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+    for i in range(warm):
+        agent.update(*a, 2 * i, *k)
+    t = time.perf_counter()
+    for i in range(steps):
+        agent.update(*a, 2 * (i + warm), *k)
+    dt = (time.perf_counter() - t) / steps
+    return {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} updates (after {warm} warm-up) of the same B={B} workload, pre-collated tensors, "
+                      "float grid_sample aug as the reference ships it"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    steps = max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 2))
+    cpu = cpu_baseline(args, steps=steps, warm=warm)
+    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    return {"impl": "reference", "metric": "DrQ-v2 updates/sec at batch 256", "value": cpu["value"],
+            "unit": "updates/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[0]: reference's CPU update path (oracle port, torch CPU), B={B}, A={A}, "
+                                   f"F={Fd}, H={H}"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--action-dim", type=int, default=6)
+    ap.add_argument("--feature-dim", type=int, default=50)
+    ap.add_argument("--hidden-dim", type=int, default=1024)
+    ap.add_argument("--episodes", type=int, default=64)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if world > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        torch.distributed.init_process_group("nccl")
+    out = run_ours(args, rank, world)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

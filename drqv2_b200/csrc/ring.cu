@@ -91,12 +91,13 @@ ring_gather_kernel(const uint8_t* __restrict__ frames, const float* __restrict__
     }
 }
 
-__global__ void ring_sample_kernel(const int* __restrict__ ep_table, int E, int nstep,
+__global__ void ring_sample_kernel(const int* __restrict__ ep_table, const int* __restrict__ n_episodes, int nstep,
                                    unsigned long long seed, const unsigned long long* counter,
                                    int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     uint32_t r[4];
+    const int E = *n_episodes;
     Philox::gen(seed, (*counter << 3) | 0ull, (uint64_t)b, r);
     // unbiased enough for E, len << 2^32: multiply-shift range reduction
     const int e = (int)(((uint64_t)r[0] * (uint64_t)E) >> 32);
@@ -147,6 +148,21 @@ __global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned 
     }
 }
 
+// out[i] ~ N(0,1): stream 5, Box-Muller on pair (i >> 1)
+__global__ void rng_normal_kernel(unsigned long long seed, const unsigned long long* counter,
+                                  float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[4];
+    Philox::gen(seed, (*counter << 3) | 5ull, (uint64_t)(i >> 1), r);
+    const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, co;
+    sincospif(2.0f * u2, &s, &co);
+    out[i] = (i & 1) ? rad * s : rad * co;
+}
+
 __global__ void counter_advance_kernel(unsigned long long* counter) { *counter += 1ull; }
 
 // out[n,c,r,col] = in[n,c,clamp(r+sy-pad),clamp(col+sx-pad)]
@@ -163,6 +179,14 @@ __global__ void random_shift_f32_kernel(const float* __restrict__ in, const int*
         const int sr = clampi(r + sy - pad, 0, H - 1), sc = clampi(col + sx - pad, 0, W - 1);
         out[n * per + i] = in[n * per + ((long long)c * H + sr) * W + sc];
     }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
+                              long long ld_dst, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = src[r * ld_src + c];
 }
 
 }  // namespace drq
@@ -206,12 +230,12 @@ int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const floa
     return check_launch("ring_gather_kernel");
 }
 
-int drq_ring_sample(const int32_t* ep_table, int E, int nstep, uint64_t seed, const uint64_t* counter,
-                    int32_t* ep_start_out, int32_t* idx_out, int B, void* stream) {
-    DRQ_REQUIRE(ep_table && counter && ep_start_out && idx_out, "ring_sample: null pointer");
-    DRQ_REQUIRE(E > 0 && nstep > 0 && B > 0, "ring_sample: bad dims");
+int drq_ring_sample(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed,
+                    const uint64_t* counter, int32_t* ep_start_out, int32_t* idx_out, int B, void* stream) {
+    DRQ_REQUIRE(ep_table && n_episodes && counter && ep_start_out && idx_out, "ring_sample: null pointer");
+    DRQ_REQUIRE(nstep > 0 && B > 0, "ring_sample: bad dims");
     ring_sample_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(
-        ep_table, E, nstep, (unsigned long long)seed, (const unsigned long long*)counter,
+        ep_table, n_episodes, nstep, (unsigned long long)seed, (const unsigned long long*)counter,
         ep_start_out, idx_out, B);
     return check_launch("ring_sample_kernel");
 }
@@ -226,6 +250,20 @@ int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_
         (unsigned long long)seed, (const unsigned long long*)counter, pad, shift_obs, shift_next,
         eps_critic, eps_actor, B, A);
     return check_launch("rng_update_draws_kernel");
+}
+
+int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
+                   void* stream) {
+    DRQ_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad args");
+    copy2d_kernel<<<(rows * cols + 255) / 256, 256, 0, as_stream(stream)>>>(src, ld_src, dst, ld_dst, rows, cols);
+    return check_launch("copy2d_kernel");
+}
+
+int drq_rng_normal_f32(uint64_t seed, const uint64_t* counter, float* out, int n, void* stream) {
+    DRQ_REQUIRE(counter && out && n > 0, "rng_normal: bad args");
+    rng_normal_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+        (unsigned long long)seed, (const unsigned long long*)counter, out, n);
+    return check_launch("rng_normal_kernel");
 }
 
 int drq_counter_advance(uint64_t* counter, void* stream) {

@@ -1,0 +1,823 @@
+"""DrQ-v2 agent on hand-written sm_100a CUDA kernels (libdrqv2_b200.so).
+
+Mirrors the reference's drqv2.py API surface — ``RandomShiftsAug``, ``Encoder``,
+``Actor``, ``Critic``, ``DrQV2Agent.{act, update, update_critic, update_actor, train}``
+(reference drqv2.py:14-262) — so that ``cfgs/config.yaml``'s ``agent._target_`` can point
+here and the reference's ``train.py`` runs unchanged.  Every tensor op of the update is
+a kernel of the C ABI in ``include/drqv2_b200.h``; PyTorch only owns memory, streams
+and the CUDA graph.  There is no CPU / eager-PyTorch fallback: on a machine without the
+built extension or without a CUDA device these classes raise.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, utils
+from ._lib import EPI_MASK, EPI_MASK_WIDE, EPI_NONE, EPI_RELU, PLANE, REPR_DIM, call
+
+F32 = 4
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; drqv2_b200 runs on CUDA only (no CPU fallback)")
+
+
+def _splitk_for(m_rows, K=REPR_DIM, target_blocks=296):
+    """Split-K factor for the skinny trunk GEMM (N <= 128): fill ~2 CTAs/SM of the 148 SMs."""
+    mblocks = (m_rows + 63) // 64
+    s0 = max(1, min(target_blocks // mblocks, K // 64))
+    chunk = -(-K // s0)
+    chunk = -(-chunk // 16) * 16
+    return -(-K // chunk)
+
+
+# ----------------------------------------------------------------------------- kernel wrappers
+def _gemm(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias=0, mask=0, ldmask=0, epi=EPI_NONE,
+          acc=0, batch=1, bs=(0, 0, 0, 0, 0), splitk=1):
+    call("drq_gemm_f32", A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, bias or None, mask or None, ldmask, M, N, K,
+         epi, acc, batch, bs[0], bs[1], bs[2], bs[3], bs[4], splitk, _stream())
+
+
+def _linear_fwd(x, ldx, W, b, y, ldy, M, n_out, n_in, relu, batch=1, bs=(0, 0, 0, 0, 0)):
+    """y = [relu](x @ W.T + b); W is [n_out, n_in] (nn.Linear layout)."""
+    _gemm(x, ldx, 1, W, 1, n_in, y, ldy, M, n_out, n_in, bias=b, epi=EPI_RELU if relu else EPI_NONE,
+          batch=batch, bs=bs)
+
+
+def _linear_dgrad(dy, ld_dy, W, dx, ld_dx, M, n_out, n_in, mask=0, ldmask=0, acc=0, batch=1,
+                  bs=(0, 0, 0, 0, 0), w_col0=0, n_cols=None):
+    """dx = dy @ W[:, w_col0:w_col0+n_cols] (optionally * (mask > 0))."""
+    n_cols = n_in if n_cols is None else n_cols
+    _gemm(dy, ld_dy, 1, W + F32 * w_col0, n_in, 1, dx, ld_dx, M, n_cols, n_out, mask=mask, ldmask=ldmask,
+          epi=EPI_MASK if mask else EPI_NONE, acc=acc, batch=batch, bs=bs)
+
+
+def _linear_wgrad(dy, ld_dy, x, ldx, dW, M, n_out, n_in, batch=1, bs=(0, 0, 0, 0, 0)):
+    """dW[n_out, n_in] = dy.T @ x."""
+    _gemm(dy, 1, ld_dy, x, ldx, 1, dW, n_in, n_out, n_in, M, batch=batch, bs=bs)
+
+
+def _colsum(X, ld, out, M, N, batch=1, bs_x=0, bs_out=0):
+    call("drq_colsum_f32", X, ld, out, M, N, batch, bs_x, bs_out, _stream())
+
+
+def _trunk_fwd(feat, B, W, b, gamma, beta, Fdim, partial, h_out, ld_h, xhat=0, rstd=0):
+    """Linear(39200->F) as split-K GEMM, then the fused reduce + bias + LayerNorm + tanh."""
+    S = _splitk_for(B)
+    _gemm(feat, REPR_DIM, 1, W, 1, REPR_DIM, partial, Fdim, B, Fdim, REPR_DIM, splitk=S,
+          bs=(0, 0, B * Fdim, 0, 0))
+    call("drq_ln_tanh_fwd", partial, S, B * Fdim, b, gamma, beta, h_out, ld_h, xhat or None, rstd or None,
+         B, Fdim, 1e-5, _stream())
+
+
+def _encoder_fwd(obs_u8, shift, w, b, acts, feat, N, cin, pad=4):
+    """conv1 (u8 + shift + normalise fused) -> conv2 -> conv3 -> conv4 (compact features).
+    w/b: 4 pointers each; acts: 3 wide-plane buffers."""
+    s = _stream()
+    call("drq_conv1_fwd_f32", obs_u8, shift or None, w[0], b[0], acts[0], N, cin, pad, s)
+    call("drq_conv3x3_fwd_f32", acts[0], w[1], b[1], acts[1], N, 39, 0, s)
+    call("drq_conv3x3_fwd_f32", acts[1], w[2], b[2], acts[2], N, 37, 0, s)
+    call("drq_conv3x3_fwd_f32", acts[2], w[3], b[3], feat, N, 35, 1, s)
+
+
+# ----------------------------------------------------------------------------- modules
+class RandomShiftsAug(nn.Module):
+    """Random translation by up to ±pad pixels after replicate padding, as the exact
+    integer shift (the reference's bilinear grid_sample equals it to 3.6e-3 on the 0..255
+    scale).  The draw is the reference's own ``torch.randint`` call, so
+    the same patch injects shifts into either implementation."""
+
+    def __init__(self, pad):
+        super().__init__()
+        self.pad = pad
+
+    def forward(self, x):
+        n, c, h, w = x.size()
+        assert h == w
+        _need_cuda(x, "RandomShiftsAug")
+        shift = torch.randint(0, 2 * self.pad + 1, size=(n, 1, 1, 2), device=x.device, dtype=x.dtype)
+        shift = shift.view(n, 2).to(torch.int32).contiguous()
+        x = x.float().contiguous()
+        out = torch.empty_like(x)
+        call("drq_random_shift_f32", x.data_ptr(), shift.data_ptr(), out.data_ptr(), n, c, h, w, self.pad,
+             _stream())
+        return out
+
+
+def _as_u8_pixels(obs):
+    if obs.dtype == torch.uint8:
+        return obs.contiguous()
+    u8 = obs.to(torch.uint8)
+    if not torch.equal(u8.to(obs.dtype), obs):
+        raise ValueError("Encoder expects integer-valued pixels in [0, 255] (uint8 frames, optionally "
+                         "shifted by RandomShiftsAug); got non-integral values")
+    return u8.contiguous()
+
+
+class Encoder(nn.Module):
+    def __init__(self, obs_shape):
+        super().__init__()
+        assert len(obs_shape) == 3
+        self.repr_dim = 32 * 35 * 35
+        chans = [int(obs_shape[0]), 32, 32, 32]
+        mods = []
+        for i, cin in enumerate(chans):
+            mods += [nn.Conv2d(cin, 32, 3, stride=2 if i == 0 else 1), nn.ReLU()]
+        self.convnet = nn.Sequential(*mods)
+        self.apply(utils.weight_init)
+
+    def conv_ptrs(self):
+        convs = [self.convnet[i] for i in (0, 2, 4, 6)]
+        return [c.weight.data_ptr() for c in convs], [c.bias.data_ptr() for c in convs]
+
+    def forward(self, obs):
+        """obs: [N, C, 84, 84] pixels on the 0..255 scale (uint8, or integer-valued float as
+        produced by RandomShiftsAug).  Returns features [N, 39200]."""
+        _need_cuda(obs, "Encoder")
+        _need_cuda(self.convnet[0].weight, "Encoder parameters")
+        u8 = _as_u8_pixels(obs)
+        n, cin = u8.shape[0], u8.shape[1]
+        acts = [torch.empty(n * 32 * PLANE, device=u8.device) for _ in range(3)]
+        feat = torch.empty(n, self.repr_dim, device=u8.device)
+        w, b = self.conv_ptrs()
+        _encoder_fwd(u8.data_ptr(), 0, w, b, [a.data_ptr() for a in acts], feat.data_ptr(), n, cin)
+        return feat
+
+
+class _Trunk(nn.Sequential):
+    def __init__(self, repr_dim, feature_dim):
+        super().__init__(nn.Linear(repr_dim, feature_dim), nn.LayerNorm(feature_dim), nn.Tanh())
+
+
+def _mlp(n_in, hidden, n_out):
+    return nn.Sequential(nn.Linear(n_in, hidden), nn.ReLU(inplace=True), nn.Linear(hidden, hidden),
+                         nn.ReLU(inplace=True), nn.Linear(hidden, n_out))
+
+
+def _lin_ptrs(seq):
+    out = []
+    for i in (0, 2, 4):
+        out += [seq[i].weight.data_ptr(), seq[i].bias.data_ptr()]
+    return out
+
+
+def _mlp_fwd(seq, x, ldx, B, n_in, hidden, n_out, out, dev):
+    """3-layer ReLU MLP forward with throw-away hidden buffers (module-level API)."""
+    w1, b1, w2, b2, w3, b3 = _lin_ptrs(seq)
+    h1 = torch.empty(B, hidden, device=dev)
+    h2 = torch.empty(B, hidden, device=dev)
+    _linear_fwd(x, ldx, w1, b1, h1.data_ptr(), hidden, B, hidden, n_in, True)
+    _linear_fwd(h1.data_ptr(), hidden, w2, b2, h2.data_ptr(), hidden, B, hidden, hidden, True)
+    _linear_fwd(h2.data_ptr(), hidden, w3, b3, out, n_out, B, n_out, hidden, False)
+    return h1, h2
+
+
+class Actor(nn.Module):
+    def __init__(self, repr_dim, action_shape, feature_dim, hidden_dim):
+        super().__init__()
+        self.trunk = _Trunk(repr_dim, feature_dim)
+        self.policy = _mlp(feature_dim, hidden_dim, action_shape[0])
+        self.apply(utils.weight_init)
+
+    def forward(self, obs, std):
+        _need_cuda(obs, "Actor")
+        B, dev = obs.shape[0], obs.device
+        Fd, H, A = self.trunk[0].out_features, self.policy[0].out_features, self.policy[4].out_features
+        obs = obs.float().contiguous()
+        partial = torch.empty(_splitk_for(B) * B * Fd, device=dev)
+        h = torch.empty(B, Fd, device=dev)
+        t = self.trunk
+        _trunk_fwd(obs.data_ptr(), B, t[0].weight.data_ptr(), t[0].bias.data_ptr(), t[1].weight.data_ptr(),
+                   t[1].bias.data_ptr(), Fd, partial.data_ptr(), h.data_ptr(), Fd)
+        mu_pre = torch.empty(B, A, device=dev)
+        keep = _mlp_fwd(self.policy, h.data_ptr(), Fd, B, Fd, H, A, mu_pre.data_ptr(), dev)
+        mu = torch.empty(B, A, device=dev)
+        call("drq_actor_sample", mu_pre.data_ptr(), None, None, 0.0, mu.data_ptr(), A, None, None, B, A,
+             _stream())
+        del keep
+        return utils.TruncatedNormal(mu, torch.ones_like(mu) * std)
+
+
+class Critic(nn.Module):
+    def __init__(self, repr_dim, action_shape, feature_dim, hidden_dim):
+        super().__init__()
+        self.trunk = _Trunk(repr_dim, feature_dim)
+        self.Q1 = _mlp(feature_dim + action_shape[0], hidden_dim, 1)
+        self.Q2 = _mlp(feature_dim + action_shape[0], hidden_dim, 1)
+        self.apply(utils.weight_init)
+
+    def forward(self, obs, action):
+        _need_cuda(obs, "Critic")
+        B, dev = obs.shape[0], obs.device
+        Fd, H = self.trunk[0].out_features, self.Q1[0].out_features
+        A = self.Q1[0].in_features - Fd
+        obs = obs.float().contiguous()
+        action = action.float().contiguous()
+        partial = torch.empty(_splitk_for(B) * B * Fd, device=dev)
+        x = torch.empty(B, Fd + A, device=dev)
+        t = self.trunk
+        _trunk_fwd(obs.data_ptr(), B, t[0].weight.data_ptr(), t[0].bias.data_ptr(), t[1].weight.data_ptr(),
+                   t[1].bias.data_ptr(), Fd, partial.data_ptr(), x.data_ptr(), Fd + A)
+        call("drq_copy2d_f32", action.data_ptr(), A, x.data_ptr() + F32 * Fd, Fd + A, B, A, _stream())
+        qs = []
+        for head in (self.Q1, self.Q2):
+            q = torch.empty(B, 1, device=dev)
+            keep = _mlp_fwd(head, x.data_ptr(), Fd + A, B, Fd + A, H, 1, q.data_ptr(), dev)
+            del keep
+            qs.append(q)
+        return qs[0], qs[1]
+
+
+# ----------------------------------------------------------------------------- flat arenas
+class _Arena:
+    """Flat fp32 storage for parameters / gradients / Adam moments of
+    [encoder | critic | actor] (each segment padded to 4 floats) and for the target
+    critic.  Module parameters become views, so state_dict()/pickle see ordinary tensors
+    in the reference's layouts while one kernel can update a whole optimiser's range."""
+
+    def __init__(self, encoder, critic, actor, critic_target, device):
+        self.seg = {}
+        off = 0
+        for name, mod in (("encoder", encoder), ("critic", critic), ("actor", actor)):
+            n = sum(p.numel() for p in mod.parameters())
+            n_pad = (n + 3) // 4 * 4
+            self.seg[name] = (off, n, n_pad)
+            off += n_pad
+        self.total = off
+        self.params = torch.zeros(off, device=device)
+        self.grads = torch.zeros(off, device=device)
+        self.exp_avg = torch.zeros(off, device=device)
+        self.exp_avg_sq = torch.zeros(off, device=device)
+        n_t = self.seg["critic"][2]
+        self.target = torch.zeros(n_t, device=device)
+        self.offsets = {}
+        for name, mod in (("encoder", encoder), ("critic", critic), ("actor", actor)):
+            o = self.seg[name][0]
+            self.offsets[name] = self._adopt(mod, self.params, self.grads, o)
+        self._adopt(critic_target, self.target, None, 0)
+
+    @staticmethod
+    def _adopt(mod, flat, flat_grad, off):
+        offs = {}
+        with torch.no_grad():
+            for pname, p in mod.named_parameters():
+                n = p.numel()
+                view = flat[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.requires_grad_(False)
+                if flat_grad is not None:
+                    p.grad = flat_grad[off:off + n].view(p.shape)
+                offs[pname] = off
+                off += n
+        return offs
+
+    def ptr(self, which, net, pname=None):
+        base = getattr(self, which).data_ptr()
+        if pname is None:
+            return base + F32 * self.seg[net][0]
+        return base + F32 * self.offsets[net][pname]
+
+
+class _Workspace:
+    """Static buffers of one update at batch size B (allocated once, graph-capturable)."""
+
+    def __init__(self, B, A, Fd, H, cin, device):
+        z = lambda *s: torch.zeros(*s, device=device)
+        self.B = B
+        NB = 2 * B
+        # inputs
+        self.obs = torch.zeros(NB, cin, 84, 84, dtype=torch.uint8, device=device)   # [obs | next_obs]
+        self.action, self.reward, self.discount = z(B, A), z(B, 1), z(B, 1)
+        self.shift = torch.full((NB, 2), 4, dtype=torch.int32, device=device)       # [obs | next_obs]
+        self.eps_c, self.eps_a = z(B, A), z(B, A)
+        # encoder
+        self.acts = [z(NB * 32 * PLANE) for _ in range(3)]
+        self.feat = z(NB, REPR_DIM)
+        self.dpre = [z(B * 32 * PLANE) for _ in range(4)]    # grads w.r.t. conv1..4 pre-ReLU outputs
+        self.wgrad_ws = z(int(_lib.lib().drq_conv_wgrad_ws_floats(32)))
+        # heads
+        self.partial = z(_splitk_for(B) * B * Fd)
+        self.xT = z(B, Fd + A)          # [h_target(next) | next_action]
+        self.xC = z(B, Fd + A)          # [h_critic(obs) | action]
+        self.xA = z(B, Fd + A)          # [h_critic'(obs) | actor action]
+        self.hA = z(B, Fd)              # actor trunk output
+        self.xhatC, self.rstdC = z(B, Fd), z(B)
+        self.xhatA, self.rstdA = z(B, Fd), z(B)
+        self.p1, self.p2 = z(B, H), z(B, H)             # actor hidden
+        self.mu_pre, self.mu = z(B, A), z(B, A)
+        self.c1, self.c2 = z(2, B, H), z(2, B, H)       # twin-Q hidden (both heads)
+        self.q, self.tq = z(2, B), z(2, B)
+        self.dq = z(2, B)
+        self.dc1, self.dc2 = z(2, B, H), z(2, B, H)
+        self.dx = z(B, Fd + A)
+        self.dz = z(2 * B * Fd)
+        self.dact, self.dmu_pre = z(B, A), z(B, A)
+        self.dp1, self.dp2 = z(B, H), z(B, H)
+        self.dhA = z(B, Fd)
+        self.target_q = z(B)
+        self.metrics = z(8)
+
+
+class _Opt:
+    """Stand-in for the reference's three torch.optim.Adam objects (drqv2.py:148-150):
+    the update itself is drq_adam_ema_step over the flat arena; this object only carries
+    hyper-parameters and the step count for inspection / pickling."""
+
+    def __init__(self, agent, net, lr):
+        self._agent, self.net = agent, net
+        self.defaults = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False)
+
+    def state_dict(self):
+        a, (off, n, _) = self._agent._arena, self._agent._arena.seg[self.net]
+        return dict(step=self._agent._opt_step, exp_avg=a.exp_avg[off:off + n].clone(),
+                    exp_avg_sq=a.exp_avg_sq[off:off + n].clone(), **self.defaults)
+
+    def zero_grad(self, set_to_none=True):
+        off, n, _ = self._agent._arena.seg[self.net]
+        self._agent._arena.grads[off:off + n].zero_()
+
+
+METRIC_KEYS = ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "critic_loss",
+               "actor_loss", "actor_logprob", "actor_ent")
+
+
+class DrQV2Agent:
+    def __init__(self, obs_shape, action_shape, device, lr, feature_dim, hidden_dim, critic_target_tau,
+                 num_expl_steps, update_every_steps, stddev_schedule, stddev_clip, use_tb,
+                 use_cuda_graph=True, seed=None):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"DrQV2Agent(device={device!r}): drqv2_b200 has no CPU path; use a CUDA device")
+        if not torch.cuda.is_available():
+            raise RuntimeError("DrQV2Agent: no CUDA device available (drqv2_b200 has no CPU fallback)")
+        _lib.lib()   # fail loudly if the extension is missing
+        self.device = device
+        self.critic_target_tau = critic_target_tau
+        self.update_every_steps = update_every_steps
+        self.use_tb = use_tb
+        self.num_expl_steps = num_expl_steps
+        self.stddev_schedule = stddev_schedule
+        self.stddev_clip = stddev_clip
+        self.lr = lr
+        self.use_cuda_graph = use_cuda_graph
+        self.obs_shape = tuple(int(v) for v in obs_shape)
+        self.action_dim = int(action_shape[0])
+        self.feature_dim, self.hidden_dim = int(feature_dim), int(hidden_dim)
+
+        # models: built on the host in the reference's order (so a seed reproduces its init)
+        self.encoder = Encoder(self.obs_shape)
+        self.actor = Actor(self.encoder.repr_dim, action_shape, feature_dim, hidden_dim)
+        self.critic = Critic(self.encoder.repr_dim, action_shape, feature_dim, hidden_dim)
+        self.critic_target = Critic(self.encoder.repr_dim, action_shape, feature_dim, hidden_dim)
+        self.critic_target.load_state_dict(self.critic.state_dict())
+        self._to_device(dev)
+
+        self.encoder_opt = _Opt(self, "encoder", lr)
+        self.actor_opt = _Opt(self, "actor", lr)
+        self.critic_opt = _Opt(self, "critic", lr)
+        self.aug = RandomShiftsAug(pad=4)
+        self._opt_step = 0
+        self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        self.train()
+        self.critic_target.train()
+
+    # ------------------------------------------------------------------ plumbing
+    def _to_device(self, dev):
+        self._dev = dev
+        for m in (self.encoder, self.actor, self.critic, self.critic_target):
+            m.to(dev)
+        self._arena = _Arena(self.encoder, self.critic, self.actor, self.critic_target, dev)
+        self._ws = {}
+        self._graphs = {}
+        self._act_ws = {}
+        self._scal_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self._scal_dev = torch.zeros(16, device=dev)        # [0..7] adam scalars, [8] stddev
+        self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._injected = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_ws", "_graphs", "_act_ws"):
+            st[k] = {}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        # re-pin host staging buffers (pinning does not survive pickling)
+        self._scal_host = self._scal_host.clone().pin_memory()
+        self._metrics_host = self._metrics_host.clone().pin_memory()
+        # parameters were pickled as views of the arenas (torch keeps shared storage); make
+        # sure .grad views exist again
+        a = self._arena
+        for name, mod in (("encoder", self.encoder), ("critic", self.critic), ("actor", self.actor)):
+            for pname, p in mod.named_parameters():
+                off = a.offsets[name][pname]
+                p.data = a.params[off:off + p.numel()].view(p.shape)
+                p.grad = a.grads[off:off + p.numel()].view(p.shape)
+        off = 0
+        for pname, p in self.critic_target.named_parameters():
+            p.data = a.target[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    def train(self, training=True):
+        self.training = training
+        self.encoder.train(training)
+        self.actor.train(training)
+        self.critic.train(training)
+
+    def workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = _Workspace(B, self.action_dim, self.feature_dim, self.hidden_dim, self.obs_shape[0], self._dev)
+            self._ws[B] = ws
+        return ws
+
+    def inject_draws(self, shift_obs, shift_next, eps_critic, eps_actor):
+        """Parity mode: use these draws (int [B,2] (x,y) shifts, float [B,A] N(0,1) noise) for
+        the next update instead of the device RNG — the four draws of one reference update
+        in order (drqv2.py:241-242, utils.py:119 twice)."""
+        self._injected = (shift_obs, shift_next, eps_critic, eps_actor)
+
+    def _p(self, net, pname):
+        return self._arena.ptr("params", net, pname)
+
+    def _g(self, net, pname):
+        return self._arena.ptr("grads", net, pname)
+
+    def _t(self, pname):
+        return self._arena.target.data_ptr() + F32 * self._arena.offsets["critic"][pname] - F32 * self._arena.seg["critic"][0]
+
+    # ------------------------------------------------------------------ act
+    def act(self, obs, step, eval_mode):
+        """drqv2.py:164-175: encoder + actor at batch 1, mean in eval mode, else an
+        exploration sample (noise not clipped), uniform before num_expl_steps."""
+        A, Fd, H = self.action_dim, self.feature_dim, self.hidden_dim
+        obs_t = torch.as_tensor(obs)
+        batched = obs_t.dim() == 4
+        if not batched:
+            obs_t = obs_t.unsqueeze(0)
+        n = obs_t.shape[0]
+        w = self._act_ws.get(n)
+        dev = self._dev
+        if w is None:
+            w = dict(obs=torch.zeros(n, *self.obs_shape, dtype=torch.uint8, device=dev),
+                     acts=[torch.zeros(n * 32 * PLANE, device=dev) for _ in range(3)],
+                     feat=torch.zeros(n, REPR_DIM, device=dev),
+                     partial=torch.zeros(_splitk_for(n) * n * Fd, device=dev),
+                     h=torch.zeros(n, Fd, device=dev), p1=torch.zeros(n, H, device=dev),
+                     p2=torch.zeros(n, H, device=dev), mu_pre=torch.zeros(n, A, device=dev),
+                     eps=torch.zeros(n, A, device=dev), out=torch.zeros(n, A, device=dev),
+                     host_in=torch.zeros(n, *self.obs_shape, dtype=torch.uint8).pin_memory(),
+                     host_out=torch.zeros(n, A).pin_memory(), graph={})
+            self._act_ws[n] = w
+        if obs_t.is_cuda:
+            w["obs"].copy_(obs_t, non_blocking=True)
+        else:
+            w["host_in"].copy_(obs_t)
+            w["obs"].copy_(w["host_in"], non_blocking=True)
+        stddev = utils.schedule(self.stddev_schedule, step)
+        self._scal_host[8] = stddev
+        self._scal_dev[8:9].copy_(self._scal_host[8:9], non_blocking=True)
+        sample = not eval_mode
+        key = bool(sample)
+        g = w["graph"].get(key)
+        if g is None:
+            self._act_body(w, n, sample)          # warm-up (also opts kernels in to big smem)
+            if self.use_cuda_graph:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._act_body(w, n, sample)
+                w["graph"][key] = g
+                g.replay()
+        else:
+            g.replay()
+        w["host_out"].copy_(w["out"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        action = w["host_out"].numpy().copy()
+        if sample and step < self.num_expl_steps:
+            action = np.random.uniform(-1.0, 1.0, size=action.shape).astype(np.float32)
+        return action if batched else action[0]
+
+    def _act_body(self, w, n, sample):
+        A, Fd, H = self.action_dim, self.feature_dim, self.hidden_dim
+        if sample:   # exploration noise draw (utils.py:119)
+            call("drq_rng_normal_f32", self._seed, self._counter.data_ptr(), w["eps"].data_ptr(), n * A, _stream())
+            call("drq_counter_advance", self._counter.data_ptr(), _stream())
+        ew = [self._p("encoder", f"convnet.{i}.weight") for i in (0, 2, 4, 6)]
+        eb = [self._p("encoder", f"convnet.{i}.bias") for i in (0, 2, 4, 6)]
+        _encoder_fwd(w["obs"].data_ptr(), 0, ew, eb, [a.data_ptr() for a in w["acts"]], w["feat"].data_ptr(),
+                     n, self.obs_shape[0])
+        pa = lambda k: self._p("actor", k)
+        _trunk_fwd(w["feat"].data_ptr(), n, pa("trunk.0.weight"), pa("trunk.0.bias"), pa("trunk.1.weight"),
+                   pa("trunk.1.bias"), Fd, w["partial"].data_ptr(), w["h"].data_ptr(), Fd)
+        _linear_fwd(w["h"].data_ptr(), Fd, pa("policy.0.weight"), pa("policy.0.bias"), w["p1"].data_ptr(), H, n, H, Fd, True)
+        _linear_fwd(w["p1"].data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), w["p2"].data_ptr(), H, n, H, H, True)
+        _linear_fwd(w["p2"].data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), w["mu_pre"].data_ptr(), A, n, A, H, False)
+        call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
+             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, n, A, _stream())
+
+    # ------------------------------------------------------------------ update
+    def update(self, replay_iter, step):
+        """drqv2.py:230-262.  Returns {} (and does not advance the iterator) when
+        step % update_every_steps != 0."""
+        metrics = dict()
+        if step % self.update_every_steps != 0:
+            return metrics
+        if hasattr(replay_iter, "next_into"):
+            # GPU-resident ring: sample + n-step gather straight into the static buffers
+            B = replay_iter.batch_size
+            ws = self.workspace(B)
+            fetch = lambda: replay_iter.next_into(ws.obs[:B], ws.action, ws.reward, ws.discount, ws.obs[B:])
+        else:
+            batch = next(replay_iter)
+            obs, action, reward, discount, next_obs = batch
+            B = obs.shape[0]
+            ws = self.workspace(B)
+            fetch = None
+            self._load_batch(ws, obs, action, reward, discount, next_obs)
+        self._host_scalars(step)
+        inj = self._injected
+        if inj is not None:
+            self._injected = None
+            ws.shift[:B].copy_(torch.as_tensor(inj[0]).to(torch.int32).view(B, 2))
+            ws.shift[B:].copy_(torch.as_tensor(inj[1]).to(torch.int32).view(B, 2))
+            ws.eps_c.copy_(torch.as_tensor(inj[2]).view(B, -1))
+            ws.eps_a.copy_(torch.as_tensor(inj[3]).view(B, -1))
+        key = (B, fetch is not None, inj is None)
+        state = self._graphs.get(key) if self.use_cuda_graph else None
+        if not self.use_cuda_graph:
+            self._update_body(ws, fetch, draw=inj is None)
+        elif state is None:
+            # first call at this shape runs eagerly: it is the warm-up (lazy module loading,
+            # shared-memory opt-in) that must not happen inside a capture
+            self._update_body(ws, fetch, draw=inj is None)
+            self._graphs[key] = "warm"
+        else:
+            if state == "warm":
+                torch.cuda.synchronize()
+                state = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(state):
+                    self._update_body(ws, fetch, draw=inj is None)
+                self._graphs[key] = state
+            state.replay()
+        self._opt_step += 1
+        if self.use_tb:
+            self._metrics_host.copy_(ws.metrics, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            vals = self._metrics_host.tolist()
+            metrics = dict(zip(METRIC_KEYS, vals))
+        return metrics
+
+    def _load_batch(self, ws, obs, action, reward, discount, next_obs):
+        B = ws.B
+        for dst, src in ((ws.obs[:B], obs), (ws.obs[B:], next_obs), (ws.action, action),
+                         (ws.reward, reward), (ws.discount, discount)):
+            src = torch.as_tensor(src)
+            if src.is_cuda and src.data_ptr() == dst.data_ptr():
+                continue
+            dst.copy_(src.view(dst.shape), non_blocking=True)
+
+    def _host_scalars(self, step):
+        stddev = utils.schedule(self.stddev_schedule, step)
+        sc = utils.adam_scalars(self.lr, self._opt_step + 1)
+        self._scal_host[:8] = torch.from_numpy(sc)
+        self._scal_host[8] = stddev
+        self._stddev = stddev
+
+    def _update_body(self, ws, fetch=None, draw=True):
+        """Everything of one update that runs on the device, in stream order; no host sync."""
+        B = ws.B
+        s = _stream()
+        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        if fetch is not None:
+            fetch()
+        if draw:
+            call("drq_rng_update_draws", self._seed, self._counter.data_ptr(), self.aug.pad,
+                 ws.shift[:B].data_ptr(), ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
+                 B, self.action_dim, s)
+            call("drq_counter_advance", self._counter.data_ptr(), s)
+        self._encode(ws)
+        self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=True)
+        self._actor_pass(ws, ws.feat[:B])
+
+    def _encode(self, ws):
+        B = ws.B
+        ew = [self._p("encoder", f"convnet.{i}.weight") for i in (0, 2, 4, 6)]
+        eb = [self._p("encoder", f"convnet.{i}.bias") for i in (0, 2, 4, 6)]
+        _encoder_fwd(ws.obs.data_ptr(), ws.shift.data_ptr(), ew, eb, [a.data_ptr() for a in ws.acts],
+                     ws.feat.data_ptr(), 2 * B, self.obs_shape[0], self.aug.pad)
+
+    def _q_strides(self):
+        Fd, A, H = self.feature_dim, self.action_dim, self.hidden_dim
+        return H * (Fd + A) + H + H * H + H + H + 1   # floats between Q1.* and Q2.* tensors
+
+    def _twin_q_fwd(self, pfn, x, c1, c2, q, B):
+        """Both Q heads in one batched launch per layer (drqv2.py:103-111,118-119)."""
+        Fd, A, H = self.feature_dim, self.action_dim, self.hidden_dim
+        qs = self._q_strides()
+        _linear_fwd(x, Fd + A, pfn("Q1.0.weight"), pfn("Q1.0.bias"), c1, H, B, H, Fd + A, True, batch=2,
+                    bs=(0, qs, B * H, qs, 0))
+        _linear_fwd(c1, H, pfn("Q1.2.weight"), pfn("Q1.2.bias"), c2, H, B, H, H, True, batch=2,
+                    bs=(B * H, qs, B * H, qs, 0))
+        _linear_fwd(c2, H, pfn("Q1.4.weight"), pfn("Q1.4.bias"), q, 1, B, 1, H, False, batch=2,
+                    bs=(B * H, qs, B, qs, 0))
+
+    def _critic_pass(self, ws, feat, feat_next, encoder_grad):
+        """update_critic (drqv2.py:177-204) + critic/encoder Adam, no host sync."""
+        B, A, Fd, H = ws.B, self.action_dim, self.feature_dim, self.hidden_dim
+        s = _stream()
+        pc = lambda k: self._p("critic", k)
+        gc = lambda k: self._g("critic", k)
+        pa = lambda k: self._p("actor", k)
+        std_ptr = self._scal_dev.data_ptr() + F32 * 8
+        qs = self._q_strides()
+        featp, featn = feat.data_ptr(), feat_next.data_ptr()
+        # --- target: online actor on next features -> clipped sample (drqv2.py:181-183)
+        _trunk_fwd(featn, B, pa("trunk.0.weight"), pa("trunk.0.bias"), pa("trunk.1.weight"), pa("trunk.1.bias"),
+                   Fd, ws.partial.data_ptr(), ws.hA.data_ptr(), Fd)
+        _linear_fwd(ws.hA.data_ptr(), Fd, pa("policy.0.weight"), pa("policy.0.bias"), ws.p1.data_ptr(), H, B, H, Fd, True)
+        _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
+        _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
+        call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_c.data_ptr(), std_ptr, float(self.stddev_clip),
+             ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, B, A, s)
+        # --- target critic on (next features, next action) (drqv2.py:184)
+        _trunk_fwd(featn, B, self._t("trunk.0.weight"), self._t("trunk.0.bias"), self._t("trunk.1.weight"),
+                   self._t("trunk.1.bias"), Fd, ws.partial.data_ptr(), ws.xT.data_ptr(), Fd + A)
+        self._twin_q_fwd(self._t, ws.xT.data_ptr(), ws.c1.data_ptr(), ws.c2.data_ptr(), ws.tq.data_ptr(), B)
+        # --- online critic on (features, action) (drqv2.py:188)
+        _trunk_fwd(featp, B, pc("trunk.0.weight"), pc("trunk.0.bias"), pc("trunk.1.weight"), pc("trunk.1.bias"),
+                   Fd, ws.partial.data_ptr(), ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(), ws.rstdC.data_ptr())
+        call("drq_copy2d_f32", ws.action.data_ptr(), A, ws.xC.data_ptr() + F32 * Fd, Fd + A, B, A, s)
+        self._twin_q_fwd(pc, ws.xC.data_ptr(), ws.c1.data_ptr(), ws.c2.data_ptr(), ws.q.data_ptr(), B)
+        # --- TD target, loss, dL/dq (drqv2.py:185-189)
+        q1, q2 = ws.q.data_ptr(), ws.q.data_ptr() + F32 * B
+        call("drq_critic_loss", q1, q2, ws.tq.data_ptr(), ws.tq.data_ptr() + F32 * B, ws.reward.data_ptr(),
+             ws.discount.data_ptr(), ws.dq.data_ptr(), ws.dq.data_ptr() + F32 * B, ws.target_q.data_ptr(),
+             ws.metrics.data_ptr(), B, s)
+        # --- backward through the twin Q heads (both heads per launch)
+        BH = B * H
+        c1, c2, dc1, dc2, dq = (t.data_ptr() for t in (ws.c1, ws.c2, ws.dc1, ws.dc2, ws.dq))
+        _linear_wgrad(dq, 1, c2, H, gc("Q1.4.weight"), B, 1, H, batch=2, bs=(B, BH, qs, 0, 0))
+        _colsum(dq, 1, gc("Q1.4.bias"), B, 1, batch=2, bs_x=B, bs_out=qs)
+        _linear_dgrad(dq, 1, pc("Q1.4.weight"), dc2, H, B, 1, H, mask=c2, ldmask=H, batch=2, bs=(B, qs, BH, 0, BH))
+        _linear_wgrad(dc2, H, c1, H, gc("Q1.2.weight"), B, H, H, batch=2, bs=(BH, BH, qs, 0, 0))
+        _colsum(dc2, H, gc("Q1.2.bias"), B, H, batch=2, bs_x=BH, bs_out=qs)
+        _linear_dgrad(dc2, H, pc("Q1.2.weight"), dc1, H, B, H, H, mask=c1, ldmask=H, batch=2, bs=(BH, qs, BH, 0, BH))
+        _linear_wgrad(dc1, H, ws.xC.data_ptr(), Fd + A, gc("Q1.0.weight"), B, H, Fd + A, batch=2, bs=(BH, 0, qs, 0, 0))
+        _colsum(dc1, H, gc("Q1.0.bias"), B, H, batch=2, bs_x=BH, bs_out=qs)
+        # d[h] = dc1[Q1] @ W1[Q1][:, :F] + dc1[Q2] @ W1[Q2][:, :F]
+        _linear_dgrad(dc1, H, pc("Q1.0.weight"), ws.dx.data_ptr(), Fd + A, B, H, Fd + A, n_cols=Fd)
+        _linear_dgrad(dc1 + F32 * BH, H, pc("Q2.0.weight"), ws.dx.data_ptr(), Fd + A, B, H, Fd + A, n_cols=Fd, acc=1)
+        # --- trunk backward: tanh, LayerNorm, Linear
+        call("drq_ln_tanh_bwd", ws.dx.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
+             ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), gc("trunk.1.weight"),
+             gc("trunk.1.bias"), B, Fd, s)
+        _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, gc("trunk.0.weight"), B, Fd, REPR_DIM)
+        _colsum(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd)
+        if encoder_grad:
+            self._encoder_bwd(ws, featp)
+        # --- critic_opt.step(); encoder_opt.step() (drqv2.py:201-202): [encoder|critic] is one range
+        a = self._arena
+        if encoder_grad:
+            off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
+        else:
+            off, n = a.seg["critic"][0], a.seg["critic"][2]
+        call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+             a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n,
+             self._scal_dev.data_ptr(), s)
+
+    def _encoder_bwd(self, ws, featp):
+        """Backward of the 4-conv encoder on the obs half of the batch (drqv2.py:200)."""
+        B, Fd = ws.B, self.feature_dim
+        s = _stream()
+        pe = lambda k: self._p("encoder", k)
+        ge = lambda k: self._g("encoder", k)
+        d = [t.data_ptr() for t in ws.dpre]
+        acts = [t.data_ptr() for t in ws.acts]
+        wsp = ws.wgrad_ws.data_ptr()
+        # d(features) = dz @ W_trunk, masked by ReLU and scattered into the wide plane of conv4's output
+        _gemm(ws.dz.data_ptr(), Fd, 1, self._p("critic", "trunk.0.weight"), REPR_DIM, 1, d[3], 32 * PLANE,
+              B, REPR_DIM, Fd, mask=featp, ldmask=REPR_DIM, epi=EPI_MASK_WIDE)
+        for layer, hout in ((3, 35), (2, 37), (1, 39)):
+            k = 2 * layer
+            call("drq_conv3x3_wgrad_f32", acts[layer - 1], d[layer], wsp, ge(f"convnet.{k}.weight"),
+                 ge(f"convnet.{k}.bias"), B, hout, s)
+            call("drq_conv3x3_dgrad_f32", d[layer], pe(f"convnet.{k}.weight"), acts[layer - 1], d[layer - 1],
+                 B, hout, s)
+        call("drq_conv1_wgrad_f32", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], wsp, ge("convnet.0.weight"),
+             ge("convnet.0.bias"), B, self.obs_shape[0], self.aug.pad, s)
+
+    def _actor_pass(self, ws, feat):
+        """update_actor (drqv2.py:206-228) + actor Adam + soft target update (drqv2.py:259-260)."""
+        B, A, Fd, H = ws.B, self.action_dim, self.feature_dim, self.hidden_dim
+        s = _stream()
+        pc = lambda k: self._p("critic", k)
+        pa = lambda k: self._p("actor", k)
+        ga = lambda k: self._g("actor", k)
+        std_ptr = self._scal_dev.data_ptr() + F32 * 8
+        qs = self._q_strides()
+        featp = feat.data_ptr()
+        BH = B * H
+        # actor forward on detached features, sample with clipped noise (drqv2.py:209-211)
+        _trunk_fwd(featp, B, pa("trunk.0.weight"), pa("trunk.0.bias"), pa("trunk.1.weight"), pa("trunk.1.bias"),
+                   Fd, ws.partial.data_ptr(), ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr())
+        _linear_fwd(ws.hA.data_ptr(), Fd, pa("policy.0.weight"), pa("policy.0.bias"), ws.p1.data_ptr(), H, B, H, Fd, True)
+        _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
+        _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
+        call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_a.data_ptr(), std_ptr, float(self.stddev_clip),
+             ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6, B, A, s)
+        # the just-updated critic on (features, action) (drqv2.py:213-216)
+        _trunk_fwd(featp, B, pc("trunk.0.weight"), pc("trunk.0.bias"), pc("trunk.1.weight"), pc("trunk.1.bias"),
+                   Fd, ws.partial.data_ptr(), ws.xA.data_ptr(), Fd + A)
+        self._twin_q_fwd(pc, ws.xA.data_ptr(), ws.c1.data_ptr(), ws.c2.data_ptr(), ws.q.data_ptr(), B)
+        call("drq_actor_loss", ws.q.data_ptr(), ws.q.data_ptr() + F32 * B, ws.dq.data_ptr(),
+             ws.dq.data_ptr() + F32 * B, ws.metrics.data_ptr() + F32 * 5, B, s)
+        # backward: Q heads data-gradient only (critic weight grads are discarded by the reference)
+        c1, c2, dc1, dc2, dq = (t.data_ptr() for t in (ws.c1, ws.c2, ws.dc1, ws.dc2, ws.dq))
+        _linear_dgrad(dq, 1, pc("Q1.4.weight"), dc2, H, B, 1, H, mask=c2, ldmask=H, batch=2, bs=(B, qs, BH, 0, BH))
+        _linear_dgrad(dc2, H, pc("Q1.2.weight"), dc1, H, B, H, H, mask=c1, ldmask=H, batch=2, bs=(BH, qs, BH, 0, BH))
+        _linear_dgrad(dc1, H, pc("Q1.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A)
+        _linear_dgrad(dc1 + F32 * BH, H, pc("Q2.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A, acc=1)
+        call("drq_actor_sample_bwd", ws.dact.data_ptr(), A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(), B, A, s)
+        # actor MLP backward
+        dmu, p1, p2, dp1, dp2 = (t.data_ptr() for t in (ws.dmu_pre, ws.p1, ws.p2, ws.dp1, ws.dp2))
+        _linear_wgrad(dmu, A, p2, H, ga("policy.4.weight"), B, A, H)
+        _colsum(dmu, A, ga("policy.4.bias"), B, A)
+        _linear_dgrad(dmu, A, pa("policy.4.weight"), dp2, H, B, A, H, mask=p2, ldmask=H)
+        _linear_wgrad(dp2, H, p1, H, ga("policy.2.weight"), B, H, H)
+        _colsum(dp2, H, ga("policy.2.bias"), B, H)
+        _linear_dgrad(dp2, H, pa("policy.2.weight"), dp1, H, B, H, H, mask=p1, ldmask=H)
+        _linear_wgrad(dp1, H, ws.hA.data_ptr(), Fd, ga("policy.0.weight"), B, H, Fd)
+        _colsum(dp1, H, ga("policy.0.bias"), B, H)
+        _linear_dgrad(dp1, H, pa("policy.0.weight"), ws.dhA.data_ptr(), Fd, B, H, Fd)
+        call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(),
+             ws.rstdA.data_ptr(), pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"),
+             ga("trunk.1.bias"), B, Fd, s)
+        _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, ga("trunk.0.weight"), B, Fd, REPR_DIM)
+        _colsum(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd)
+        # actor_opt.step() fused with the soft target update of the (already stepped) critic
+        a = self._arena
+        off, n = a.seg["actor"][0], a.seg["actor"][2]
+        coff, cn = a.seg["critic"][0], a.seg["critic"][2]
+        tau = float(self.critic_target_tau)
+        call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+             a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, self._scal_dev.data_ptr(),
+             a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, tau, float(1 - tau), s)
+
+    # ------------------------------------------------------------------ public stage API
+    def _stage_inputs(self, ws, **named):
+        for k, v in named.items():
+            dst = getattr(ws, k)
+            v = torch.as_tensor(v, device=self._dev)
+            if v.data_ptr() != dst.data_ptr():
+                dst.copy_(v.view(dst.shape))
+
+    def update_critic(self, obs, action, reward, discount, next_obs, step):
+        """drqv2.py:177-204 on encoded features [B, 39200].  When `obs` is the feature
+        buffer produced by this agent's own encode (as in update()), the encoder is
+        updated too, as autograd would; detached features leave it untouched."""
+        B = obs.shape[0]
+        ws = self.workspace(B)
+        own = obs.data_ptr() == ws.feat.data_ptr()
+        if not own:
+            ws.feat[:B].copy_(obs)
+        if next_obs.data_ptr() != ws.feat[B:].data_ptr():
+            ws.feat[B:].copy_(next_obs)
+        self._stage_inputs(ws, action=action, reward=reward, discount=discount)
+        self._host_scalars(step)
+        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=own)
+        metrics = dict()
+        if self.use_tb:
+            m = ws.metrics.tolist()
+            metrics = dict(critic_target_q=m[1], critic_q1=m[2], critic_q2=m[3], critic_loss=m[4])
+        return metrics
+
+    def update_actor(self, obs, step):
+        """drqv2.py:206-228 on (detached) features; also performs the actor Adam step.
+        The soft target update that the fused kernel applies belongs to update(); callers of
+        this stage API who do not want it should snapshot the target first."""
+        B = obs.shape[0]
+        ws = self.workspace(B)
+        if obs.data_ptr() != ws.feat.data_ptr():
+            ws.feat[:B].copy_(obs)
+        self._host_scalars(step)
+        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        self._actor_pass(ws, ws.feat[:B])
+        metrics = dict()
+        if self.use_tb:
+            m = ws.metrics.tolist()
+            metrics = dict(actor_loss=m[5], actor_logprob=m[6], actor_ent=m[7])
+        return metrics

@@ -88,9 +88,11 @@ int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const floa
 
 /* Device-side sampler: episode ~ U{0..E-1} then idx ~ U{1..len-nstep+1}
  * (replay_buffer.py:96-98,150).  ep_table is int32 [E][2] = (start slot, len)
- * with len = transitions in the episode (rows-1).  Philox4x32-10 keyed by
- * (seed, *counter); the kernel does not advance the counter. */
-int drq_ring_sample(const int32_t* ep_table, int E, int nstep, uint64_t seed,
+ * with len = transitions in the episode (rows-1); E = *n_episodes is read on
+ * the device so that a captured graph follows the ring as it fills.
+ * Philox4x32-10 keyed by (seed, *counter); the kernel does not advance the
+ * counter. */
+int drq_ring_sample(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed,
                     const uint64_t* counter, int32_t* ep_start_out, int32_t* idx_out, int B,
                     void* stream);
 
@@ -103,6 +105,8 @@ int drq_ring_sample(const int32_t* ep_table, int E, int nstep, uint64_t seed,
 int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_t* shift_obs,
                          int32_t* shift_next, float* eps_critic, float* eps_actor, int B, int A,
                          void* stream);
+/* out[0..n) ~ N(0,1): the exploration noise of act() (drqv2.py:172, utils.py:119). */
+int drq_rng_normal_f32(uint64_t seed, const uint64_t* counter, float* out, int n, void* stream);
 int drq_counter_advance(uint64_t* counter, void* stream);
 
 /* ------------------------------------------------------------------ augmentation */
@@ -220,6 +224,10 @@ int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const fl
  * metrics [1]: actor_loss. */
 int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, float* metrics,
                    int B, void* stream);
+
+/* dst[r*ld_dst + c] = src[r*ld_src + c]  (the `torch.cat([h, action])` of drqv2.py:117) */
+int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
+                   void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 
