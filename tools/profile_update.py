@@ -1,0 +1,26 @@
+"""Short driver for ncu: a few eager (non-graph) updates of the bench workload so that each
+kernel launch appears individually.  usage: python tools/profile_update.py [updates] [mode]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from drqv2_b200 import DrQV2Agent, make_replay_loader  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+mode = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+B, A, Fd, H = 256, 6, 50, 1024
+torch.manual_seed(0)
+np.random.seed(7)
+kw = dict(mode=mode) if mode != "fp32" else {}
+agent = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, bench.SCHED, 0.3, False,
+                   use_cuda_graph=False, seed=0, **kw)
+bench.fill_ring("/prof/ring", A, 16, 501, torch.device("cuda"))
+it = iter(make_replay_loader("/prof/ring", 16 * 501, B, 0, False, 3, 0.99))
+for i in range(n):
+    agent.update(it, 2 * i)
+torch.cuda.synchronize()
+print("done", n, "updates")
