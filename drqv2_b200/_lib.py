@@ -31,6 +31,9 @@ SIGNATURES = {
     "drq_conv3x3_fwd_f32": [P, P, P, P, I, I, I, P],
     "drq_conv3x3_dgrad_f32": [P, P, P, P, I, I, P],
     "drq_conv3x3_wgrad_f32": [P, P, P, P, P, I, I, P],
+    "drq_pack_conv_w_bf16": [P, P, P, P],
+    "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, P],
+    "drq_conv3x3_dgrad_bf16": [P, P, P, I, P, I, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
     "drq_splitk_reduce": [P, I, L, P, L, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
@@ -51,10 +54,12 @@ SPECIAL = {
     "drq_last_error": (C.c_char_p, []),
     "drq_device_sm_count": (I, []),
     "drq_conv_wgrad_ws_floats": (L, [I]),
+    "drq_wb_elems": (L, [I]),
 }
 
 EPI_NONE, EPI_RELU, EPI_MASK, EPI_MASK_WIDE = 0, 1, 2, 3
 IMG, PW, PLANE, CONV_CH, REPR_DIM = 84, 41, 1696, 32, 39200
+PLB, GUARD, WB_SLACK = 1776, 88, 128
 
 
 class DrqError(RuntimeError):

@@ -1,0 +1,266 @@
+// bf16 tensor-core encoder kernels (tcgen05 + TMEM + bulk-async loads), sm_100a only.
+// Reference ops: the 3x3 stride-1 convolutions of Encoder (drqv2.py:56-59) forward, and
+// their data gradients.
+//
+// Layout "WB" (wide, blocked, bf16): [4 channel-blocks][N images * kPLB pixel rows + slack][8 ch].
+// Image n's wide position p (row stride 41, see encoder_f32.cu) is pixel row n*kPLB + kGuard + p;
+// the kGuard leading rows of every image stay zero in gradient buffers so that dgrad's
+// negative tap offsets read zeros.  One pixel row of one block is 16 bytes = one K unit of a
+// K-major (no-swizzle) UMMA operand, so a [128 + 84]-row window staged once in shared memory
+// serves all nine taps: tap (ky,kx) is the same descriptor advanced by (ky*41+kx)*16 bytes.
+//
+//   out[p][:] = sum_tap  A_tap[128 x 32] * W_tap[32 x 32]      (18 UMMAs of M128 N32 K16 per tile)
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = UMMA issuer, warps 2..5 =
+// epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> coalesced 16-byte stores).
+#include "tc_common.cuh"
+
+namespace drq {
+
+constexpr int kPLB = DRQ_PLB;        // pixel rows per image in WB buffers
+constexpr int kGuard = DRQ_GUARD;    // zero rows in front of every image
+constexpr int kSlack = DRQ_WB_SLACK; // rows after the last image of each block
+constexpr int kTM = 128;             // output positions per tile
+constexpr int kHaloTC = 2 * kPW + 2; // 84
+constexpr int kWinRows = kTM + kHaloTC;      // 212 rows loaded per block
+constexpr int kStageRows = 216;              // smem rows per block (8-row aligned)
+constexpr int kStageBytes = 4 * kStageRows * 16;
+constexpr int kStagesTC = 4;
+constexpr int kAccStages = 4;
+constexpr int kWBytes = 36 * 32 * 16;        // 9 taps x 4 K units x 32 n x 16 B
+constexpr int kThreadsTC = 192;
+
+using namespace tc;
+
+struct ConvTcArgs {
+    const __nv_bfloat16* in; long long cs_in;       // chunk stride in pixel rows
+    const __nv_bfloat16* w;                         // packed [36][32][8]
+    const float* bias;                              // fwd
+    const __nv_bfloat16* mask; long long cs_mask;   // dgrad: input activation (WB)
+    __nv_bfloat16* out; long long cs_out;
+    int n_images, ntiles, n_pos, w_valid, nhwc_out;
+};
+
+template <bool DGRAD>
+__global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + kWBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + kStagesTC * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStagesTC;
+    uint64_t* tfull = bars + 2 * kStagesTC;
+    uint64_t* tempty = bars + 2 * kStagesTC + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesTC + 2 * kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = a.n_images * a.ntiles;
+
+    // packed weights -> smem (same byte layout)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.w);
+        uint4* dst = reinterpret_cast<uint4*>(w_s);
+        for (int i = threadIdx.x; i < kWBytes / 16; i += kThreadsTC) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStagesTC; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kAccStages * 32);
+        tmem_relinquish();
+    }
+    fence_proxy_async();      // generic-proxy smem writes (weights) -> visible to the async proxy (UMMA)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+                mbar_wait(empty + stage, phase ^ 1);
+                mbar_arrive_expect_tx(full + stage, 4 * kWinRows * 16);
+                const long long row0 = (long long)n * kPLB + kGuard + p0 - (DGRAD ? kHaloTC : 0);
+                uint8_t* dst = a_s + stage * kStageBytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    bulk_g2s(dst + c * kStageRows * 16, a.in + (c * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
+                if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ UMMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t w_addr = smem_u32(w_s);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(tempty + acc, acc_phase ^ 1);
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(a_s + stage * kStageBytes);
+                const uint32_t d_tmem = tmem_base + acc * 32;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int off = (tap / 3) * kPW + (tap % 3);
+                    const int o = DGRAD ? kHaloTC - off : off;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t da = make_smem_desc(a_addr + o * 16 + h * 2 * kStageRows * 16, kStageRows * 16, 128);
+                        const uint64_t db = make_smem_desc(w_addr + (tap * 4 + h * 2) * 512, 512, 128);
+                        umma_bf16(d_tmem, da, db, idesc, (tap | h) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty + stage);    // smem stage reusable once these UMMAs retire
+                umma_commit(tfull + acc);      // accumulator ready for the epilogue
+            }
+            __syncwarp();
+            if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+            mbar_wait(tfull + acc, acc_phase);
+            tc_fence_after();
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+
+            const int p = p0 + q * 32 + lane;
+            if (p >= a.n_pos) continue;
+            const int y = p / kPW, x = p - y * kPW;
+            const long long row = (long long)n * kPLB + kGuard + p;
+            uint32_t packed[16];
+            if (!DGRAD) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float lo = fmaxf(v[2 * i] + __ldg(a.bias + 2 * i), 0.f);
+                    const float hi = fmaxf(v[2 * i + 1] + __ldg(a.bias + 2 * i + 1), 0.f);
+                    packed[i] = pack_bf16x2(lo, hi);
+                }
+                if (a.nhwc_out) {
+                    if (x < a.w_valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.out + (((long long)n * a.w_valid + y) * a.w_valid + x) * 32);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                    }
+                    continue;
+                }
+            } else {
+                const bool col_ok = x < a.w_valid;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask + (c * a.cs_mask + row) * 8));
+                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float lo = (col_ok && bf16_lo(mw[j]) > 0.f) ? v[8 * c + 2 * j] : 0.f;
+                        const float hi = (col_ok && bf16_hi(mw[j]) > 0.f) ? v[8 * c + 2 * j + 1] : 0.f;
+                        packed[4 * c + j] = pack_bf16x2(lo, hi);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(a.out + (c * a.cs_out + row) * 8) =
+                    make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kAccStages * 32);
+}
+
+// fp32 master conv weights [co][ci][3][3] -> bf16 UMMA B operands [tap*4 + k/8][n][k%8]:
+//   fwd  : n = co, k = ci   (out = in * W)
+//   dgrad: n = ci, k = co   (din = dout * W^T with flipped offsets)
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_fwd,
+                                   __nv_bfloat16* __restrict__ w_dgrad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * 32 * 9) return;
+    const int co = i / 288, ci = (i / 9) % 32, tap = i % 9;
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    w_fwd[((tap * 4 + ci / 8) * 32 + co) * 8 + (ci & 7)] = v;
+    w_dgrad[((tap * 4 + co / 8) * 32 + ci) * 8 + (co & 7)] = v;
+}
+
+constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16;
+
+static int conv_tc_grid(int total_tiles) {
+    const int sms = 148;
+    return total_tiles < sms ? total_tiles : sms;
+}
+
+}  // namespace drq
+
+using namespace drq;
+
+extern "C" {
+
+int64_t drq_wb_elems(int n_images) { return 4ll * ((long long)n_images * kPLB + kSlack) * 8; }
+
+int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream) {
+    DRQ_REQUIRE(w && w_fwd && w_dgrad, "pack_conv_w: null pointer");
+    pack_conv_w_kernel<<<(9216 + 255) / 256, 256, 0, as_stream(stream)>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
+    return check_launch("pack_conv_w_kernel");
+}
+
+int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out, int N,
+                         int hout, int nhwc_out, void* stream) {
+    DRQ_REQUIRE(in && w_fwd && bias && out, "conv3x3_fwd_bf16: null pointer");
+    DRQ_REQUIRE(N > 0 && hout > 0 && hout <= kPW - 2, "conv3x3_fwd_bf16: bad dims");
+    if (int rc = ensure_smem((const void*)conv3x3_tc_kernel<false>, kConvTcSmem, "conv3x3_fwd_bf16")) return rc;
+    ConvTcArgs a{};
+    a.in = reinterpret_cast<const __nv_bfloat16*>(in);
+    a.cs_in = (long long)N * kPLB + kSlack;
+    a.w = reinterpret_cast<const __nv_bfloat16*>(w_fwd);
+    a.bias = bias;
+    a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a.cs_out = a.cs_in;
+    a.n_images = N;
+    a.n_pos = hout * kPW;
+    a.ntiles = (a.n_pos + kTM - 1) / kTM;
+    a.w_valid = hout;
+    a.nhwc_out = nhwc_out;
+    conv3x3_tc_kernel<false><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
+    return check_launch("conv3x3_tc_kernel<fwd>");
+}
+
+int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const uint16_t* act_in, int n_act,
+                           uint16_t* din, int N, int hout, void* stream) {
+    DRQ_REQUIRE(dout && w_dgrad && act_in && din, "conv3x3_dgrad_bf16: null pointer");
+    DRQ_REQUIRE(N > 0 && n_act >= N && hout > 0 && hout <= kPW - 2, "conv3x3_dgrad_bf16: bad dims");
+    if (int rc = ensure_smem((const void*)conv3x3_tc_kernel<true>, kConvTcSmem, "conv3x3_dgrad_bf16")) return rc;
+    ConvTcArgs a{};
+    a.in = reinterpret_cast<const __nv_bfloat16*>(dout);
+    a.cs_in = (long long)N * kPLB + kSlack;
+    a.w = reinterpret_cast<const __nv_bfloat16*>(w_dgrad);
+    a.mask = reinterpret_cast<const __nv_bfloat16*>(act_in);
+    a.cs_mask = (long long)n_act * kPLB + kSlack;
+    a.out = reinterpret_cast<__nv_bfloat16*>(din);
+    a.cs_out = a.cs_in;
+    a.n_images = N;
+    const int hin = hout + 2;
+    a.n_pos = hin * kPW;
+    a.ntiles = (a.n_pos + kTM - 1) / kTM;
+    a.w_valid = hin;
+    a.nhwc_out = 0;
+    conv3x3_tc_kernel<true><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
+    return check_launch("conv3x3_tc_kernel<dgrad>");
+}
+
+}  // extern "C"

@@ -53,6 +53,12 @@ extern "C" {
 #define DRQ_CONV_CH 32      /* drqv2.py:55 */
 #define DRQ_REPR_DIM 39200  /* drqv2.py:53 32*35*35 */
 
+/* bf16 tensor-core mode: "WB" activation layout [4 channel-blocks][N*DRQ_PLB + DRQ_WB_SLACK pixel rows][8 ch]
+ * (bf16); image n's wide position p is pixel row n*DRQ_PLB + DRQ_GUARD + p. */
+#define DRQ_PLB 1776
+#define DRQ_GUARD 88
+#define DRQ_WB_SLACK 128
+
 /* GEMM epilogues (drq_gemm_f32) */
 #define DRQ_EPI_NONE 0       /* C = acc (+bias) */
 #define DRQ_EPI_RELU 1       /* C = relu(acc + bias)            nn.ReLU in drqv2.py:77-81,103-111 */
@@ -155,6 +161,26 @@ int drq_conv3x3_dgrad_f32(const float* dout, const float* w, const float* act_in
 int drq_conv3x3_wgrad_f32(const float* in, const float* dpre, float* partial, float* dw,
                           float* db, int N, int hout, void* stream);
 int64_t drq_conv_wgrad_ws_floats(int cin);
+
+/* ------------------------------------------------------------------ encoder, bf16 tensor cores */
+
+/* bf16 elements of a WB buffer holding n_images images. */
+int64_t drq_wb_elems(int n_images);
+
+/* fp32 conv weight [32][32][3][3] -> the two packed bf16 UMMA B operands ([36][32][8] each)
+ * used by the forward and data-gradient kernels. */
+int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream);
+
+/* conv2..4 (drqv2.py:56-59) + bias + ReLU on tcgen05 tensor cores, bf16 in / fp32 accumulate
+ * (TMEM) / bf16 out.  in, out: WB buffers of N images.  nhwc_out != 0: out is the compact
+ * feature matrix [N][hout*hout][32] (the bf16-mode feature layout) instead of WB. */
+int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out,
+                         int N, int hout, int nhwc_out, void* stream);
+
+/* data gradient on tensor cores; dout/din: WB buffers of N images (zero guard rows);
+ * act_in: WB buffer of n_act >= N images holding the layer's input activation (ReLU mask). */
+int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const uint16_t* act_in,
+                           int n_act, uint16_t* din, int N, int hout, void* stream);
 
 /* ------------------------------------------------------------------ dense, fp32 */
 

@@ -42,3 +42,27 @@ def rel_l2(a, b):
     a = np.asarray(a, np.float64).ravel()
     b = np.asarray(b, np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ---- bf16 "WB" layout helpers (see include/drqv2_b200.h): torch-side conversions for tests
+PLB, GUARD, WB_SLACK = 1776, 88, 128
+
+
+def wb_from_nchw(x):
+    """x float [N,32,H,W] (H,W <= 41) -> WB bf16 tensor [4][N*PLB+SLACK][8] on x.device."""
+    import torch
+    N, C, H, W = x.shape
+    wide = torch.zeros(N, C, 41, 41, dtype=torch.float32, device=x.device)
+    wide[:, :, :H, :W] = x
+    rows = torch.zeros(N, PLB, C, dtype=torch.float32, device=x.device)
+    rows[:, GUARD:GUARD + 1681, :] = wide.view(N, C, 1681).permute(0, 2, 1)
+    wb = torch.zeros(4, N * PLB + WB_SLACK, 8, dtype=torch.bfloat16, device=x.device)
+    wb[:, :N * PLB, :] = rows.view(N * PLB, 4, 8).permute(1, 0, 2).to(torch.bfloat16)
+    return wb.contiguous()
+
+
+def nchw_from_wb(wb, N, H, W):
+    """inverse of wb_from_nchw: float32 [N,32,H,W] (only the valid region)."""
+    rows = wb[:, :N * PLB, :].float().permute(1, 0, 2).reshape(N, PLB, 32)
+    wide = rows[:, GUARD:GUARD + 1681, :].permute(0, 2, 1).reshape(N, 32, 41, 41)
+    return wide[:, :, :H, :W].contiguous()
