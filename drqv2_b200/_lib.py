@@ -34,6 +34,7 @@ SIGNATURES = {
     "drq_pack_conv_w_bf16": [P, P, P, P],
     "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, P],
     "drq_conv3x3_dgrad_bf16": [P, P, P, I, P, I, I, P],
+    "drq_conv3x3_wgrad_bf16": [P, I, P, P, P, P, I, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
     "drq_splitk_reduce": [P, I, L, P, L, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
@@ -55,6 +56,7 @@ SPECIAL = {
     "drq_device_sm_count": (I, []),
     "drq_conv_wgrad_ws_floats": (L, [I]),
     "drq_wb_elems": (L, [I]),
+    "drq_conv_wgrad_bf16_ws_floats": (L, []),
 }
 
 EPI_NONE, EPI_RELU, EPI_MASK, EPI_MASK_WIDE = 0, 1, 2, 3

@@ -197,6 +197,148 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
     w_dgrad[((tap * 4 + co / 8) * 32 + ci) * 8 + (co & 7)] = v;
 }
 
+
+// ---------------------------------------------------------------- conv 32->32 weight gradient
+// dW[tap][ci][co] = sum_{n,p} in[n][p + off(tap)][ci] * d[n][p][co]: per tap a GEMM with
+// M = ci, N = co and K = positions.  Both operands are read straight from WB-layout windows
+// as MN-major UMMA operands (8 channels = one 16-byte unit, consecutive positions 16 bytes
+// apart = consecutive K).  M is padded to 64 (rows 32..63 read neighbouring smem and are
+// ignored).  A tenth "tap" multiplies d by an all-ones A operand: its row 0 is the bias
+// gradient.  Every CTA keeps its 10 accumulators (320 TMEM columns) across all of its tiles
+// and writes one fp32 partial at the end; partials are reduced in fixed order.
+constexpr int kWgStages = 4;
+constexpr int kWgDRows = kTM;                              // d tile rows per block
+constexpr int kWgStageBytes = kStageBytes + 4 * kWgDRows * 16;   // in-window + d tile
+constexpr int kWgOnesBytes = 8 * 16 * 16;                  // 8 MN units x 16 K x 16 B of bf16 ones
+constexpr int kWgAcc = 10;
+constexpr int kWgPartial = kWgAcc * 32 * 32;               // floats per CTA
+
+struct WgradTcArgs {
+    const __nv_bfloat16* in; long long cs_in;
+    const __nv_bfloat16* d; long long cs_d;
+    float* partial;
+    int n_images, ntiles;
+};
+
+__global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ones_s = smem;
+    uint8_t* st_s = smem + kWgOnesBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kWgStages * kWgStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kWgStages;
+    uint64_t* done = bars + 2 * kWgStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = a.n_images * a.ntiles;
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kThreadsTC)
+        reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;    // bf16 1.0 x2
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+                mbar_wait(empty + stage, phase ^ 1);
+                mbar_arrive_expect_tx(full + stage, 4 * (kWinRows + kWgDRows) * 16);
+                const long long row0 = (long long)n * kPLB + kGuard + p0;
+                uint8_t* dst = st_s + stage * kWgStageBytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    bulk_g2s(dst + c * kStageRows * 16, a.in + (c * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
+                    bulk_g2s(dst + kStageBytes + c * kWgDRows * 16, a.d + (c * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
+                }
+                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(64, 32, true, true);
+        int stage = 0; uint32_t phase = 0;
+        bool first = true;
+        const uint32_t ones_addr = smem_u32(ones_s);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(st_s + stage * kWgStageBytes);
+                const uint32_t d_addr = a_addr + kStageBytes;
+#pragma unroll 1
+                for (int ks = 0; ks < kTM / 16; ++ks) {
+                    const uint64_t db = make_smem_desc(d_addr + ks * 256, 128, kWgDRows * 16);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int off = (tap / 3) * kPW + (tap % 3);
+                        const uint64_t da = make_smem_desc(a_addr + (off + ks * 16) * 16, 128, kStageRows * 16);
+                        umma_bf16(tmem_base + tap * 32, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+                    }
+                    const uint64_t d1 = make_smem_desc(ones_addr, 128, 256);
+                    umma_bf16(tmem_base + 9 * 32, d1, db, idesc, (first && ks == 0) ? 0u : 1u);
+                }
+                umma_commit(empty + stage);
+            }
+            __syncwarp();
+            first = false;
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* out = a.partial + (long long)blockIdx.x * kWgPartial;
+        if (q < 2) {
+            // M = 64 accumulator: rows 0..15 -> lanes 0..15, rows 16..31 -> lanes 32..47
+            for (int tap = 0; tap < kWgAcc; ++tap) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + tap * 32, v);
+                if (lane < 16) {
+                    float4* dst = reinterpret_cast<float4*>(out + (tap * 32 + q * 16 + lane) * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co]
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G, float* __restrict__ dw,
+                                       float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * 32 * 32 + 32) return;
+    float s = 0.f;
+    if (i < 9216) {
+        for (int g = 0; g < G; ++g) s += partial[(long long)g * kWgPartial + i];
+        const int tap = i / 1024, ci = (i / 32) % 32, co = i % 32;
+        dw[(co * 32 + ci) * 9 + tap] = s;
+    } else {
+        const int co = i - 9216;
+        for (int g = 0; g < G; ++g) s += partial[(long long)g * kWgPartial + 9 * 1024 + co];
+        db[co] = s;
+    }
+}
+
+constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * kWgStages + 1) * 8 + 16;
+
 constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16;
 
 static int conv_tc_grid(int total_tiles) {
@@ -261,6 +403,28 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.nhwc_out = 0;
     conv3x3_tc_kernel<true><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
+}
+
+int64_t drq_conv_wgrad_bf16_ws_floats(void) { return 148ll * kWgPartial; }
+
+int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, float* partial, float* dw,
+                           float* db, int N, int hout, void* stream) {
+    DRQ_REQUIRE(in && dpre && partial && dw && db, "conv3x3_wgrad_bf16: null pointer");
+    DRQ_REQUIRE(N > 0 && n_in >= N && hout > 0 && hout <= kPW - 2, "conv3x3_wgrad_bf16: bad dims");
+    if (int rc = ensure_smem((const void*)conv3x3_wgrad_tc_kernel, kWgradTcSmem, "conv3x3_wgrad_bf16")) return rc;
+    WgradTcArgs a{};
+    a.in = reinterpret_cast<const __nv_bfloat16*>(in);
+    a.cs_in = (long long)n_in * kPLB + kSlack;
+    a.d = reinterpret_cast<const __nv_bfloat16*>(dpre);
+    a.cs_d = (long long)N * kPLB + kSlack;
+    a.partial = partial;
+    a.n_images = N;
+    a.ntiles = (hout * kPW + kTM - 1) / kTM;
+    const int G = conv_tc_grid(N * a.ntiles);
+    conv3x3_wgrad_tc_kernel<<<G, kThreadsTC, kWgradTcSmem, as_stream(stream)>>>(a);
+    if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
+    wgrad_tc_reduce_kernel<<<(9248 + 127) / 128, 128, 0, as_stream(stream)>>>(partial, G, dw, db);
+    return check_launch("wgrad_tc_reduce_kernel");
 }
 
 }  // extern "C"

@@ -182,6 +182,13 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
 int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const uint16_t* act_in,
                            int n_act, uint16_t* din, int N, int hout, void* stream);
 
+/* weight + bias gradient of a 32->32 layer on tensor cores (fp32 accumulation in TMEM, fp32
+ * output in the reference layout dw [32][32][3][3], db [32]).  in: WB buffer of n_in >= N images
+ * (input activation), dpre: WB buffer of N images.  partial: drq_conv_wgrad_bf16_ws_floats(). */
+int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, float* partial, float* dw,
+                           float* db, int N, int hout, void* stream);
+int64_t drq_conv_wgrad_bf16_ws_floats(void);
+
 /* ------------------------------------------------------------------ dense, fp32 */
 
 /* C[z][m][n] = epi( sum_k A[z](m,k) * B[z](k,n) + bias[z][n] ), general strides.

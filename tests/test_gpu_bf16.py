@@ -80,3 +80,24 @@ def test_conv3x3_dgrad_bf16(dev, hout, N):
     # columns beyond the valid width are written as exact zeros (consumed by wgrad/dgrad below)
     full = nchw_from_wb(din.view(4, -1, 8), N, 41, 41)
     assert torch.count_nonzero(full[:, :, :hin, hin:]) == 0
+
+
+@pytest.mark.parametrize("hout,N", [(39, 3), (35, 7)])
+def test_conv3x3_wgrad_bf16(dev, hout, N):
+    from drqv2_b200 import _lib
+    g = torch.Generator().manual_seed(200 + hout)
+    hin = hout + 2
+    x = torch.rand(N + 2, 32, hin, hin, generator=g).to(dev)                   # input activation (more images than d)
+    d = ((torch.rand(N, 32, hout, hout, generator=g) * 2 - 1) * 1e-2).to(dev)
+    x_wb, d_wb = wb_from_nchw(x), wb_from_nchw(d)
+    ws = torch.zeros(_lib.lib().drq_conv_wgrad_bf16_ws_floats(), device=dev)
+    dw = torch.zeros(32, 32, 3, 3, device=dev)
+    db = torch.zeros(32, device=dev)
+    _lib.call("drq_conv3x3_wgrad_bf16", x_wb.data_ptr(), N + 2, d_wb.data_ptr(), ws.data_ptr(), dw.data_ptr(),
+              db.data_ptr(), N, hout, _stream())
+    torch.cuda.synchronize()
+    xr, dr = _bf(x[:N]).double(), _bf(d).double()
+    want_w = torch.nn.grad.conv2d_weight(xr, (32, 32, 3, 3), dr)
+    want_b = dr.sum(dim=(0, 2, 3))
+    assert (dw.double() - want_w).abs().max().item() <= 1e-5 * want_w.abs().max().item() + 1e-7
+    assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7
