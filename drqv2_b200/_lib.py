@@ -35,6 +35,8 @@ SIGNATURES = {
     "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, P],
     "drq_conv3x3_dgrad_bf16": [P, P, P, I, P, I, I, P],
     "drq_conv3x3_wgrad_bf16": [P, I, P, P, P, P, I, I, P],
+    "drq_gemm_bf16": [P, L, I, P, L, I, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, I, P],
+    "drq_pack_linear_bf16": [P, P, I, I, I, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
     "drq_splitk_reduce": [P, I, L, P, L, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
@@ -60,6 +62,7 @@ SPECIAL = {
 }
 
 EPI_NONE, EPI_RELU, EPI_MASK, EPI_MASK_WIDE = 0, 1, 2, 3
+TEPI_F32, TEPI_RELU_BF16, TEPI_MASK_BF16, TEPI_TRUNK_WGRAD, TEPI_TRUNK_DGRAD = 0, 1, 2, 3, 4
 IMG, PW, PLANE, CONV_CH, REPR_DIM = 84, 41, 1696, 32, 39200
 PLB, GUARD, WB_SLACK = 1776, 88, 128
 

@@ -337,7 +337,9 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G,
     }
 }
 
-constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * kWgStages + 1) * 8 + 16;
+// + kStageBytes of tail padding: rows 32..63 of the M=64 A operand address 4 more channel blocks
+// past the staged window (results ignored) and must stay inside the allocation
+constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * kWgStages + 1) * 8 + 16 + kStageBytes;
 
 constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16;
 

@@ -189,6 +189,32 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
                            float* db, int N, int hout, void* stream);
 int64_t drq_conv_wgrad_bf16_ws_floats(void);
 
+/* ------------------------------------------------------------------ dense, bf16 tensor cores */
+
+/* epilogues of drq_gemm_bf16 */
+#define DRQ_TEPI_F32 0          /* C(fp32) = acc (+bias) (+C if accumulate)                      */
+#define DRQ_TEPI_RELU_BF16 1    /* C(bf16) = relu(acc + bias)                                    */
+#define DRQ_TEPI_MASK_BF16 2    /* C(bf16) = acc * (mask > 0)                                    */
+#define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: NHWC feature column -> reference order */
+#define DRQ_TEPI_TRUNK_DGRAD 4  /* C(bf16 WB of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows */
+
+/* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
+ * a_mn_major == 0: A stored [m][k] (row stride lda); != 0: A stored [k][m].  Same for B with n.
+ * lda/ldb must be multiples of 8 and rows zero-padded up to a multiple of 8 elements.
+ * batch / split-K / strides as drq_gemm_f32 (strides in elements of the respective type).
+ * bn = N tile (32, 64 or 128). */
+int drq_gemm_bf16(const uint16_t* A, int64_t lda, int a_mn_major, const uint16_t* B, int64_t ldb,
+                  int b_mn_major, void* C, int64_t ldc, const float* bias, const uint16_t* mask,
+                  int64_t ldmask, int M, int N, int K, int epilogue, int accumulate, int batch,
+                  int64_t bs_a, int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask, int splitk,
+                  int bn, void* stream);
+
+/* fp32 nn.Linear weight [rows][cols] -> bf16 [rows][ld] zero padded; nhwc_permute != 0 (trunk,
+ * cols = 39200): output column k is the NHWC feature index (y*35+x)*32+c of the bf16 feature
+ * layout, read from the reference column c*1225+y*35+x (drqv2.py:66). */
+int drq_pack_linear_bf16(const float* w, uint16_t* out, int rows, int cols, int ld, int nhwc_permute,
+                         void* stream);
+
 /* ------------------------------------------------------------------ dense, fp32 */
 
 /* C[z][m][n] = epi( sum_k A[z](m,k) * B[z](k,n) + bias[z][n] ), general strides.

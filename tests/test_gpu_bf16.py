@@ -101,3 +101,111 @@ def test_conv3x3_wgrad_bf16(dev, hout, N):
     want_b = dr.sum(dim=(0, 2, 3))
     assert (dw.double() - want_w).abs().max().item() <= 1e-5 * want_w.abs().max().item() + 1e-7
     assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7
+
+
+def _gemm_bf16(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, epi, bias=None, mask=None, ldmask=0, acc=0,
+               batch=1, bs=(0, 0, 0, 0, 0), splitk=1, bn=64):
+    from drqv2_b200 import _lib
+    _lib.call("drq_gemm_bf16", A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, C.data_ptr(), ldc,
+              None if bias is None else bias.data_ptr(), None if mask is None else mask.data_ptr(), ldmask,
+              M, N, K, epi, acc, batch, bs[0], bs[1], bs[2], bs[3], bs[4], splitk, bn, _stream())
+
+
+def _pad_bf16(x, ld):
+    out = torch.zeros(*x.shape[:-1], ld, dtype=torch.bfloat16, device=x.device)
+    out[..., :x.shape[-1]] = x.to(torch.bfloat16)
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 1024, 56, 64), (37, 130, 1024, 32), (256, 50, 1000, 64), (300, 256, 256, 128)])
+def test_gemm_bf16_kmajor_relu_and_f32(dev, M, N, K, bn):
+    """Linear forward: y = relu(x W^T + b) (bf16 out) and plain fp32 out."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.rand(M, K, generator=g) - 0.5).to(dev)
+    w = ((torch.rand(N, K, generator=g) - 0.5) * 0.2).to(dev)
+    b = (torch.rand(N, generator=g) - 0.5).to(dev)
+    ldk = (K + 7) // 8 * 8
+    xb, wb = _pad_bf16(x, ldk), _pad_bf16(w, ldk)
+    want = _bf(x).double() @ _bf(w).double().T + b.double()
+    ldn = (N + 7) // 8 * 8
+    y = torch.zeros(M, ldn, dtype=torch.bfloat16, device=dev)
+    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, y, ldn, M, N, K, 1, bias=b, bn=bn)
+    yf = torch.zeros(M, N, device=dev)
+    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, yf, N, M, N, K, 0, bias=b, bn=bn)
+    torch.cuda.synchronize()
+    scale = want.abs().max().item()
+    assert (yf.double() - want).abs().max().item() <= 2e-5 * scale
+    assert (y[:, :N].double() - torch.relu(want)).abs().max().item() <= 2 ** -8 * scale
+    assert torch.count_nonzero(y[:, N:]) == 0
+    # accumulate into C
+    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, yf, N, M, N, K, 0, acc=1, bn=bn)
+    torch.cuda.synchronize()
+    assert (yf.double() - (2 * want - b.double())).abs().max().item() <= 4e-5 * scale
+
+
+def test_gemm_bf16_dgrad_wgrad_layouts(dev):
+    """dgrad: dx = (dy W) * (x_act > 0) with W as an MN-major B operand; wgrad: dW = dy^T x with both
+    operands MN-major; twin-head batching; split-K partials."""
+    g = torch.Generator().manual_seed(5)
+    Bt, H, I = 256, 1024, 56
+    dy = ((torch.rand(2, Bt, H, generator=g) - 0.5) * 1e-2).to(dev)
+    w = ((torch.rand(2, H, I, generator=g) - 0.5) * 0.2).to(dev)
+    xact = (torch.rand(2, Bt, I, generator=g) - 0.5).clamp_min(0).to(dev)
+    dyb, wb, xb = dy.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous(), xact.to(torch.bfloat16).contiguous()
+    # dgrad, batch of 2 heads: A = dy [B][H] K-major (K = H); B(k=h, n=i) = W[h][i] -> MN-major
+    dx = torch.zeros(2, Bt, I, dtype=torch.bfloat16, device=dev)
+    _gemm_bf16(dyb, H, 0, wb, I, 1, dx, I, Bt, I, H, 2, mask=xb, ldmask=I, batch=2,
+               bs=(Bt * H, H * I, Bt * I, 0, Bt * I), bn=64)
+    torch.cuda.synchronize()
+    want = (_bf(dy).double() @ _bf(w).double()) * (xact.double() > 0)
+    assert (dx.double() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item()
+    # wgrad: dW[h][i] = sum_b dy[b][h] x[b][i]: A(m=h,k=b) = dy[b][h] MN-major, B(n=i,k=b) = x[b][i] MN-major
+    dw = torch.zeros(2, H, I, device=dev)
+    _gemm_bf16(dyb, H, 1, xb, I, 1, dw, I, H, I, Bt, 0, batch=2, bs=(Bt * H, Bt * I, H * I, 0, 0), bn=64)
+    torch.cuda.synchronize()
+    want_w = _bf(dy).double().transpose(1, 2) @ _bf(xact).double()
+    assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
+    # split-K partials sum to the full product
+    K = 39200
+    feat = (torch.rand(64, K, generator=g) - 0.3).clamp_min(0).to(dev).to(torch.bfloat16)
+    wt = ((torch.rand(50, K, generator=g) - 0.5) * 0.01).to(dev).to(torch.bfloat16)
+    S = 37
+    part = torch.zeros(S, 64, 50, device=dev)
+    _gemm_bf16(feat, K, 0, wt, K, 0, part, 50, 64, 50, K, 0, splitk=S, bs=(0, 0, 64 * 50, 0, 0), bn=64)
+    torch.cuda.synchronize()
+    want_t = feat.double() @ wt.double().T
+    assert (part.double().sum(0) - want_t).abs().max().item() <= 2e-5 * want_t.abs().max().item()
+
+
+def test_trunk_weight_pack_and_epilogues(dev):
+    """NHWC-permuted trunk weight pack; wgrad epilogue writes the reference [F][39200] order;
+    dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane."""
+    from drqv2_b200 import _lib
+    from drqv2_b200._lib import PLB as PLB_
+    g = torch.Generator().manual_seed(9)
+    Fd, Bt, K = 50, 6, 39200
+    w = ((torch.rand(Fd, K, generator=g) - 0.5) * 0.02).to(dev)
+    ldf = 56
+    wp = torch.zeros(ldf, K, dtype=torch.bfloat16, device=dev)        # rows padded to 56 so MN-major N reads stay in bounds
+    _lib.call("drq_pack_linear_bf16", w.data_ptr(), wp.data_ptr(), Fd, K, K, 1, _stream())
+    # reference order -> NHWC: column (y*35+x)*32+c holds w[:, c*1225 + y*35 + x]
+    w_nhwc = w.view(Fd, 32, 1225).permute(0, 2, 1).reshape(Fd, K)
+    assert torch.equal(wp[:Fd].float(), _bf(w_nhwc))
+    feat_nchw = (torch.rand(Bt, 32, 35, 35, generator=g) - 0.4).clamp_min(0).to(dev)
+    feat = feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K).to(torch.bfloat16).contiguous()           # NHWC bf16
+    dz = ((torch.rand(Bt, Fd, generator=g) - 0.5) * 1e-2).to(dev)
+    dzb = _pad_bf16(dz, ldf)
+    # wgrad: dW[f][ref(n)] = sum_b dz[b][f] feat[b][n]
+    dw = torch.zeros(Fd, K, device=dev)
+    _gemm_bf16(dzb, ldf, 1, feat, K, 1, dw, K, Fd, K, Bt, 3, bn=128)
+    torch.cuda.synchronize()
+    want_w = _bf(dz).double().T @ _bf(feat_nchw).double().reshape(Bt, K)
+    assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
+    # dgrad: d4pre = (dz W) * (feat > 0) scattered to WB
+    d4 = torch.zeros(_lib.lib().drq_wb_elems(Bt), dtype=torch.bfloat16, device=dev)
+    cs = Bt * PLB_ + 128
+    _gemm_bf16(dzb, ldf, 0, wp, K, 1, d4, cs, Bt, K, Fd, 4, mask=feat, ldmask=K, bn=128)
+    torch.cuda.synchronize()
+    want_d = (_bf(dz).double() @ _bf(w).double()).view(Bt, 32, 35, 35) * (feat_nchw.double() > 0)
+    got = nchw_from_wb(d4.view(4, -1, 8), Bt, 35, 35).double()
+    assert (got - want_d).abs().max().item() <= 2 ** -8 * want_d.abs().max().item()
