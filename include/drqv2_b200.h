@@ -189,6 +189,17 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
                            float* db, int N, int hout, void* stream);
 int64_t drq_conv_wgrad_bf16_ws_floats(void);
 
+/* conv1 (drqv2.py:55, stride 2) on tensor cores with RandomShiftsAug + obs/255-0.5 fused into an
+ * in-shared-memory im2col loader; output WB bf16 of N images.  w_packed from drq_pack_conv1_w_bf16.
+ * cin*9+1 <= 96. */
+int drq_pack_conv1_w_bf16(const float* w, uint16_t* out, int cin, void* stream);
+int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, const float* bias,
+                       uint16_t* out, int N, int cin, int pad, void* stream);
+/* conv1 weight + bias gradient (fp32, reference layout) from dpre (WB bf16 of N images). */
+int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
+                         float* dw, float* db, int N, int cin, int pad, void* stream);
+int64_t drq_conv1_wgrad_bf16_ws_floats(void);
+
 /* ------------------------------------------------------------------ dense, bf16 tensor cores */
 
 /* epilogues of drq_gemm_bf16 */
