@@ -16,7 +16,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, utils
+import os
+
+from . import _bf16, _lib, utils
 from ._lib import EPI_MASK, EPI_MASK_WIDE, EPI_NONE, EPI_RELU, PLANE, REPR_DIM, call
 
 F32 = 4
@@ -76,7 +78,7 @@ def _trunk_fwd(feat, B, W, b, gamma, beta, Fdim, partial, h_out, ld_h, xhat=0, r
     _gemm(feat, REPR_DIM, 1, W, 1, REPR_DIM, partial, Fdim, B, Fdim, REPR_DIM, splitk=S,
           bs=(0, 0, B * Fdim, 0, 0))
     call("drq_ln_tanh_fwd", partial, S, B * Fdim, b, gamma, beta, h_out, ld_h, xhat or None, rstd or None,
-         B, Fdim, 1e-5, _stream())
+         None, 0, B, Fdim, 1e-5, _stream())
 
 
 def _encoder_fwd(obs_u8, shift, w, b, acts, feat, N, cin, pad=4):
@@ -201,7 +203,7 @@ class Actor(nn.Module):
         mu_pre = torch.empty(B, A, device=dev)
         keep = _mlp_fwd(self.policy, h.data_ptr(), Fd, B, Fd, H, A, mu_pre.data_ptr(), dev)
         mu = torch.empty(B, A, device=dev)
-        call("drq_actor_sample", mu_pre.data_ptr(), None, None, 0.0, mu.data_ptr(), A, None, None, B, A,
+        call("drq_actor_sample", mu_pre.data_ptr(), None, None, 0.0, mu.data_ptr(), A, None, None, None, 0, B, A,
              _stream())
         del keep
         return utils.TruncatedNormal(mu, torch.ones_like(mu) * std)
@@ -291,7 +293,7 @@ class _Arena:
 class _Workspace:
     """Static buffers of one update at batch size B (allocated once, graph-capturable)."""
 
-    def __init__(self, B, A, Fd, H, cin, device):
+    def __init__(self, B, A, Fd, H, cin, device, fp32_encoder=True):
         z = lambda *s: torch.zeros(*s, device=device)
         self.B = B
         NB = 2 * B
@@ -301,10 +303,11 @@ class _Workspace:
         self.shift = torch.full((NB, 2), 4, dtype=torch.int32, device=device)       # [obs | next_obs]
         self.eps_c, self.eps_a = z(B, A), z(B, A)
         # encoder
-        self.acts = [z(NB * 32 * PLANE) for _ in range(3)]
-        self.feat = z(NB, REPR_DIM)
-        self.dpre = [z(B * 32 * PLANE) for _ in range(4)]    # grads w.r.t. conv1..4 pre-ReLU outputs
-        self.wgrad_ws = z(int(_lib.lib().drq_conv_wgrad_ws_floats(32)))
+        if fp32_encoder:
+            self.acts = [z(NB * 32 * PLANE) for _ in range(3)]
+            self.feat = z(NB, REPR_DIM)
+            self.dpre = [z(B * 32 * PLANE) for _ in range(4)]    # grads w.r.t. conv1..4 pre-ReLU outputs
+            self.wgrad_ws = z(int(_lib.lib().drq_conv_wgrad_ws_floats(32)))
         # heads
         self.partial = z(_splitk_for(B) * B * Fd)
         self.xT = z(B, Fd + A)          # [h_target(next) | next_action]
@@ -354,7 +357,11 @@ METRIC_KEYS = ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "cri
 class DrQV2Agent:
     def __init__(self, obs_shape, action_shape, device, lr, feature_dim, hidden_dim, critic_target_tau,
                  num_expl_steps, update_every_steps, stddev_schedule, stddev_clip, use_tb,
-                 use_cuda_graph=True, seed=None):
+                 use_cuda_graph=True, seed=None, mode=None):
+        """Reference signature (drqv2.py:125-127) plus three keyword-only extras: use_cuda_graph,
+        seed (device RNG key) and mode — "fp32" (parity mode, CUDA-core kernels, <= 1e-4 vs the
+        reference on pre-optimiser quantities) or "bf16" (tcgen05 tensor-core kernels, bf16
+        operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "fp32"."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError(f"DrQV2Agent(device={device!r}): drqv2_b200 has no CPU path; use a CUDA device")
@@ -370,6 +377,9 @@ class DrQV2Agent:
         self.stddev_clip = stddev_clip
         self.lr = lr
         self.use_cuda_graph = use_cuda_graph
+        self.mode = mode or os.environ.get("DRQV2_B200_MODE", "fp32")
+        if self.mode not in ("fp32", "bf16"):
+            raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
         self.obs_shape = tuple(int(v) for v in obs_shape)
         self.action_dim = int(action_shape[0])
         self.feature_dim, self.hidden_dim = int(feature_dim), int(hidden_dim)
@@ -405,11 +415,15 @@ class DrQV2Agent:
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._injected = None
+        self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None
+        self._bf16_ws = {}
+        self._bf16_dirty = True
 
     def __getstate__(self):
         st = dict(self.__dict__)
-        for k in ("_ws", "_graphs", "_act_ws"):
+        for k in ("_ws", "_graphs", "_act_ws", "_bf16_ws"):
             st[k] = {}
+        st["_bf16"] = None
         return st
 
     def __setstate__(self, st):
@@ -429,6 +443,15 @@ class DrQV2Agent:
         for pname, p in self.critic_target.named_parameters():
             p.data = a.target[off:off + p.numel()].view(p.shape)
             off += p.numel()
+        self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None
+        self._bf16_dirty = True
+
+    def refresh(self):
+        """Re-derive the bf16 operand copies after parameters were changed from outside
+        (load_state_dict, manual edits).  No-op in fp32 mode."""
+        if self._bf16 is not None:
+            self._bf16.repack_all()
+        self._bf16_dirty = False
 
     def train(self, training=True):
         self.training = training
@@ -439,9 +462,17 @@ class DrQV2Agent:
     def workspace(self, B):
         ws = self._ws.get(B)
         if ws is None:
-            ws = _Workspace(B, self.action_dim, self.feature_dim, self.hidden_dim, self.obs_shape[0], self._dev)
+            ws = _Workspace(B, self.action_dim, self.feature_dim, self.hidden_dim, self.obs_shape[0], self._dev,
+                            fp32_encoder=self.mode == "fp32")
             self._ws[B] = ws
         return ws
+
+    def bf16_workspace(self, B):
+        bw = self._bf16_ws.get(B)
+        if bw is None:
+            bw = _bf16.Bf16Workspace(B, self.action_dim, self.feature_dim, self.hidden_dim, self._bf16, self._dev)
+            self._bf16_ws[B] = bw
+        return bw
 
     def inject_draws(self, shift_obs, shift_next, eps_critic, eps_actor):
         """Parity mode: use these draws (int [B,2] (x,y) shifts, float [B,A] N(0,1) noise) for
@@ -480,6 +511,13 @@ class DrQV2Agent:
                      eps=torch.zeros(n, A, device=dev), out=torch.zeros(n, A, device=dev),
                      host_in=torch.zeros(n, *self.obs_shape, dtype=torch.uint8).pin_memory(),
                      host_out=torch.zeros(n, A).pin_memory(), graph={})
+            if self.mode == "bf16":
+                nel = _lib.lib().drq_wb_elems(n)
+                zb = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+                S = _bf16.splitk_for(n)
+                w.update(acts_b=[zb(nel) for _ in range(3)], feat_b=zb(n, REPR_DIM), S_b=S,
+                         partial_b=torch.zeros(S * n * Fd, device=dev), h_b=zb(n, self._bf16.ldF),
+                         p1_b=zb(n, H), p2_b=zb(n, H))
             self._act_ws[n] = w
         if obs_t.is_cuda:
             w["obs"].copy_(obs_t, non_blocking=True)
@@ -489,6 +527,8 @@ class DrQV2Agent:
         stddev = utils.schedule(self.stddev_schedule, step)
         self._scal_host[8] = stddev
         self._scal_dev[8:9].copy_(self._scal_host[8:9], non_blocking=True)
+        if self._bf16_dirty:
+            self.refresh()
         sample = not eval_mode
         key = bool(sample)
         g = w["graph"].get(key)
@@ -512,6 +552,8 @@ class DrQV2Agent:
 
     def _act_body(self, w, n, sample):
         A, Fd, H = self.action_dim, self.feature_dim, self.hidden_dim
+        if self.mode == "bf16":
+            return _bf16.act_body(self, w, n, sample)
         if sample:   # exploration noise draw (utils.py:119)
             call("drq_rng_normal_f32", self._seed, self._counter.data_ptr(), w["eps"].data_ptr(), n * A, _stream())
             call("drq_counter_advance", self._counter.data_ptr(), _stream())
@@ -526,7 +568,7 @@ class DrQV2Agent:
         _linear_fwd(w["p1"].data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), w["p2"].data_ptr(), H, n, H, H, True)
         _linear_fwd(w["p2"].data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), w["mu_pre"].data_ptr(), A, n, A, H, False)
         call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
-             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, n, A, _stream())
+             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, None, 0, n, A, _stream())
 
     # ------------------------------------------------------------------ update
     def update(self, replay_iter, step):
@@ -548,6 +590,8 @@ class DrQV2Agent:
             fetch = None
             self._load_batch(ws, obs, action, reward, discount, next_obs)
         self._host_scalars(step)
+        if self._bf16_dirty:
+            self.refresh()
         inj = self._injected
         if inj is not None:
             self._injected = None
@@ -608,6 +652,12 @@ class DrQV2Agent:
                  ws.shift[:B].data_ptr(), ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
                  B, self.action_dim, s)
             call("drq_counter_advance", self._counter.data_ptr(), s)
+        if self.mode == "bf16":
+            bw = self.bf16_workspace(B)
+            _bf16.encode(self, ws, bw)
+            _bf16.critic_pass(self, ws, bw)
+            _bf16.actor_pass(self, ws, bw)
+            return
         self._encode(ws)
         self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=True)
         self._actor_pass(ws, ws.feat[:B])
@@ -651,7 +701,7 @@ class DrQV2Agent:
         _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
         _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
         call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_c.data_ptr(), std_ptr, float(self.stddev_clip),
-             ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, B, A, s)
+             ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, None, 0, B, A, s)
         # --- target critic on (next features, next action) (drqv2.py:184)
         _trunk_fwd(featn, B, self._t("trunk.0.weight"), self._t("trunk.0.bias"), self._t("trunk.1.weight"),
                    self._t("trunk.1.bias"), Fd, ws.partial.data_ptr(), ws.xT.data_ptr(), Fd + A)
@@ -683,7 +733,7 @@ class DrQV2Agent:
         # --- trunk backward: tanh, LayerNorm, Linear
         call("drq_ln_tanh_bwd", ws.dx.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
              ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), gc("trunk.1.weight"),
-             gc("trunk.1.bias"), B, Fd, s)
+             gc("trunk.1.bias"), None, 0, B, Fd, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, gc("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd)
         if encoder_grad:
@@ -737,7 +787,7 @@ class DrQV2Agent:
         _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
         _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
         call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_a.data_ptr(), std_ptr, float(self.stddev_clip),
-             ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6, B, A, s)
+             ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6, None, 0, B, A, s)
         # the just-updated critic on (features, action) (drqv2.py:213-216)
         _trunk_fwd(featp, B, pc("trunk.0.weight"), pc("trunk.0.bias"), pc("trunk.1.weight"), pc("trunk.1.bias"),
                    Fd, ws.partial.data_ptr(), ws.xA.data_ptr(), Fd + A)
@@ -750,7 +800,7 @@ class DrQV2Agent:
         _linear_dgrad(dc2, H, pc("Q1.2.weight"), dc1, H, B, H, H, mask=c1, ldmask=H, batch=2, bs=(BH, qs, BH, 0, BH))
         _linear_dgrad(dc1, H, pc("Q1.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A)
         _linear_dgrad(dc1 + F32 * BH, H, pc("Q2.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A, acc=1)
-        call("drq_actor_sample_bwd", ws.dact.data_ptr(), A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(), B, A, s)
+        call("drq_actor_sample_bwd", ws.dact.data_ptr(), A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(), None, 0, B, A, s)
         # actor MLP backward
         dmu, p1, p2, dp1, dp2 = (t.data_ptr() for t in (ws.dmu_pre, ws.p1, ws.p2, ws.dp1, ws.dp2))
         _linear_wgrad(dmu, A, p2, H, ga("policy.4.weight"), B, A, H)
@@ -764,7 +814,7 @@ class DrQV2Agent:
         _linear_dgrad(dp1, H, pa("policy.0.weight"), ws.dhA.data_ptr(), Fd, B, H, Fd)
         call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(),
              ws.rstdA.data_ptr(), pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"),
-             ga("trunk.1.bias"), B, Fd, s)
+             ga("trunk.1.bias"), None, 0, B, Fd, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, ga("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd)
         # actor_opt.step() fused with the soft target update of the (already stepped) critic
@@ -788,6 +838,9 @@ class DrQV2Agent:
         """drqv2.py:177-204 on encoded features [B, 39200].  When `obs` is the feature
         buffer produced by this agent's own encode (as in update()), the encoder is
         updated too, as autograd would; detached features leave it untouched."""
+        if self.mode != "fp32":
+            raise RuntimeError("update_critic on externally supplied features is available in mode='fp32' only "
+                               "(bf16 mode keeps features in its own NHWC bf16 layout); use update()")
         B = obs.shape[0]
         ws = self.workspace(B)
         own = obs.data_ptr() == ws.feat.data_ptr()
@@ -809,6 +862,9 @@ class DrQV2Agent:
         """drqv2.py:206-228 on (detached) features; also performs the actor Adam step.
         The soft target update that the fused kernel applies belongs to update(); callers of
         this stage API who do not want it should snapshot the target first."""
+        if self.mode != "fp32":
+            raise RuntimeError("update_actor on externally supplied features is available in mode='fp32' only; "
+                               "use update()")
         B = obs.shape[0]
         ws = self.workspace(B)
         if obs.data_ptr() != ws.feat.data_ptr():

@@ -253,17 +253,20 @@ int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int bat
 /* trunk tail: z = sum_s partial[s] + bias; LayerNorm(F, eps) affine; tanh
  * (drqv2.py:74-75,100-101).  h written at h_out[b*ld_h + f] (so it can land in
  * the [h, action] concat buffer of drqv2.py:117).  xhat [B][F] and rstd [B]
- * are saved for backward when non-NULL. */
+ * are saved for backward when non-NULL; h_bf16 (nullable, row stride ld_hb) receives a bf16 copy
+ * of h for the tensor-core heads. */
 int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
                     const float* gamma, const float* beta, float* h_out, int64_t ld_h,
-                    float* xhat, float* rstd, int B, int F, float eps, void* stream);
+                    float* xhat, float* rstd, uint16_t* h_bf16, int64_t ld_hb, int B, int F, float eps,
+                    void* stream);
 
 /* backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
  * output), dgamma[F], dbeta[F].  h is the saved tanh output (ld_h).
  * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) is scratch. */
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h,
                     const float* xhat, const float* rstd, const float* gamma, float* dz,
-                    float* dgamma, float* dbeta, int B, int F, void* stream);
+                    float* dgamma, float* dbeta, uint16_t* dz_bf16, int64_t ld_zb, int B, int F,
+                    void* stream);
 
 /* ------------------------------------------------------------------ heads */
 
@@ -274,12 +277,12 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
  * metrics (nullable) [2]: mean_b sum_j log_prob, mean_b sum_j entropy
  * (drqv2.py:212,226). */
 int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev, float clip,
-                     float* action_out, int64_t ld_a, float* mu_out, float* metrics, int B, int A,
-                     void* stream);
+                     float* action_out, int64_t ld_a, float* mu_out, float* metrics,
+                     uint16_t* action_bf16, int64_t ld_ab, int B, int A, void* stream);
 
 /* d(mu_pre) = d(action) * (1 - mu^2)   (straight-through clamp, utils.py:113-116) */
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
-                         int B, int A, void* stream);
+                         uint16_t* dmu_bf16, int64_t ld_mb, int B, int A, void* stream);
 
 /* TD target + critic loss (drqv2.py:185-189): tq = r + d*min(tq1,tq2);
  * loss = mean((q1-tq)^2) + mean((q2-tq)^2); dq1 = 2(q1-tq)/B, dq2 likewise.
@@ -298,6 +301,22 @@ int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, flo
 /* dst[r*ld_dst + c] = src[r*ld_src + c]  (the `torch.cat([h, action])` of drqv2.py:117) */
 int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
                    void* stream);
+
+/* bf16-mode helpers of the heads */
+int drq_copy2d_f32_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int rows, int cols,
+                        void* stream);
+int drq_colsum_bf16(const uint16_t* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,
+                    int64_t bs_out, void* stream);
+/* final Linear(hidden,1) of the Q heads (drqv2.py:106,111) on a bf16 hidden activation c2 [heads][B][H]:
+ * q[z][b] = c2[z][b].w3[z] + b3[z]; w3/b3 of head z at w3 + z*w_stride / b3 + z*w_stride. */
+int drq_q_head_fwd_bf16(const uint16_t* c2, const float* w3, const float* b3, float* q, int B, int H,
+                        int heads, int64_t w_stride, void* stream);
+/* its backward: dc2 = dq w3 (c2 > 0) in bf16; dw3 / db3 (nullable) in fp32 at the same strides. */
+int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, const float* w3, uint16_t* dc2, float* dw3,
+                        float* db3, int B, int H, int heads, int64_t w_stride, void* stream);
+/* table-driven fp32 -> bf16 packing of nn.Linear weights after an optimiser step.  table (device,
+ * int64 [n][6]): src offset (floats), dst offset (bf16 elements), rows, cols, ld, nhwc_permute. */
+int drq_pack_table_bf16(const float* src, uint16_t* dst, const int64_t* table, int n_entries, void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 

@@ -252,3 +252,110 @@ def test_conv1_bf16_fwd_and_wgrad(dev, N):
     want_b = dr.sum(dim=(0, 2, 3))
     assert (dw.double() - want_w).abs().max().item() <= 1e-5 * want_w.abs().max().item() + 1e-7
     assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7
+
+
+# ----------------------------------------------------------------------------- full update, bf16 mode
+SCHED = "linear(1.0,0.1,100000)"
+
+
+def _make_agent(A, Fd, H, lr, params, mode, use_graph=False):
+    from drqv2_b200 import DrQV2Agent
+    agent = DrQV2Agent((9, 84, 84), (A,), "cuda", lr, Fd, H, 0.01, 2000, 2, SCHED, 0.3, True,
+                       use_cuda_graph=use_graph, seed=5, mode=mode)
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        getattr(agent, net).load_state_dict(params[net])
+    return agent
+
+
+def _run(agent, b, step):
+    agent.inject_draws(b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+    return agent.update(iter([(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])]), step)
+
+
+# Stated bf16-mode tolerances (vs the fp64 oracle, one update from identical parameters and draws):
+#   Q values / TD target / losses : 2e-2 relative (+1e-3 absolute)      (measured 3e-4 .. 8e-3)
+#   gradients, per tensor, rel-L2  : twin-Q MLPs 0.15, critic trunk 0.2, encoder / actor 0.3 (B <= 16 here)
+#                                    (measured 3e-3 .. 0.15 at B=16..192; cosine similarity >= 0.95 everywhere)
+#   post-update parameters         : |delta| <= 2.5 lr per step (Adam's first steps are sign-like)
+# Why gradients are this loose while every kernel is checked to 2^-8 above: an activation stored in
+# bf16 carries ~0.3 % relative error, so ~0.3 % of the ReLU units (and a few min(Q1,Q2) selections)
+# sit on the other side of zero than in fp64.  A flipped unit contributes its whole gradient as
+# "error": rel-L2 ~ sqrt(flipped fraction) ~ 5 % per ReLU layer, accumulating down the backward
+# chain (Q.4 0.3 % -> Q.0 3 % -> trunk 4 % -> conv4 6 % -> conv1 15 %, tools/bf16_error_scan*.py).
+# It does not shrink with finer accumulation; it is the gradient of a slightly perturbed network.
+BF16_METRIC_RTOL = 2e-2
+
+
+def _bf16_grad_tol(net, name):
+    if net == "critic" and name.startswith("Q"):
+        return 0.15
+    if net == "critic":
+        return 0.2
+    return 0.3
+
+
+@pytest.mark.parametrize("case", [dict(B=16, A=6, F=50, H=256, lr=1e-4), dict(B=6, A=21, F=100, H=128, lr=8e-5)])
+def test_update_bf16_matches_oracle(dev, case, capsys):
+    """Stage-wise, as SURVEY §8c prescribes: with lr = 0 the optimiser steps are no-ops, so the
+    actor stage sees the same critic as the oracle and every loss / Q / gradient is comparable at
+    bf16 precision; with the real lr the post-update parameters are bounded by Adam's step size."""
+    from oracle import drq_oracle as O
+    from tests.helpers import rel_l2
+    torch.set_num_threads(8)
+    A, Fd, H, B, lr = case["A"], case["F"], case["H"], case["B"], case["lr"]
+    params = O.synthetic_params(9, A, Fd, H, seed=4)
+    b = O.synthetic_batch(B, A, seed=10)
+    args = (b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"], 0, b["shift_obs"],
+            b["shift_next"], b["eps_critic"], b["eps_actor"])
+    # --- lr = 0: all stages
+    agent = _make_agent(A, Fd, H, 0.0, params, "bf16")
+    o64 = O.OracleAgent(params, 0.0, 0.01, SCHED, 0.3, dtype=torch.float64)
+    m, m64 = _run(agent, b, 0), o64.update(*args)
+    report = {}
+    for k in m64:
+        report[k] = abs(m[k] - m64[k]) / (abs(m64[k]) + 1e-12)
+        assert abs(m[k] - m64[k]) <= BF16_METRIC_RTOL * abs(m64[k]) + 1e-3, (k, m[k], m64[k])
+    for net in ("encoder", "critic", "actor"):
+        for name, p in getattr(agent, net).named_parameters():
+            err = rel_l2(p.grad.cpu().numpy(), o64.grads[net][name].numpy())
+            report[f"{net}.{name}"] = err
+    with capsys.disabled():
+        print("\nbf16 update errors vs fp64 oracle:", {k: float(f"{v:.2e}") for k, v in report.items()})
+    for net in ("encoder", "critic", "actor"):
+        for name, p in getattr(agent, net).named_parameters():
+            assert report[f"{net}.{name}"] <= _bf16_grad_tol(net, name), (net, name, report[f"{net}.{name}"])
+            g, w = p.grad.cpu().double().flatten(), o64.grads[net][name].flatten()
+            cos = float(torch.dot(g, w) / (g.norm() * w.norm() + 1e-300))
+            assert cos >= 0.95, (net, name, cos)
+    # --- real lr: critic-side metrics and the parameter step bound
+    agent = _make_agent(A, Fd, H, lr, params, "bf16")
+    o64 = O.OracleAgent(params, lr, 0.01, SCHED, 0.3, dtype=torch.float64)
+    m, m64 = _run(agent, b, 0), o64.update(*args)
+    for k in ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "critic_loss"):
+        assert abs(m[k] - m64[k]) <= BF16_METRIC_RTOL * abs(m64[k]) + 1e-3, (k, m[k], m64[k])
+    for net in ("encoder", "critic", "actor", "critic_target"):
+        for name, p in getattr(agent, net).named_parameters():
+            assert (p.detach().cpu().double() - o64.p[net][name]).abs().max().item() <= 2.5 * lr, (net, name)
+
+
+def test_bf16_graph_equals_eager_and_act(dev):
+    from oracle import drq_oracle as O
+    A, Fd, H, B = 6, 50, 128, 8
+    params = O.synthetic_params(9, A, Fd, H, seed=6)
+    eager = _make_agent(A, Fd, H, 1e-4, params, "bf16", use_graph=False)
+    graph = _make_agent(A, Fd, H, 1e-4, params, "bf16", use_graph=True)
+    for s in range(4):
+        b = O.synthetic_batch(B, A, seed=50 + s)
+        _run(eager, b, 2 * s)
+        _run(graph, b, 2 * s)
+    torch.cuda.synchronize()
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        for (n1, p1), (n2, p2) in zip(getattr(eager, net).named_parameters(), getattr(graph, net).named_parameters()):
+            assert torch.equal(p1, p2), (net, n1)
+    o64 = O.OracleAgent(params, 1e-4, 0.01, SCHED, 0.3, dtype=torch.float64)
+    fresh = _make_agent(A, Fd, H, 1e-4, params, "bf16", use_graph=True)
+    obs = O.synthetic_batch(2, A, seed=5)["obs"]
+    for i in range(2):
+        a = fresh.act(obs[i].numpy(), 5000, True)
+        want = o64.act(obs[i], 5000, True)[0].numpy()
+        assert np.abs(a - want).max() < 2e-2
