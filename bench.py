@@ -129,7 +129,7 @@ def run_ours(args, rank, world):
     torch.manual_seed(rank)                       # ensemble member = independent seed
     np.random.seed(7 + rank)
     agent = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
-                       use_cuda_graph=True, seed=rank)
+                       use_cuda_graph=True, seed=rank, mode=args.mode)
     key = f"/bench/ring{rank}"
     fill_ring(key, A, args.episodes, 501, dev, seed=1 + rank)
     loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
@@ -224,9 +224,22 @@ def run_ours(args, rank, world):
         s = torch.cuda.current_stream().cuda_stream
         pe = lambda k: agent._p("encoder", k)
         ge = lambda k: agent._g("encoder", k)
-        acts = [a.data_ptr() for a in ws.acts]
-        d = [t.data_ptr() for t in ws.dpre]
-        cand = {
+        if args.mode == "bf16":
+            bw, st = agent.bf16_workspace(B), agent._bf16
+            acts = [a.data_ptr() for a in bw.acts]
+            d = [t.data_ptr() for t in bw.dpre]
+            cand = {
+                "conv3x3_tc_kernel<fwd>(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, s),
+                                                        2 * CONV_MACS[39] * 2 * B),
+                "conv3x3_tc_kernel<dgrad>(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_bf16", d[1], st.conv_wd[0].data_ptr(), acts[0], 2 * B, d[0], B, 39, s),
+                                                         2 * CONV_MACS[39] * B),
+                "conv3x3_wgrad_tc_kernel(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_bf16", acts[0], 2 * B, d[1], bw.wg_ws.data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
+                                                        2 * CONV_MACS[39] * B),
+            }
+        else:
+            acts = [a.data_ptr() for a in ws.acts]
+            d = [t.data_ptr() for t in ws.dpre]
+        cand = cand if args.mode == "bf16" else {
             "conv3x3_fwd_f32(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_f32", acts[0], pe("convnet.2.weight"), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, s),
                                               2 * CONV_MACS[39] * 2 * B),
             "conv3x3_dgrad_f32(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_f32", d[1], pe("convnet.2.weight"), acts[0], d[0], B, 39, s),
@@ -247,14 +260,15 @@ def run_ours(args, rank, world):
         cpu = cpu_baseline(args, steps=2)
         out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16" if args.mode == "bf16" else "f32",
                "data": "synthetic",
                "config": {"workload": f"configs[1]: walker_walk-shape agent.update, B={B}, 9x84x84 u8 stacks, A={A}, "
                                       f"F={Fd}, H={H}, n-step 3, GPU-resident replay ring ({args.episodes} episodes x 501 "
-                                      "rows), CUDA-graphed, fp32 parity mode" + (f"; {world} independent agents (ensemble), one per GPU" if world > 1 else ""),
+                                      f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; {world} independent agents (ensemble), one per GPU" if world > 1 else ""),
                           "l2": "inputs larger than L2: each step gathers a fresh 32.5 MB batch from a "
                                 f"{args.episodes * 501 * 21168 / 1e6:.0f} MB ring and streams ~700 MB of activations",
-                          "mode": "fp32"},
+                          "mode": args.mode},
                "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": launches_per_update * args.steps, "launches_per_update": launches_per_update,
                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
@@ -311,6 +325,7 @@ def main():
     ap.add_argument("--feature-dim", type=int, default=50)
     ap.add_argument("--hidden-dim", type=int, default=1024)
     ap.add_argument("--episodes", type=int, default=64)
+    ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -29,9 +29,9 @@ def pad8(n):
 
 def splitk_for(m_rows, K=REPR_DIM, target_blocks=148):
     mblocks = (m_rows + 127) // 128
-    s0 = max(1, min(target_blocks // mblocks, K // 64))
+    s0 = max(1, min(target_blocks // mblocks, K // 128))
     chunk = -(-K // s0)
-    chunk = -(-chunk // 64) * 64
+    chunk = -(-chunk // 128) * 128
     return -(-K // chunk)
 
 
@@ -48,10 +48,13 @@ class PackedNet:
 
     def __init__(self, entries, dev):
         # entries: name -> (src_off_floats, rows, cols, ld, nhwc)
-        self.off, rows_tbl, total = {}, [], 0
+        self.off, rows_tbl, total, self.trunk = {}, [], 0, None
         for name, (src, rows, cols, ld, nhwc) in entries.items():
             self.off[name] = total
-            rows_tbl.append([src, total, rows, cols, ld, nhwc])
+            if nhwc:
+                self.trunk = (src, total, rows)        # packed by the transposing kernel
+            else:
+                rows_tbl.append([src, total, rows, cols, ld, nhwc])
             total += pad8(rows) * ld + 64          # row padding: MN-major reads of 8-row units stay in bounds
         self.buf = torch.zeros(total + 64, dtype=torch.bfloat16, device=dev)
         self.table = torch.tensor(rows_tbl, dtype=torch.int64, device=dev)
@@ -62,6 +65,9 @@ class PackedNet:
 
     def repack(self, src_ptr):
         call("drq_pack_table_bf16", src_ptr, self.buf.data_ptr(), self.table.data_ptr(), self.n, _stream())
+        if self.trunk is not None:
+            src, dst, rows = self.trunk
+            call("drq_pack_trunk_bf16", src_ptr + F32 * src, self.buf.data_ptr() + BF * dst, rows, _stream())
 
 
 class Bf16State:

@@ -52,6 +52,7 @@ SIGNATURES = {
     "drq_q_head_fwd_bf16": [P, P, P, P, I, I, I, L, P],
     "drq_q_head_bwd_bf16": [P, P, P, P, P, P, I, I, I, L, P],
     "drq_pack_table_bf16": [P, P, P, I, P],
+    "drq_pack_trunk_bf16": [P, P, I, P],
     "drq_critic_loss": [P, P, P, P, P, P, P, P, P, P, I, P],
     "drq_actor_loss": [P, P, P, P, P, I, P],
     "drq_copy2d_f32": [P, L, P, L, I, I, P],

@@ -36,29 +36,76 @@ struct Conv1TcArgs {
     int n_images;
 };
 
-// one builder thread: position r of the tile, K range [K0, K0+48)
+// Input rows of one tile staged in shared memory: per channel the contiguous byte range of the
+// (clamped) source rows [rlo, rhi], at most 11 rows x 84 B = 231 words.
+constexpr int kC1RowWords = kImg / 4;                 // 21
+constexpr int kC1ChWords = 11 * kC1RowWords;          // 231
+constexpr int kC1ChBytes = 928;                       // 231 words padded to 16 B
+constexpr int kC1StageWords = 10;                     // ceil(10 ch * 231 / 256) words per builder thread (cin <= 10)
+constexpr int kC1InBytes = 10 * kC1ChBytes;           // one staging buffer
+
+struct TileGeom { int n, p0, rlo, nrows; };
+
+__device__ __forceinline__ TileGeom tile_geom(int t, const int* __restrict__ shift, int pad) {
+    constexpr int TILES_PER_IMG = (kPW * kPW + kC1Tile - 1) / kC1Tile;
+    TileGeom g;
+    g.n = t / TILES_PER_IMG;
+    g.p0 = (t - g.n * TILES_PER_IMG) * kC1Tile;
+    const int sy = shift ? shift[2 * g.n + 1] : pad;
+    const int oy_min = g.p0 / kPW;
+    const int oy_max = min(g.p0 + kC1Tile - 1, kPW * kPW - 1) / kPW;
+    g.rlo = clampi(2 * oy_min + sy - pad, 0, kImg - 1);
+    const int rhi = clampi(2 * oy_max + 2 + sy - pad, 0, kImg - 1);
+    g.nrows = rhi - g.rlo + 1;
+    return g;
+}
+
+// each builder thread fetches up to kC1StageWords 4-byte words of the tile's input rows
+__device__ __forceinline__ void fetch_rows(uint32_t (&regs)[kC1StageWords], const uint8_t* __restrict__ obs,
+                                           const TileGeom& g, int cin, int b) {
+    const uint32_t* img = reinterpret_cast<const uint32_t*>(obs + (long long)g.n * cin * kImg * kImg);
+    const int nwords = g.nrows * kC1RowWords;
+#pragma unroll
+    for (int i = 0; i < kC1StageWords; ++i) {
+        const int w = b + 256 * i;
+        const int ci = w / kC1ChWords, j = w - ci * kC1ChWords;
+        regs[i] = (ci < cin && j < nwords) ? __ldg(img + ci * (kImg * kImg / 4) + g.rlo * kC1RowWords + j) : 0u;
+    }
+}
+__device__ __forceinline__ void store_rows(const uint32_t (&regs)[kC1StageWords], uint8_t* stage, int b) {
+#pragma unroll
+    for (int i = 0; i < kC1StageWords; ++i) {
+        const int w = b + 256 * i;
+        const int ci = w / kC1ChWords, j = w - ci * kC1ChWords;
+        if (ci < 10) *reinterpret_cast<uint32_t*>(stage + ci * kC1ChBytes + 4 * j) = regs[i];
+    }
+}
+
+// one builder thread: position r of the tile, K range [K0, K0+48); pixels come from the staged
+// rows, the u8 -> bf16(x/255 - 0.5) map (drqv2.py:64) from a 256-entry table
 template <int K0>
-__device__ __forceinline__ void build_half(uint8_t* tile, const uint8_t* __restrict__ img, int cin, int r,
-                                           bool valid, const int (&off9)[9]) {
+__device__ __forceinline__ void build_half(uint8_t* tile, const uint8_t* __restrict__ stage,
+                                           const uint16_t* __restrict__ lut, int cin, int r, bool valid,
+                                           const int (&off9)[9]) {
     const int kmax = cin * 9;
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float f[2];
+            uint32_t hv[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = K0 + u * 8 + e * 2 + h;
                 const int ci = k / 9, t = k % 9;
-                float v = 0.f;
+                uint32_t v = 0;
                 if (valid) {
-                    if (k < kmax) v = __fsub_rn(__fdiv_rn((float)img[ci * (kImg * kImg) + off9[t]], 255.0f), 0.5f);
-                    else if (k == kmax) v = 1.0f;
+                    if (k < kmax) v = lut[stage[ci * kC1ChBytes + off9[t]]];
+                    else if (k == kmax) v = 0x3F80u;       // bf16 1.0: the bias-gradient column
                 }
-                f[h] = v;
+                hv[h] = v;
             }
-            w[e] = pack_bf16x2(f[0], f[1]);
+            w[e] = hv[0] | (hv[1] << 16);
         }
         *reinterpret_cast<uint4*>(tile + (K0 / 8 + u) * (kC1Tile * 16) + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -69,7 +116,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int STAGE = kC1ABytes + (WGRAD ? kC1DBytes : 0);
     uint8_t* w_s = smem;                                    // fwd only
-    uint8_t* st_s = smem + kC1WBytes;
+    uint8_t* in_s = smem + kC1WBytes;                       // 2 x staged input rows
+    uint16_t* lut_s = reinterpret_cast<uint16_t*>(in_s + 2 * kC1InBytes);
+    uint8_t* st_s = in_s + 2 * kC1InBytes + 512;
     uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kC1Stages * STAGE + (WGRAD ? kC1DBytes : 0));
     uint64_t* full = bars;                     // builders (256 arrivals) [+ d-tile tx in wgrad: separate barrier]
     uint64_t* empty = bars + kC1Stages;
@@ -88,6 +137,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
         uint4* dst = reinterpret_cast<uint4*>(w_s);
         for (int i = threadIdx.x; i < kC1WBytes / 16; i += kC1Threads) dst[i] = __ldg(src + i);
     }
+    if (threadIdx.x < 256)
+        lut_s[threadIdx.x] = __bfloat16_as_ushort(__float2bfloat16_rn(
+            __fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f)));          // drqv2.py:64, then bf16
     if (threadIdx.x == 0) {
         for (int i = 0; i < kC1Stages; ++i) { mbar_init(full + i, 256); mbar_init(empty + i, 1); mbar_init(dfull + i, 1); }
         for (int i = 0; i < kC1Acc; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
@@ -107,28 +159,40 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     if (warp < 8) {
         // ------------------------------------------------ im2col builders
         const int b = threadIdx.x, r = b & 127, half = b >> 7;
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0; uint32_t phase = 0; int buf = 0;
+        uint32_t regs[kC1StageWords];
+        TileGeom g = tile_geom(blockIdx.x, a.shift, a.pad);
+        if ((int)blockIdx.x < total_tiles) fetch_rows(regs, a.obs, g, a.cin, b);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int n = t / TILES_PER_IMG, p0 = (t - n * TILES_PER_IMG) * kC1Tile;
-            const int p = p0 + r;
+            uint8_t* stg = in_s + buf * kC1InBytes;
+            store_rows(regs, stg, b);
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // staged rows visible to all builders
+            const TileGeom cur = g;
+            const int tn = t + gridDim.x;
+            if (tn < total_tiles) {                              // prefetch the next tile's rows (in flight during the build)
+                g = tile_geom(tn, a.shift, a.pad);
+                fetch_rows(regs, a.obs, g, a.cin, b);
+            }
+            const int p = cur.p0 + r;
             const bool valid = p < kPW * kPW;
             const int oy = p / kPW, ox = p - oy * kPW;
-            const int sx = a.shift ? a.shift[2 * n] : a.pad, sy = a.shift ? a.shift[2 * n + 1] : a.pad;
+            const int sx = a.shift ? a.shift[2 * cur.n] : a.pad, sy = a.shift ? a.shift[2 * cur.n + 1] : a.pad;
             int off9[9];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                const int sr = clampi(2 * oy + ky + sy - a.pad, 0, kImg - 1);
+                const int sr = clampi(2 * oy + ky + sy - a.pad, 0, kImg - 1) - cur.rlo;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) off9[ky * 3 + kx] = sr * kImg + clampi(2 * ox + kx + sx - a.pad, 0, kImg - 1);
+                for (int kx = 0; kx < 3; ++kx)
+                    off9[ky * 3 + kx] = valid ? sr * kImg + clampi(2 * ox + kx + sx - a.pad, 0, kImg - 1) : 0;
             }
-            const uint8_t* img = a.obs + (long long)n * a.cin * kImg * kImg;
             mbar_wait(empty + stage, phase ^ 1);
             uint8_t* tile = st_s + stage * STAGE;
-            if (half == 0) build_half<0>(tile, img, a.cin, r, valid, off9);
-            else           build_half<48>(tile, img, a.cin, r, valid, off9);
+            if (half == 0) build_half<0>(tile, stg, lut_s, a.cin, r, valid, off9);
+            else           build_half<48>(tile, stg, lut_s, a.cin, r, valid, off9);
             fence_proxy_async();
             mbar_arrive(full + stage);
             if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+            buf ^= 1;
         }
     } else if (warp == 8) {
         // ------------------------------------------------ UMMA issuer (+ d-tile producer in wgrad)
@@ -271,9 +335,9 @@ __global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int
     if (k < cin * 9) dw[co * cin * 9 + k] = s; else db[co] = s;
 }
 
-constexpr size_t kConv1FwdSmem = kC1WBytes + kC1Stages * kC1ABytes + (3 * kC1Stages + 2 * kC1Acc + 1) * 8 + 16;
+constexpr size_t kConv1FwdSmem = kC1WBytes + 2 * kC1InBytes + 512 + kC1Stages * kC1ABytes + (3 * kC1Stages + 2 * kC1Acc + 1) * 8 + 16;
 // wgrad: + one extra d-tile worth of tail padding (rows 32..63 of the M=64 operand read 4 blocks past the tile)
-constexpr size_t kConv1WgSmem = kC1WBytes + kC1Stages * (kC1ABytes + kC1DBytes) + kC1DBytes +
+constexpr size_t kConv1WgSmem = kC1WBytes + 2 * kC1InBytes + 512 + kC1Stages * (kC1ABytes + kC1DBytes) + kC1DBytes +
                                 (3 * kC1Stages + 2 * kC1Acc + 1) * 8 + 16;
 
 }  // namespace drq

@@ -16,7 +16,7 @@ namespace drq {
 
 using namespace tc;
 
-constexpr int GT_BM = 128, GT_BK = 64, GT_STAGES = 3, GT_THREADS = 128;
+constexpr int GT_BM = 128, GT_BK = 128, GT_STAGES = 3, GT_LOADERS = 128, GT_THREADS = 160;
 
 struct GemmTcArgs {
     const __nv_bfloat16* A; long long lda; int a_mn;
@@ -34,20 +34,27 @@ struct GemmTcArgs {
 //   K-major : line = row (valid < rows_valid), unit = k/8   (valid while k < k_valid)
 //   MN-major: line = k   (valid < k_valid),    unit = row/8 (valid while row < rows_valid)
 // global unit address = base + line*ld + unit*8 ; smem = unit*(nlines*16) + line*16
+__device__ __forceinline__ void cp_async16(uint8_t* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;      // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int NLINES, int NUNITS>
 __device__ __forceinline__ void stage_tile(uint8_t* smem_tile, const __nv_bfloat16* base, long long ld,
                                            int lines_valid, int units_valid_elems, int tid) {
     constexpr int TOTAL = NLINES * NUNITS;
 #pragma unroll
-    for (int i = 0; i < TOTAL / GT_THREADS; ++i) {
-        const int idx = tid + i * GT_THREADS;
+    for (int i = 0; i < TOTAL / GT_LOADERS; ++i) {
+        const int idx = tid + i * GT_LOADERS;
         const int line_lo = idx & 7;
         const int u = (idx >> 3) % NUNITS;
         const int line = ((idx >> 3) / NUNITS) * 8 + line_lo;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (line < lines_valid && u * 8 < units_valid_elems)
-            v = __ldg(reinterpret_cast<const uint4*>(base + line * ld + u * 8));
-        *reinterpret_cast<uint4*>(smem_tile + u * (NLINES * 16) + line * 16) = v;
+        const bool ok = line < lines_valid && u * 8 < units_valid_elems;
+        cp_async16(smem_tile + u * (NLINES * 16) + line * 16, ok ? (const void*)(base + line * ld + u * 8) : (const void*)base, ok);
     }
 }
 
@@ -86,11 +93,11 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(GemmTcArgs g) {
         c_off = (long long)z * g.bs_c;
     }
     if (tid == 0) {
-        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(full + i, GT_THREADS); mbar_init(empty + i, 1); }
+        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(full + i, GT_LOADERS); mbar_init(empty + i, 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == 4) {
         tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
         tmem_relinquish();
     }
@@ -99,25 +106,44 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(GemmTcArgs g) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = make_idesc_bf16(GT_BM, BN, g.a_mn != 0, g.b_mn != 0);
-
     const int nk = (k_end - k_begin + GT_BK - 1) / GT_BK;
-    int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < nk; ++kb) {
-        const int k0 = k_begin + kb * GT_BK;
-        const int kv = k_end - k0;                      // valid k in this block (may exceed BK)
-        mbar_wait(empty + stage, phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE;
-        uint8_t* sb = sa + A_BYTES;
-        if (!g.a_mn) stage_tile<GT_BM, GT_BK / 8>(sa, A + (long long)m0 * g.lda + k0, g.lda, g.M - m0, kv, tid);
-        else         stage_tile<GT_BK, GT_BM / 8>(sa, A + (long long)k0 * g.lda + m0, g.lda, kv, g.M - m0, tid);
-        if (!g.b_mn) stage_tile<BN, GT_BK / 8>(sb, B + (long long)n0 * g.ldb + k0, g.ldb, g.N - n0, kv, tid);
-        else         stage_tile<GT_BK, BN / 8>(sb, B + (long long)k0 * g.ldb + n0, g.ldb, kv, g.N - n0, tid);
-        fence_proxy_async();            // my generic-proxy smem writes -> visible to the UMMA (async proxy)
-        mbar_arrive(full + stage);
-        if (tid == 0) {
-            mbar_wait(full + stage, phase);
+
+    if (warp < 4) {
+        // ------------------------------------------------ loaders: cp.async straight into the UMMA layout,
+        // GT_STAGES-1 stages of loads in flight per thread
+        auto issue = [&](int kb) {
+            const int st = kb % GT_STAGES;
+            const int k0 = k_begin + kb * GT_BK;
+            const int kv = k_end - k0;
+            uint8_t* sa = smem + st * STAGE;
+            uint8_t* sb = sa + A_BYTES;
+            if (!g.a_mn) stage_tile<GT_BM, GT_BK / 8>(sa, A + (long long)m0 * g.lda + k0, g.lda, g.M - m0, kv, tid);
+            else         stage_tile<GT_BK, GT_BM / 8>(sa, A + (long long)k0 * g.lda + m0, g.lda, kv, g.M - m0, tid);
+            if (!g.b_mn) stage_tile<BN, GT_BK / 8>(sb, B + (long long)n0 * g.ldb + k0, g.ldb, g.N - n0, kv, tid);
+            else         stage_tile<GT_BK, BN / 8>(sb, B + (long long)k0 * g.ldb + n0, g.ldb, kv, g.N - n0, tid);
+        };
+        for (int kb = 0; kb < GT_STAGES - 1; ++kb) {
+            if (kb < nk) issue(kb);
+            cp_async_commit();
+        }
+        for (int kb = 0; kb < nk; ++kb) {
+            const int nxt = kb + GT_STAGES - 1;
+            if (nxt < nk) {
+                mbar_wait(empty + nxt % GT_STAGES, ((nxt / GT_STAGES) & 1) ^ 1);
+                issue(nxt);
+            }
+            cp_async_commit();
+            cp_async_wait<GT_STAGES - 1>();      // the group of k-block kb has landed
+            fence_proxy_async();                 // generic-proxy writes -> visible to the UMMA (async proxy)
+            mbar_arrive(full + kb % GT_STAGES);
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------ UMMA issuer
+        for (int kb = 0; kb < nk; ++kb) {
+            const int st = kb % GT_STAGES;
+            mbar_wait(full + st, (kb / GT_STAGES) & 1);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+            const uint32_t a_addr = smem_u32(smem + st * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
             for (int ks = 0; ks < GT_BK / 16; ++ks) {
                 const uint64_t da = g.a_mn ? make_smem_desc(a_addr + ks * 256, 128, GT_BK * 16)
@@ -126,10 +152,16 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(GemmTcArgs g) {
                                            : make_smem_desc(b_addr + ks * 2 * BN * 16, BN * 16, 128);
                 umma_bf16(tmem_base, da, db, idesc, (kb | ks) ? 1u : 0u);
             }
-            umma_commit(empty + stage);
+            umma_commit(empty + st);
             if (kb == nk - 1) umma_commit(done);
         }
-        if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (warp >= 4) {
+        // the issuer warp takes no part in the epilogue; it only frees TMEM at the end
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 4) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        return;
     }
     mbar_wait(done, 0);
     tc_fence_after();
@@ -209,7 +241,6 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(GemmTcArgs g) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
 template <int BN>

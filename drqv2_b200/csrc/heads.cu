@@ -26,7 +26,17 @@ ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_str
         const int f = lane + 32 * i;
         float v = 0.f;
         if (f < F) {
-            for (int s = 0; s < S; ++s) v += partial[s * split_stride + (long long)row * F + f];
+            const float* pp = partial + (long long)row * F + f;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;      // fixed association: 4 interleaved chains
+            int s = 0;
+            for (; s + 4 <= S; s += 4) {
+                v0 += pp[(s + 0) * split_stride];
+                v1 += pp[(s + 1) * split_stride];
+                v2 += pp[(s + 2) * split_stride];
+                v3 += pp[(s + 3) * split_stride];
+            }
+            for (; s < S; ++s) v0 += pp[s * split_stride];
+            v = (v0 + v1) + (v2 + v3);
             v += bias[f];
         }
         z[i] = v;
@@ -281,31 +291,63 @@ q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, const float* __restrict_
     if (lane == 0) q[(long long)z * B + row] = s + b3[z * w_stride];
 }
 
-// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0)  (bf16);  block (x = k chunk of 256, y = head)
-// optionally dw3[z][k] = sum_b dq[z][b] * c2[z][b][k] and db3[z] = sum_b dq[z][b]
+// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0)  (bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
+// and db3[z] = sum_b dq[z][b].  block = 32 k x 8 row lanes; grid (H/32, heads); fixed-order reduce.
 __global__ void __launch_bounds__(256)
 q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict__ c2,
                   const float* __restrict__ w3, __nv_bfloat16* __restrict__ dc2, float* __restrict__ dw3,
                   float* __restrict__ db3, int B, int H, long long w_stride) {
+    __shared__ float red[8][33];
     const int z = blockIdx.y;
-    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + tx;
     const float* dqz = dq + (long long)z * B;
+    float acc = 0.f;
     if (k < H) {
         const float w = w3[z * w_stride + k];
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) {
+#pragma unroll 4
+        for (int b = ty; b < B; b += 8) {
             const long long o = ((long long)z * B + b) * H + k;
             const float a = __bfloat162float(c2[o]);
             const float g = dqz[b];
             dc2[o] = __float2bfloat16_rn(a > 0.f ? g * w : 0.f);
             acc = fmaf(g, a, acc);
         }
-        if (dw3) dw3[z * w_stride + k] = acc;
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (dw3 && ty == 0 && k < H) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += red[r][tx];
+        dw3[z * w_stride + k] = t;
     }
     if (db3 && blockIdx.x == 0 && threadIdx.x == 0) {
         float s = 0.f;
         for (int b = 0; b < B; ++b) s += dqz[b];
         db3[z * w_stride] = s;
+    }
+}
+
+// trunk weight fp32 [rows][32*1225] (reference NCHW-flatten columns c*1225+yx) -> bf16 [rows][1225*32]
+// (NHWC columns yx*32+c): a 32x32 shared-memory transpose per tile so both sides are coalesced
+__global__ void __launch_bounds__(256)
+pack_trunk_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int r = blockIdx.y, yx0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* wr = w + (long long)r * DRQ_REPR_DIM;
+    __nv_bfloat16* orow = out + (long long)r * DRQ_REPR_DIM;
+#pragma unroll
+    for (int c = ty; c < 32; c += 8) {
+        const int yx = yx0 + tx;
+        tile[c][tx] = yx < 1225 ? wr[c * 1225 + yx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const int yx = yx0 + i;
+        if (yx < 1225) orow[yx * 32 + tx] = __float2bfloat16_rn(tile[tx][i]);
     }
 }
 
@@ -419,10 +461,17 @@ int drq_q_head_fwd_bf16(const uint16_t* c2, const float* w3, const float* b3, fl
 int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, const float* w3, uint16_t* dc2, float* dw3,
                         float* db3, int B, int H, int heads, int64_t w_stride, void* stream) {
     DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && heads > 0, "q_head_bwd: bad args");
-    q_head_bwd_kernel<<<dim3((H + 255) / 256, heads), 256, 0, as_stream(stream)>>>(
+    q_head_bwd_kernel<<<dim3((H + 31) / 32, heads), 256, 0, as_stream(stream)>>>(
         dq, reinterpret_cast<const __nv_bfloat16*>(c2), w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3, db3, B, H,
         w_stride);
     return check_launch("q_head_bwd_kernel");
+}
+
+int drq_pack_trunk_bf16(const float* w, uint16_t* out, int rows, void* stream) {
+    DRQ_REQUIRE(w && out && rows > 0, "pack_trunk: bad args");
+    pack_trunk_kernel<<<dim3((1225 + 31) / 32, rows), 256, 0, as_stream(stream)>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(out));
+    return check_launch("pack_trunk_kernel");
 }
 
 int drq_pack_table_bf16(const float* src, uint16_t* dst, const int64_t* table, int n_entries, void* stream) {

@@ -317,6 +317,8 @@ int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, const float* w3, ui
 /* table-driven fp32 -> bf16 packing of nn.Linear weights after an optimiser step.  table (device,
  * int64 [n][6]): src offset (floats), dst offset (bf16 elements), rows, cols, ld, nhwc_permute. */
 int drq_pack_table_bf16(const float* src, uint16_t* dst, const int64_t* table, int n_entries, void* stream);
+/* trunk Linear(39200->rows) weight: fp32 reference order -> bf16 NHWC feature order (coalesced transpose) */
+int drq_pack_trunk_bf16(const float* w, uint16_t* out, int rows, void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 
