@@ -38,7 +38,8 @@ struct ConvTcArgs {
     const float* bias;                              // fwd
     const __nv_bfloat16* mask; long long cs_mask;   // dgrad: input activation (WB)
     __nv_bfloat16* out; long long cs_out;
-    int n_images, ntiles, n_pos, w_valid, nhwc_out;
+    int n_images, ntiles, n_pos, w_valid, nhwc_out;   // nhwc_out: 0 WB, 1 compact NHWC, 2 FB features
+    long long feat_rpad;
 };
 
 template <bool DGRAD>
@@ -52,9 +53,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
     uint64_t* tfull = bars + 2 * kStagesTC;
     uint64_t* tempty = bars + 2 * kStagesTC + kAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesTC + 2 * kAccStages);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = a.n_images * a.ntiles;
+    if (!DGRAD && threadIdx.x < 32) bias_s[threadIdx.x] = a.bias[threadIdx.x];
 
     // packed weights -> smem (same byte layout)
     {
@@ -129,6 +132,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+            const int p = p0 + q * 32 + lane;
+            const long long row = (long long)n * kPLB + kGuard + p;
+            uint4 mk[4];
+            if (DGRAD && p < a.n_pos) {       // ReLU-mask loads in flight while the accumulator is being produced
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mk[c] = __ldg(reinterpret_cast<const uint4*>(a.mask + (c * a.cs_mask + row) * 8));
+            }
             mbar_wait(tfull + acc, acc_phase);
             tc_fence_after();
             float v[32];
@@ -138,17 +148,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
             if (lane == 0) mbar_arrive(tempty + acc);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
-            const int p = p0 + q * 32 + lane;
             if (p >= a.n_pos) continue;
             const int y = p / kPW, x = p - y * kPW;
-            const long long row = (long long)n * kPLB + kGuard + p;
             uint32_t packed[16];
             if (!DGRAD) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float lo = fmaxf(v[2 * i] + __ldg(a.bias + 2 * i), 0.f);
-                    const float hi = fmaxf(v[2 * i + 1] + __ldg(a.bias + 2 * i + 1), 0.f);
+                    const float lo = fmaxf(v[2 * i] + bias_s[2 * i], 0.f);
+                    const float hi = fmaxf(v[2 * i + 1] + bias_s[2 * i + 1], 0.f);
                     packed[i] = pack_bf16x2(lo, hi);
+                }
+                if (a.nhwc_out == 2) {
+                    // FB feature matrix: unit (y*w + x)*4 + c/8, row = image
+                    if (x < a.w_valid) {
+                        const long long u0 = ((long long)y * a.w_valid + x) * 4;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(a.out + ((u0 + c) * a.feat_rpad + n) * 8) =
+                                make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                    }
+                    continue;
                 }
                 if (a.nhwc_out) {
                     if (x < a.w_valid) {
@@ -163,8 +182,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
                 const bool col_ok = x < a.w_valid;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.mask + (c * a.cs_mask + row) * 8));
-                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                    const uint32_t mw[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float lo = (col_ok && bf16_lo(mw[j]) > 0.f) ? v[8 * c + 2 * j] : 0.f;
@@ -341,7 +359,7 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G,
 // past the staged window (results ignored) and must stay inside the allocation
 constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * kWgStages + 1) * 8 + 16 + kStageBytes;
 
-constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16;
+constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16 + 128;
 
 static int conv_tc_grid(int total_tiles) {
     const int sms = 148;
@@ -364,7 +382,7 @@ int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, voi
 }
 
 int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out, int N,
-                         int hout, int nhwc_out, void* stream) {
+                         int hout, int nhwc_out, int64_t feat_rpad, void* stream) {
     DRQ_REQUIRE(in && w_fwd && bias && out, "conv3x3_fwd_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && hout > 0 && hout <= kPW - 2, "conv3x3_fwd_bf16: bad dims");
     if (int rc = ensure_smem((const void*)conv3x3_tc_kernel<false>, kConvTcSmem, "conv3x3_fwd_bf16")) return rc;
@@ -380,6 +398,8 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.ntiles = (a.n_pos + kTM - 1) / kTM;
     a.w_valid = hout;
     a.nhwc_out = nhwc_out;
+    a.feat_rpad = feat_rpad;
+    DRQ_REQUIRE(nhwc_out != 2 || feat_rpad >= N, "conv3x3_fwd_bf16: FB feature rpad < N");
     conv3x3_tc_kernel<false><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
     return check_launch("conv3x3_tc_kernel<fwd>");
 }

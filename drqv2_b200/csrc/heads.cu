@@ -9,13 +9,18 @@ namespace drq {
 
 constexpr int kMaxFPerLane = 8;  // F <= 256
 
+// feature-blocked (FB) bf16 layout of the tensor-core heads: element (row, f) of X_fb[f/8][row][8]
+__device__ __forceinline__ long long fb_index(int f, long long row, long long rpad) {
+    return ((long long)(f >> 3) * rpad + row) * 8 + (f & 7);
+}
+
 // one warp per row
 __global__ void __launch_bounds__(128)
 ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_stride,
                    const float* __restrict__ bias, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ h_out, long long ld_h,
                    float* __restrict__ xhat, float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ h_bf,
-                   long long ld_hb, int B, int F, float eps) {
+                   long long rpad_hb, int B, int F, float eps) {
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -60,7 +65,7 @@ ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_str
             const float y = xh * gamma[f] + beta[f];
             const float hv = tanhf(y);
             h_out[(long long)row * ld_h + f] = hv;
-            if (h_bf) h_bf[(long long)row * ld_hb + f] = __float2bfloat16_rn(hv);
+            if (h_bf) h_bf[fb_index(f, row, rpad_hb)] = __float2bfloat16_rn(hv);
             if (xhat) xhat[(long long)row * F + f] = xh;
         }
     }
@@ -74,7 +79,7 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
                        long long ld_h, const float* __restrict__ xhat,
                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                        float* __restrict__ dz, float* __restrict__ dy_out, __nv_bfloat16* __restrict__ dz_bf,
-                       long long ld_zb, int B, int F) {
+                       long long rpad_zb, int B, int F) {
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -102,7 +107,7 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
         if (f < F) {
             const float g = r * (dxh[i] - m1 - xh[i] * m2);
             dz[(long long)row * F + f] = g;
-            if (dz_bf) dz_bf[(long long)row * ld_zb + f] = __float2bfloat16_rn(g);
+            if (dz_bf) dz_bf[fb_index(f, row, rpad_zb)] = __float2bfloat16_rn(g);
         }
     }
 }
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(256)
 actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ eps,
                     const float* __restrict__ std_dev, float clip, float* __restrict__ action_out,
                     long long ld_a, float* __restrict__ mu_out, float* __restrict__ metrics,
-                    __nv_bfloat16* __restrict__ a_bf, long long ld_ab, int B, int A) {
+                    __nv_bfloat16* __restrict__ a_bf, long long rpad_ab, int feat_off, int B, int A) {
     __shared__ float sh[256];
     const float std = std_dev ? *std_dev : 0.f;
     const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;  // utils.py:113 (python: -1.0 + 1e-6 -> fp32)
@@ -167,7 +172,7 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
                 lp += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
             }
             action_out[(long long)b * ld_a + j] = a;
-            if (a_bf) a_bf[(long long)b * ld_ab + j] = __float2bfloat16_rn(a);
+            if (a_bf) a_bf[fb_index(feat_off + j, b, rpad_ab)] = __float2bfloat16_rn(a);
             if (mu_out) mu_out[(long long)b * A + j] = mu;
         }
         lp_sum += lp;
@@ -183,14 +188,14 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
 
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long ld_da,
                                         const float* __restrict__ mu, float* __restrict__ dmu_pre,
-                                        __nv_bfloat16* __restrict__ dmu_bf, long long ld_mb, int B, int A) {
+                                        __nv_bfloat16* __restrict__ dmu_bf, long long rpad_mb, int B, int A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * A) return;
     const int b = i / A, j = i - b * A;
     const float m = mu[i];
     const float g = da[(long long)b * ld_da + j] * (1.0f - m * m);
     dmu_pre[i] = g;
-    if (dmu_bf) dmu_bf[(long long)b * ld_mb + j] = __float2bfloat16_rn(g);
+    if (dmu_bf) dmu_bf[fb_index(j, b, rpad_mb)] = __float2bfloat16_rn(g);
 }
 
 __global__ void __launch_bounds__(256)
@@ -242,131 +247,117 @@ actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
     if (metrics && threadIdx.x == 0) metrics[0] = -(t / (float)B);   // drqv2.py:216
 }
 
-// ---------------------------------------------------------------- bf16-mode helpers
-__global__ void copy2d_f32_bf16_kernel(const float* __restrict__ src, long long ld_src,
-                                       __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows, int cols) {
+// ---------------------------------------------------------------- bf16-mode helpers (FB layout)
+__global__ void scatter_fb_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                  long long rpad, int feat_off, int rows, int cols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int r = i / cols, c = i - r * cols;
-    dst[r * ld_dst + c] = __float2bfloat16_rn(src[r * ld_src + c]);
+    dst[fb_index(feat_off + c, r, rpad)] = __float2bfloat16_rn(src[r * ld_src + c]);
 }
 
-// out[z][n] = sum_m X[z][m][n] for a bf16 matrix (bias gradients of the hidden layers)
+// out[z][8u..8u+7] = sum_b X_fb[z][u][b][0..7]; one block per unit, fixed-order tree over 256 threads
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ld, float* __restrict__ out, int M, int N,
-                   long long bs_x, long long bs_out) {
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + tx;
-    const __nv_bfloat16* Xz = X + blockIdx.y * bs_x;
-    float s = 0.f;
-    if (n < N)
-        for (int m = ty; m < M; m += 8) s += __bfloat162float(Xz[m * ld + n]);
-    red[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0 && n < N) {
-        float t = red[0][tx];
+colsum_fb_kernel(const __nv_bfloat16* __restrict__ X, long long rpad, float* __restrict__ out, int M, int N,
+                 long long bs_x, long long bs_out) {
+    __shared__ float red[256][9];
+    const int u = blockIdx.x, z = blockIdx.y;
+    const __nv_bfloat16* Xu = X + z * bs_x + (long long)u * rpad * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < M; b += 256) {
+        const uint4 v = *reinterpret_cast<const uint4*>(Xu + (long long)b * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int r = 1; r < 8; ++r) t += red[r][tx];
-        out[blockIdx.y * bs_out + n] = t;
-    }
-}
-
-// q[z][b] = c2[z][b][:] . w3[z][:] + b3[z]   (the Linear(hidden, 1) of drqv2.py:106,111); warp per row
-__global__ void __launch_bounds__(128)
-q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, const float* __restrict__ w3,
-                  const float* __restrict__ b3, float* __restrict__ q, int B, int H, long long w_stride) {
-    const int z = blockIdx.y;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= B) return;
-    const __nv_bfloat16* x = c2 + ((long long)z * B + row) * H;
-    const float* w = w3 + z * w_stride;
-    float s = 0.f;
-    for (int k = lane * 2; k < H; k += 64) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + k);
-        s = fmaf(__bfloat162float(v.x), w[k], s);
-        s = fmaf(__bfloat162float(v.y), w[k + 1], s);
-    }
-    s = warp_sum(s);
-    if (lane == 0) q[(long long)z * B + row] = s + b3[z * w_stride];
-}
-
-// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0)  (bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
-// and db3[z] = sum_b dq[z][b].  block = 32 k x 8 row lanes; grid (H/32, heads); fixed-order reduce.
-__global__ void __launch_bounds__(256)
-q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict__ c2,
-                  const float* __restrict__ w3, __nv_bfloat16* __restrict__ dc2, float* __restrict__ dw3,
-                  float* __restrict__ db3, int B, int H, long long w_stride) {
-    __shared__ float red[8][33];
-    const int z = blockIdx.y;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int k = blockIdx.x * 32 + tx;
-    const float* dqz = dq + (long long)z * B;
-    float acc = 0.f;
-    if (k < H) {
-        const float w = w3[z * w_stride + k];
-#pragma unroll 4
-        for (int b = ty; b < B; b += 8) {
-            const long long o = ((long long)z * B + b) * H + k;
-            const float a = __bfloat162float(c2[o]);
-            const float g = dqz[b];
-            dc2[o] = __float2bfloat16_rn(a > 0.f ? g * w : 0.f);
-            acc = fmaf(g, a, acc);
+        for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __uint_as_float(w[j] << 16);
+            acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
         }
     }
-    red[ty][tx] = acc;
-    __syncthreads();
-    if (dw3 && ty == 0 && k < H) {
-        float t = red[0][tx];
 #pragma unroll
-        for (int r = 1; r < 8; ++r) t += red[r][tx];
-        dw3[z * w_stride + k] = t;
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + o][j];
+        }
+        __syncthreads();
     }
-    if (db3 && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (threadIdx.x < 8 && u * 8 + threadIdx.x < N) out[z * bs_out + u * 8 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+// q[z][b] = c2[z][b][:] . w3[z][:] + b3[z]   (the Linear(hidden, 1) of drqv2.py:106,111) on an FB
+// activation; thread per row, w3 staged in shared memory
+__global__ void __launch_bounds__(128)
+q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, long long rpad, long long bs_c2,
+                  const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q, int B, int H,
+                  long long w_stride) {
+    extern __shared__ float w_s[];
+    const int z = blockIdx.y;
+    for (int k = threadIdx.x; k < H; k += 128) w_s[k] = w3[z * w_stride + k];
+    __syncthreads();
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= B) return;
+    const __nv_bfloat16* x = c2 + z * bs_c2 + (long long)b * 8;
+    float s0 = 0.f, s1 = 0.f;
+    for (int u = 0; u < H / 8; ++u) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)u * rpad * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s0 = fmaf(__uint_as_float(w[j] << 16), w_s[u * 8 + 2 * j], s0);
+            s1 = fmaf(__uint_as_float(w[j] & 0xFFFF0000u), w_s[u * 8 + 2 * j + 1], s1);
+        }
+    }
+    q[(long long)z * B + b] = (s0 + s1) + b3[z * w_stride];
+}
+
+// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0) (FB bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
+// and db3[z] = sum_b dq[z][b].  One block per 8-feature unit; fixed-order tree.
+__global__ void __launch_bounds__(256)
+q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict__ c2, long long rpad,
+                  long long bs_c2, const float* __restrict__ w3, __nv_bfloat16* __restrict__ dc2,
+                  float* __restrict__ dw3, float* __restrict__ db3, int B, long long w_stride) {
+    __shared__ float red[256][9];
+    const int u = blockIdx.x, z = blockIdx.y;
+    const float* dqz = dq + (long long)z * B;
+    const long long base = z * bs_c2 + (long long)u * rpad * 8;
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = w3[z * w_stride + u * 8 + j];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const uint4 v = *reinterpret_cast<const uint4*>(c2 + base + (long long)b * 8);
+        const uint32_t cw[4] = {v.x, v.y, v.z, v.w};
+        const float g = dqz[b];
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a0 = __uint_as_float(cw[j] << 16), a1 = __uint_as_float(cw[j] & 0xFFFF0000u);
+            acc[2 * j] = fmaf(g, a0, acc[2 * j]);
+            acc[2 * j + 1] = fmaf(g, a1, acc[2 * j + 1]);
+            const __nv_bfloat162 t = __floats2bfloat162_rn(a0 > 0.f ? g * w[2 * j] : 0.f, a1 > 0.f ? g * w[2 * j + 1] : 0.f);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(dc2 + base + (long long)b * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (dw3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + o][j];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < 8) dw3[z * w_stride + u * 8 + threadIdx.x] = red[0][threadIdx.x];
+    }
+    if (db3 && u == 0 && threadIdx.x == 0) {
         float s = 0.f;
         for (int b = 0; b < B; ++b) s += dqz[b];
         db3[z * w_stride] = s;
-    }
-}
-
-// trunk weight fp32 [rows][32*1225] (reference NCHW-flatten columns c*1225+yx) -> bf16 [rows][1225*32]
-// (NHWC columns yx*32+c): a 32x32 shared-memory transpose per tile so both sides are coalesced
-__global__ void __launch_bounds__(256)
-pack_trunk_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
-    __shared__ float tile[32][33];
-    const int r = blockIdx.y, yx0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float* wr = w + (long long)r * DRQ_REPR_DIM;
-    __nv_bfloat16* orow = out + (long long)r * DRQ_REPR_DIM;
-#pragma unroll
-    for (int c = ty; c < 32; c += 8) {
-        const int yx = yx0 + tx;
-        tile[c][tx] = yx < 1225 ? wr[c * 1225 + yx] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = ty; i < 32; i += 8) {
-        const int yx = yx0 + i;
-        if (yx < 1225) orow[yx * 32 + tx] = __float2bfloat16_rn(tile[tx][i]);
-    }
-}
-
-// table-driven fp32 -> bf16 weight packing: entry e = {src_off, dst_off, rows, cols, ld, nhwc}
-__global__ void pack_table_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                  const long long* __restrict__ table) {
-    const long long* e = table + blockIdx.y * 6;
-    const float* w = src + e[0];
-    __nv_bfloat16* out = dst + e[1];
-    const int rows = (int)e[2], cols = (int)e[3], ld = (int)e[4], nhwc = (int)e[5];
-    const long long n = (long long)rows * ld;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / ld), c = (int)(i - (long long)r * ld);
-        float v = 0.f;
-        if (c < cols) {
-            const int cs = nhwc ? ((c & 31) * 1225 + (c >> 5)) : c;
-            v = w[(long long)r * cols + cs];
-        }
-        out[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -378,26 +369,26 @@ extern "C" {
 
 int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
                     const float* gamma, const float* beta, float* h_out, int64_t ld_h, float* xhat,
-                    float* rstd, uint16_t* h_bf16, int64_t ld_hb, int B, int F, float eps, void* stream) {
+                    float* rstd, uint16_t* h_bf16, int64_t rpad_hb, int B, int F, float eps, void* stream) {
     DRQ_REQUIRE(partial && bias && gamma && beta && h_out, "ln_tanh_fwd: null pointer");
     DRQ_REQUIRE(B >= 0 && F > 0 && F <= 32 * kMaxFPerLane && S >= 1, "ln_tanh_fwd: bad dims (F<=256)");
     if (B == 0) return DRQ_OK;
     ln_tanh_fwd_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(
         partial, S, split_stride, bias, gamma, beta, h_out, ld_h, xhat, rstd,
-        reinterpret_cast<__nv_bfloat16*>(h_bf16), ld_hb, B, F, eps);
+        reinterpret_cast<__nv_bfloat16*>(h_bf16), rpad_hb, B, F, eps);
     return check_launch("ln_tanh_fwd_kernel");
 }
 
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, const float* xhat,
                     const float* rstd, const float* gamma, float* dz, float* dgamma, float* dbeta,
-                    uint16_t* dz_bf16, int64_t ld_zb, int B, int F, void* stream) {
+                    uint16_t* dz_bf16, int64_t rpad_zb, int B, int F, void* stream) {
     DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && dgamma && dbeta, "ln_tanh_bwd: null pointer");
     DRQ_REQUIRE(B > 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_bwd: bad dims (F<=256)");
     // dy = dh * tanh' is staged in the second half of the caller's 2*B*F buffer
     float* dy = dz + (long long)B * F;
     ln_tanh_bwd_row_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(dh, ld_dh, h, ld_h, xhat, rstd,
                                                                       gamma, dz, dy,
-                                                                      reinterpret_cast<__nv_bfloat16*>(dz_bf16), ld_zb, B, F);
+                                                                      reinterpret_cast<__nv_bfloat16*>(dz_bf16), rpad_zb, B, F);
     if (int rc = check_launch("ln_tanh_bwd_row_kernel")) return rc;
     ln_param_grad_kernel<<<F, 256, 0, as_stream(stream)>>>(dy, xhat, dgamma, dbeta, B, F);
     return check_launch("ln_param_grad_kernel");
@@ -405,22 +396,22 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
 
 int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev, float clip,
                      float* action_out, int64_t ld_a, float* mu_out, float* metrics, uint16_t* action_bf16,
-                     int64_t ld_ab, int B, int A, void* stream) {
+                     int64_t rpad_ab, int feat_off, int B, int A, void* stream) {
     DRQ_REQUIRE(mu_pre && action_out, "actor_sample: null pointer");
     DRQ_REQUIRE(!(eps && !std_dev), "actor_sample: eps without std");
     DRQ_REQUIRE(B > 0 && A > 0, "actor_sample: bad dims");
     actor_sample_kernel<<<1, 256, 0, as_stream(stream)>>>(mu_pre, eps, std_dev, clip, action_out, ld_a,
                                                           mu_out, metrics,
-                                                          reinterpret_cast<__nv_bfloat16*>(action_bf16), ld_ab, B, A);
+                                                          reinterpret_cast<__nv_bfloat16*>(action_bf16), rpad_ab, feat_off, B, A);
     return check_launch("actor_sample_kernel");
 }
 
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
-                         uint16_t* dmu_bf16, int64_t ld_mb, int B, int A, void* stream) {
+                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, void* stream) {
     DRQ_REQUIRE(daction && mu && dmu_pre && B > 0 && A > 0, "actor_sample_bwd: bad args");
     actor_sample_bwd_kernel<<<(B * A + 255) / 256, 256, 0, as_stream(stream)>>>(daction, ld_da, mu,
                                                                                 dmu_pre,
-                                                                                reinterpret_cast<__nv_bfloat16*>(dmu_bf16), ld_mb, B, A);
+                                                                                reinterpret_cast<__nv_bfloat16*>(dmu_bf16), rpad_mb, B, A);
     return check_launch("actor_sample_bwd_kernel");
 }
 
@@ -434,51 +425,38 @@ int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const fl
     return check_launch("critic_loss_kernel");
 }
 
-int drq_copy2d_f32_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int rows, int cols,
-                        void* stream) {
-    DRQ_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d_bf16: bad args");
-    copy2d_f32_bf16_kernel<<<(rows * cols + 255) / 256, 256, 0, as_stream(stream)>>>(
-        src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
-    return check_launch("copy2d_f32_bf16_kernel");
+int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
+                   int cols, void* stream) {
+    DRQ_REQUIRE(src && dst && rows > 0 && cols > 0 && feat_off >= 0, "scatter_fb: bad args");
+    scatter_fb_kernel<<<(rows * cols + 255) / 256, 256, 0, as_stream(stream)>>>(
+        src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), rpad, feat_off, rows, cols);
+    return check_launch("scatter_fb_kernel");
 }
 
-int drq_colsum_bf16(const uint16_t* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,
-                    int64_t bs_out, void* stream) {
-    DRQ_REQUIRE(X && out && M > 0 && N > 0 && batch > 0, "colsum_bf16: bad args");
-    colsum_bf16_kernel<<<dim3((N + 31) / 32, batch), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(X), ld, out, M, N, bs_x, bs_out);
-    return check_launch("colsum_bf16_kernel");
+int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int batch, int64_t bs_x,
+                  int64_t bs_out, void* stream) {
+    DRQ_REQUIRE(X && out && M > 0 && N > 0 && batch > 0, "colsum_fb: bad args");
+    colsum_fb_kernel<<<dim3((N + 7) / 8, batch), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(X), rpad, out, M, N, bs_x, bs_out);
+    return check_launch("colsum_fb_kernel");
 }
 
-int drq_q_head_fwd_bf16(const uint16_t* c2, const float* w3, const float* b3, float* q, int B, int H,
-                        int heads, int64_t w_stride, void* stream) {
-    DRQ_REQUIRE(c2 && w3 && b3 && q && B > 0 && H > 0 && H % 2 == 0 && heads > 0, "q_head_fwd: bad args");
-    q_head_fwd_kernel<<<dim3((B + 3) / 4, heads), 128, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(c2), w3, b3, q, B, H, w_stride);
+int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
+                        float* q, int B, int H, int heads, int64_t w_stride, void* stream) {
+    DRQ_REQUIRE(c2 && w3 && b3 && q && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_fwd: bad args");
+    q_head_fwd_kernel<<<dim3((B + 127) / 128, heads), 128, H * sizeof(float), as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, b3, q, B, H, w_stride);
     return check_launch("q_head_fwd_kernel");
 }
 
-int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, const float* w3, uint16_t* dc2, float* dw3,
-                        float* db3, int B, int H, int heads, int64_t w_stride, void* stream) {
-    DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && heads > 0, "q_head_bwd: bad args");
-    q_head_bwd_kernel<<<dim3((H + 31) / 32, heads), 256, 0, as_stream(stream)>>>(
-        dq, reinterpret_cast<const __nv_bfloat16*>(c2), w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3, db3, B, H,
-        w_stride);
+int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
+                        uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
+                        void* stream) {
+    DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_bwd: bad args");
+    q_head_bwd_kernel<<<dim3(H / 8, heads), 256, 0, as_stream(stream)>>>(
+        dq, reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3,
+        db3, B, w_stride);
     return check_launch("q_head_bwd_kernel");
-}
-
-int drq_pack_trunk_bf16(const float* w, uint16_t* out, int rows, void* stream) {
-    DRQ_REQUIRE(w && out && rows > 0, "pack_trunk: bad args");
-    pack_trunk_kernel<<<dim3((1225 + 31) / 32, rows), 256, 0, as_stream(stream)>>>(
-        w, reinterpret_cast<__nv_bfloat16*>(out));
-    return check_launch("pack_trunk_kernel");
-}
-
-int drq_pack_table_bf16(const float* src, uint16_t* dst, const int64_t* table, int n_entries, void* stream) {
-    DRQ_REQUIRE(src && dst && table && n_entries > 0, "pack_table: bad args");
-    pack_table_kernel<<<dim3(64, n_entries), 256, 0, as_stream(stream)>>>(
-        src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<const long long*>(table));
-    return check_launch("pack_table_kernel");
 }
 
 int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, float* metrics, int B,

@@ -203,7 +203,7 @@ class Actor(nn.Module):
         mu_pre = torch.empty(B, A, device=dev)
         keep = _mlp_fwd(self.policy, h.data_ptr(), Fd, B, Fd, H, A, mu_pre.data_ptr(), dev)
         mu = torch.empty(B, A, device=dev)
-        call("drq_actor_sample", mu_pre.data_ptr(), None, None, 0.0, mu.data_ptr(), A, None, None, None, 0, B, A,
+        call("drq_actor_sample", mu_pre.data_ptr(), None, None, 0.0, mu.data_ptr(), A, None, None, None, 0, 0, B, A,
              _stream())
         del keep
         return utils.TruncatedNormal(mu, torch.ones_like(mu) * std)
@@ -512,12 +512,7 @@ class DrQV2Agent:
                      host_in=torch.zeros(n, *self.obs_shape, dtype=torch.uint8).pin_memory(),
                      host_out=torch.zeros(n, A).pin_memory(), graph={})
             if self.mode == "bf16":
-                nel = _lib.lib().drq_wb_elems(n)
-                zb = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
-                S = _bf16.splitk_for(n)
-                w.update(acts_b=[zb(nel) for _ in range(3)], feat_b=zb(n, REPR_DIM), S_b=S,
-                         partial_b=torch.zeros(S * n * Fd, device=dev), h_b=zb(n, self._bf16.ldF),
-                         p1_b=zb(n, H), p2_b=zb(n, H))
+                w.update(_bf16.act_workspace(self, n, dev))
             self._act_ws[n] = w
         if obs_t.is_cuda:
             w["obs"].copy_(obs_t, non_blocking=True)
@@ -568,7 +563,7 @@ class DrQV2Agent:
         _linear_fwd(w["p1"].data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), w["p2"].data_ptr(), H, n, H, H, True)
         _linear_fwd(w["p2"].data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), w["mu_pre"].data_ptr(), A, n, A, H, False)
         call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
-             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, None, 0, n, A, _stream())
+             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, _stream())
 
     # ------------------------------------------------------------------ update
     def update(self, replay_iter, step):
@@ -701,7 +696,7 @@ class DrQV2Agent:
         _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
         _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
         call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_c.data_ptr(), std_ptr, float(self.stddev_clip),
-             ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, None, 0, B, A, s)
+             ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, None, 0, 0, B, A, s)
         # --- target critic on (next features, next action) (drqv2.py:184)
         _trunk_fwd(featn, B, self._t("trunk.0.weight"), self._t("trunk.0.bias"), self._t("trunk.1.weight"),
                    self._t("trunk.1.bias"), Fd, ws.partial.data_ptr(), ws.xT.data_ptr(), Fd + A)
@@ -787,7 +782,7 @@ class DrQV2Agent:
         _linear_fwd(ws.p1.data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), ws.p2.data_ptr(), H, B, H, H, True)
         _linear_fwd(ws.p2.data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), ws.mu_pre.data_ptr(), A, B, A, H, False)
         call("drq_actor_sample", ws.mu_pre.data_ptr(), ws.eps_a.data_ptr(), std_ptr, float(self.stddev_clip),
-             ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6, None, 0, B, A, s)
+             ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6, None, 0, 0, B, A, s)
         # the just-updated critic on (features, action) (drqv2.py:213-216)
         _trunk_fwd(featp, B, pc("trunk.0.weight"), pc("trunk.0.bias"), pc("trunk.1.weight"), pc("trunk.1.bias"),
                    Fd, ws.partial.data_ptr(), ws.xA.data_ptr(), Fd + A)

@@ -172,10 +172,11 @@ int64_t drq_wb_elems(int n_images);
 int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream);
 
 /* conv2..4 (drqv2.py:56-59) + bias + ReLU on tcgen05 tensor cores, bf16 in / fp32 accumulate
- * (TMEM) / bf16 out.  in, out: WB buffers of N images.  nhwc_out != 0: out is the compact
- * feature matrix [N][hout*hout][32] (the bf16-mode feature layout) instead of WB. */
+ * (TMEM) / bf16 out.  in, out: WB buffers of N images.  nhwc_out == 1: out is the compact NHWC
+ * feature matrix [N][hout*hout][32]; nhwc_out == 2: out is the FB feature matrix the tensor-core
+ * trunk consumes (feature (y*hout+x)*32+c, row = image, feat_rpad rows per unit block). */
 int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out,
-                         int N, int hout, int nhwc_out, void* stream);
+                         int N, int hout, int nhwc_out, int64_t feat_rpad, void* stream);
 
 /* data gradient on tensor cores; dout/din: WB buffers of N images (zero guard rows);
  * act_in: WB buffer of n_act >= N images holding the layer's input activation (ReLU mask). */
@@ -202,29 +203,33 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void);
 
 /* ------------------------------------------------------------------ dense, bf16 tensor cores */
 
+/* Feature-blocked "FB" layout of every bf16 matrix the tensor-core heads touch (activations,
+ * gradients, packed weights):  X_fb[f/8][row][8] - 16-byte units of 8 consecutive features, `rpad`
+ * rows per unit block; rows and features are zero padded (features to a multiple of 16, rows to a
+ * multiple of 128).  The same buffer is a K-major operand when the contraction runs over the
+ * feature dim and an MN-major operand when it runs over the rows (weight gradients). */
+
 /* epilogues of drq_gemm_bf16 */
-#define DRQ_TEPI_F32 0          /* C(fp32) = acc (+bias) (+C if accumulate)                      */
-#define DRQ_TEPI_RELU_BF16 1    /* C(bf16) = relu(acc + bias)                                    */
-#define DRQ_TEPI_MASK_BF16 2    /* C(bf16) = acc * (mask > 0)                                    */
-#define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: NHWC feature column -> reference order */
-#define DRQ_TEPI_TRUNK_DGRAD 4  /* C(bf16 WB of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows */
+#define DRQ_TEPI_F32 0          /* C(fp32 row-major, stride ldc) = acc (+bias) (+C if accumulate)   */
+#define DRQ_TEPI_RELU_BF16 1    /* C(FB bf16, rpad = ldc) = relu(acc + bias)                          */
+#define DRQ_TEPI_MASK_BF16 2    /* C(FB bf16) = acc * (mask > 0), mask FB with rpad_mask              */
+#define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: NHWC feature column -> reference order   */
+#define DRQ_TEPI_TRUNK_DGRAD 4  /* C(WB bf16 of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows; mask = FB features */
 
-/* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 operands, fp32 accumulate.
- * a_mn_major == 0: A stored [m][k] (row stride lda); != 0: A stored [k][m].  Same for B with n.
- * lda/ldb must be multiples of 8 and rows zero-padded up to a multiple of 8 elements.
- * batch / split-K / strides as drq_gemm_f32 (strides in elements of the respective type).
- * bn = N tile (32, 64 or 128). */
-int drq_gemm_bf16(const uint16_t* A, int64_t lda, int a_mn_major, const uint16_t* B, int64_t ldb,
-                  int b_mn_major, void* C, int64_t ldc, const float* bias, const uint16_t* mask,
-                  int64_t ldmask, int M, int N, int K, int epilogue, int accumulate, int batch,
-                  int64_t bs_a, int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask, int splitk,
-                  int bn, void* stream);
+/* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 FB operands, fp32 accumulate (TMEM).
+ * a_mn_major == 0: A is blocked over k (rows = m); != 0: A is blocked over m (rows = k).  Same for B.
+ * rpad_a / rpad_b: rows per unit block.  FB outputs write feature columns [0, max(N, n_store)) with
+ * zeros beyond N.  batch / split-K as drq_gemm_f32 (strides in elements).  bn = N tile (32, 64, 128). */
+int drq_gemm_bf16(const uint16_t* A, int64_t rpad_a, int a_mn_major, const uint16_t* B, int64_t rpad_b,
+                  int b_mn_major, void* C, int64_t ldc, int n_store, const float* bias, const uint16_t* mask,
+                  int64_t rpad_mask, int M, int N, int K, int epilogue, int accumulate, int batch, int64_t bs_a,
+                  int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask, int splitk, int bn, void* stream);
 
-/* fp32 nn.Linear weight [rows][cols] -> bf16 [rows][ld] zero padded; nhwc_permute != 0 (trunk,
- * cols = 39200): output column k is the NHWC feature index (y*35+x)*32+c of the bf16 feature
- * layout, read from the reference column c*1225+y*35+x (drqv2.py:66). */
-int drq_pack_linear_bf16(const float* w, uint16_t* out, int rows, int cols, int ld, int nhwc_permute,
-                         void* stream);
+/* fp32 nn.Linear weight [rows][cols] -> FB bf16 [ceil16(cols)/8][rpad][8]. */
+int drq_pack_linear_fb(const float* w, uint16_t* out, int rows, int cols, int rpad, void* stream);
+/* trunk Linear(39200->rows) weight -> FB bf16 in the NHWC feature order (y*35+x)*32+c of the bf16
+ * feature layout (reference column c*1225+y*35+x, drqv2.py:66). */
+int drq_pack_trunk_fb(const float* w, uint16_t* out, int rows, int rpad, void* stream);
 
 /* ------------------------------------------------------------------ dense, fp32 */
 
@@ -253,11 +258,11 @@ int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int bat
 /* trunk tail: z = sum_s partial[s] + bias; LayerNorm(F, eps) affine; tanh
  * (drqv2.py:74-75,100-101).  h written at h_out[b*ld_h + f] (so it can land in
  * the [h, action] concat buffer of drqv2.py:117).  xhat [B][F] and rstd [B]
- * are saved for backward when non-NULL; h_bf16 (nullable, row stride ld_hb) receives a bf16 copy
- * of h for the tensor-core heads. */
+ * are saved for backward when non-NULL; h_bf16 (nullable, FB layout with rpad_hb rows per unit
+ * block) receives a bf16 copy of h for the tensor-core heads. */
 int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
                     const float* gamma, const float* beta, float* h_out, int64_t ld_h,
-                    float* xhat, float* rstd, uint16_t* h_bf16, int64_t ld_hb, int B, int F, float eps,
+                    float* xhat, float* rstd, uint16_t* h_bf16, int64_t rpad_hb, int B, int F, float eps,
                     void* stream);
 
 /* backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
@@ -265,7 +270,7 @@ int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const flo
  * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) is scratch. */
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h,
                     const float* xhat, const float* rstd, const float* gamma, float* dz,
-                    float* dgamma, float* dbeta, uint16_t* dz_bf16, int64_t ld_zb, int B, int F,
+                    float* dgamma, float* dbeta, uint16_t* dz_bf16, int64_t rpad_zb, int B, int F,
                     void* stream);
 
 /* ------------------------------------------------------------------ heads */
@@ -278,11 +283,11 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
  * (drqv2.py:212,226). */
 int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev, float clip,
                      float* action_out, int64_t ld_a, float* mu_out, float* metrics,
-                     uint16_t* action_bf16, int64_t ld_ab, int B, int A, void* stream);
+                     uint16_t* action_bf16, int64_t rpad_ab, int feat_off, int B, int A, void* stream);
 
 /* d(mu_pre) = d(action) * (1 - mu^2)   (straight-through clamp, utils.py:113-116) */
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
-                         uint16_t* dmu_bf16, int64_t ld_mb, int B, int A, void* stream);
+                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, void* stream);
 
 /* TD target + critic loss (drqv2.py:185-189): tq = r + d*min(tq1,tq2);
  * loss = mean((q1-tq)^2) + mean((q2-tq)^2); dq1 = 2(q1-tq)/B, dq2 likewise.
@@ -302,23 +307,21 @@ int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, flo
 int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
                    void* stream);
 
-/* bf16-mode helpers of the heads */
-int drq_copy2d_f32_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int rows, int cols,
+/* bf16-mode helpers of the heads (FB layout) */
+/* dst_fb[(feat_off + c)][r] = src[r*ld_src + c]  (the action half of torch.cat([h, action]), drqv2.py:117) */
+int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
+                   int cols, void* stream);
+/* out[z][n] = sum_m X_fb[z](m, n): bias gradients of the hidden layers */
+int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int batch, int64_t bs_x,
+                  int64_t bs_out, void* stream);
+/* final Linear(hidden,1) of the Q heads (drqv2.py:106,111) on an FB hidden activation c2 (head z at
+ * c2 + z*bs_c2): q[z][b] = c2[z][b].w3[z] + b3[z]; w3/b3 of head z at w3 + z*w_stride / b3 + z*w_stride. */
+int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
+                        float* q, int B, int H, int heads, int64_t w_stride, void* stream);
+/* its backward: dc2 = dq w3 (c2 > 0) as FB bf16; dw3 / db3 (nullable) in fp32 at the same strides. */
+int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
+                        uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
                         void* stream);
-int drq_colsum_bf16(const uint16_t* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,
-                    int64_t bs_out, void* stream);
-/* final Linear(hidden,1) of the Q heads (drqv2.py:106,111) on a bf16 hidden activation c2 [heads][B][H]:
- * q[z][b] = c2[z][b].w3[z] + b3[z]; w3/b3 of head z at w3 + z*w_stride / b3 + z*w_stride. */
-int drq_q_head_fwd_bf16(const uint16_t* c2, const float* w3, const float* b3, float* q, int B, int H,
-                        int heads, int64_t w_stride, void* stream);
-/* its backward: dc2 = dq w3 (c2 > 0) in bf16; dw3 / db3 (nullable) in fp32 at the same strides. */
-int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, const float* w3, uint16_t* dc2, float* dw3,
-                        float* db3, int B, int H, int heads, int64_t w_stride, void* stream);
-/* table-driven fp32 -> bf16 packing of nn.Linear weights after an optimiser step.  table (device,
- * int64 [n][6]): src offset (floats), dst offset (bf16 elements), rows, cols, ld, nhwc_permute. */
-int drq_pack_table_bf16(const float* src, uint16_t* dst, const int64_t* table, int n_entries, void* stream);
-/* trunk Linear(39200->rows) weight: fp32 reference order -> bf16 NHWC feature order (coalesced transpose) */
-int drq_pack_trunk_bf16(const float* w, uint16_t* out, int rows, void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 

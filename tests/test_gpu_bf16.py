@@ -44,7 +44,7 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
     xin = wb_from_nchw(x)
     wf, _ = _pack_w(w, dev)
     out = torch.zeros(_lib.lib().drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
-    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), out.data_ptr(), N, hout, 0, _stream())
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), out.data_ptr(), N, hout, 0, 0, _stream())
     torch.cuda.synchronize()
     want = torch.relu(torch.nn.functional.conv2d(_bf(x).double(), _bf(w).double(), b.double()))
     got = nchw_from_wb(out.view(4, -1, 8), N, hout, hout).double()
@@ -52,10 +52,17 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
     assert err <= 2 ** -8 * want.abs().max().item() + 1e-6, err
     # compact NHWC feature output
     feat = torch.zeros(N, hout * hout, 32, dtype=torch.bfloat16, device=dev)
-    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), feat.data_ptr(), N, hout, 1, _stream())
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), feat.data_ptr(), N, hout, 1, 0, _stream())
     torch.cuda.synchronize()
     got2 = feat.float().view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
     assert torch.equal(got2, got)
+    # FB feature matrix (rows = images, features in NHWC order)
+    from drqv2_b200._bf16 import FB
+    fb = FB(N, hout * hout * 32, dev)
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), fb.ptr(), N, hout, 2, fb.rpad, _stream())
+    torch.cuda.synchronize()
+    got3 = fb.dense().view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
+    assert torch.equal(got3, got)
 
 
 @pytest.mark.parametrize("hout,N", [(39, 2), (35, 3)])
@@ -103,108 +110,130 @@ def test_conv3x3_wgrad_bf16(dev, hout, N):
     assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7
 
 
-def _gemm_bf16(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, epi, bias=None, mask=None, ldmask=0, acc=0,
-               batch=1, bs=(0, 0, 0, 0, 0), splitk=1, bn=64):
+def _fb(x, rpad=None):
+    """[rows][feats] (or [batch][rows][feats]) fp32 -> FB bf16 buffer object (drqv2_b200._bf16.FB)."""
+    from drqv2_b200._bf16 import FB
+    x3 = x if x.dim() == 3 else x.unsqueeze(0)
+    fb = FB(x3.shape[1], x3.shape[2], x.device, batch=x3.shape[0], rpad=rpad)
+    v = fb.buf.view(fb.batch, fb.units, fb.rpad, 8)
+    pad = torch.zeros(fb.batch, fb.rpad, fb.units * 8, dtype=torch.bfloat16, device=x.device)
+    pad[:, :x3.shape[1], :x3.shape[2]] = x3.to(torch.bfloat16)
+    v.copy_(pad.view(fb.batch, fb.rpad, fb.units, 8).permute(0, 2, 1, 3))
+    return fb
+
+
+def _gemm_bf16(A, a_mn, B, b_mn, C, ldc, M, N, K, epi, bias=None, mask=None, acc=0, batch=1, bs_c=0, bs_bias=0,
+               splitk=1, bn=64, n_store=0, a_row0=0):
+    """A, B, mask: FB objects; C: FB object (bf16 epilogues) or fp32 tensor."""
     from drqv2_b200 import _lib
-    _lib.call("drq_gemm_bf16", A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, C.data_ptr(), ldc,
-              None if bias is None else bias.data_ptr(), None if mask is None else mask.data_ptr(), ldmask,
-              M, N, K, epi, acc, batch, bs[0], bs[1], bs[2], bs[3], bs[4], splitk, bn, _stream())
-
-
-def _pad_bf16(x, ld):
-    out = torch.zeros(*x.shape[:-1], ld, dtype=torch.bfloat16, device=x.device)
-    out[..., :x.shape[-1]] = x.to(torch.bfloat16)
-    return out
+    from drqv2_b200._bf16 import FB
+    c_ptr = C.ptr() if isinstance(C, FB) else C.data_ptr()
+    _lib.call("drq_gemm_bf16", A.ptr(row=a_row0), A.rpad, a_mn, B.ptr(), B.rpad, b_mn, c_ptr, ldc, n_store,
+              None if bias is None else bias.data_ptr(), None if mask is None else mask.ptr(),
+              0 if mask is None else mask.rpad, M, N, K, epi, acc, batch,
+              A.stride if A.batch > 1 else 0, B.stride if B.batch > 1 else 0,
+              C.stride if isinstance(C, FB) else bs_c, bs_bias,
+              0 if mask is None else (mask.stride if mask.batch > 1 else 0), splitk, bn, _stream())
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(256, 1024, 56, 64), (37, 130, 1024, 32), (256, 50, 1000, 64), (300, 256, 256, 128)])
 def test_gemm_bf16_kmajor_relu_and_f32(dev, M, N, K, bn):
-    """Linear forward: y = relu(x W^T + b) (bf16 out) and plain fp32 out."""
+    """Linear forward: y = relu(x W^T + b) (FB bf16 out) and plain fp32 out."""
+    from drqv2_b200._bf16 import FB
     g = torch.Generator().manual_seed(M + N + K)
     x = (torch.rand(M, K, generator=g) - 0.5).to(dev)
     w = ((torch.rand(N, K, generator=g) - 0.5) * 0.2).to(dev)
     b = (torch.rand(N, generator=g) - 0.5).to(dev)
-    ldk = (K + 7) // 8 * 8
-    xb, wb = _pad_bf16(x, ldk), _pad_bf16(w, ldk)
+    xb, wb = _fb(x), _fb(w)
     want = _bf(x).double() @ _bf(w).double().T + b.double()
-    ldn = (N + 7) // 8 * 8
-    y = torch.zeros(M, ldn, dtype=torch.bfloat16, device=dev)
-    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, y, ldn, M, N, K, 1, bias=b, bn=bn)
+    y = FB(M, N, dev)
+    y.buf.fill_(7.0)
+    _gemm_bf16(xb, 0, wb, 0, y, y.rpad, M, N, K, 1, bias=b, bn=bn, n_store=y.units * 8)
     yf = torch.zeros(M, N, device=dev)
-    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, yf, N, M, N, K, 0, bias=b, bn=bn)
+    _gemm_bf16(xb, 0, wb, 0, yf, N, M, N, K, 0, bias=b, bn=bn)
     torch.cuda.synchronize()
     scale = want.abs().max().item()
     assert (yf.double() - want).abs().max().item() <= 2e-5 * scale
-    assert (y[:, :N].double() - torch.relu(want)).abs().max().item() <= 2 ** -8 * scale
-    assert torch.count_nonzero(y[:, N:]) == 0
+    assert (y.dense().double() - torch.relu(want)).abs().max().item() <= 2 ** -8 * scale
+    # feature padding columns [N, ceil16(N)) are written as zeros
+    full = y.buf.view(y.units, y.rpad, 8).permute(1, 0, 2).reshape(y.rpad, -1)
+    assert torch.count_nonzero(full[:M, N:]) == 0
     # accumulate into C
-    _gemm_bf16(xb, ldk, 0, wb, ldk, 0, yf, N, M, N, K, 0, acc=1, bn=bn)
+    _gemm_bf16(xb, 0, wb, 0, yf, N, M, N, K, 0, acc=1, bn=bn)
     torch.cuda.synchronize()
     assert (yf.double() - (2 * want - b.double())).abs().max().item() <= 4e-5 * scale
 
 
 def test_gemm_bf16_dgrad_wgrad_layouts(dev):
     """dgrad: dx = (dy W) * (x_act > 0) with W as an MN-major B operand; wgrad: dW = dy^T x with both
-    operands MN-major; twin-head batching; split-K partials."""
+    operands MN-major; twin-head batching; split-K partials; row-offset A operand."""
+    from drqv2_b200._bf16 import FB
     g = torch.Generator().manual_seed(5)
     Bt, H, I = 256, 1024, 56
     dy = ((torch.rand(2, Bt, H, generator=g) - 0.5) * 1e-2).to(dev)
     w = ((torch.rand(2, H, I, generator=g) - 0.5) * 0.2).to(dev)
     xact = (torch.rand(2, Bt, I, generator=g) - 0.5).clamp_min(0).to(dev)
-    dyb, wb, xb = dy.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous(), xact.to(torch.bfloat16).contiguous()
-    # dgrad, batch of 2 heads: A = dy [B][H] K-major (K = H); B(k=h, n=i) = W[h][i] -> MN-major
-    dx = torch.zeros(2, Bt, I, dtype=torch.bfloat16, device=dev)
-    _gemm_bf16(dyb, H, 0, wb, I, 1, dx, I, Bt, I, H, 2, mask=xb, ldmask=I, batch=2,
-               bs=(Bt * H, H * I, Bt * I, 0, Bt * I), bn=64)
+    dyb, wb, xb = _fb(dy), _fb(w), _fb(xact)
+    # dgrad, batch of 2 heads: A = dy (contraction over its features h); B(k=h, n=i) = W[h][i] -> MN-major
+    dx = FB(Bt, I, dev, batch=2)
+    _gemm_bf16(dyb, 0, wb, 1, dx, dx.rpad, Bt, I, H, 2, mask=xb, batch=2, bn=64)
     torch.cuda.synchronize()
     want = (_bf(dy).double() @ _bf(w).double()) * (xact.double() > 0)
-    assert (dx.double() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item()
-    # wgrad: dW[h][i] = sum_b dy[b][h] x[b][i]: A(m=h,k=b) = dy[b][h] MN-major, B(n=i,k=b) = x[b][i] MN-major
+    got = torch.stack([dx.dense(0), dx.dense(1)]).double()
+    assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item()
+    # wgrad: dW[h][i] = sum_b dy[b][h] x[b][i]: both operands contract over their rows -> MN-major
     dw = torch.zeros(2, H, I, device=dev)
-    _gemm_bf16(dyb, H, 1, xb, I, 1, dw, I, H, I, Bt, 0, batch=2, bs=(Bt * H, Bt * I, H * I, 0, 0), bn=64)
+    _gemm_bf16(dyb, 1, xb, 1, dw, I, H, I, Bt, 0, batch=2, bs_c=H * I, bn=64)
     torch.cuda.synchronize()
     want_w = _bf(dy).double().transpose(1, 2) @ _bf(xact).double()
     assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
-    # split-K partials sum to the full product
+    # split-K partials sum to the full product; A rows taken at an offset (the "next" half of the features)
     K = 39200
-    feat = (torch.rand(64, K, generator=g) - 0.3).clamp_min(0).to(dev).to(torch.bfloat16)
-    wt = ((torch.rand(50, K, generator=g) - 0.5) * 0.01).to(dev).to(torch.bfloat16)
+    feat = (torch.rand(128, K, generator=g) - 0.3).clamp_min(0).to(dev)
+    wt = ((torch.rand(50, K, generator=g) - 0.5) * 0.01).to(dev)
+    fb, wtb = _fb(feat), _fb(wt, rpad=64)
     S = 35
     part = torch.zeros(S, 64, 50, device=dev)
-    _gemm_bf16(feat, K, 0, wt, K, 0, part, 50, 64, 50, K, 0, splitk=S, bs=(0, 0, 64 * 50, 0, 0), bn=64)
+    _gemm_bf16(fb, 0, wtb, 0, part, 50, 64, 50, K, 0, splitk=S, bs_c=64 * 50, bn=64, a_row0=64)
     torch.cuda.synchronize()
-    want_t = feat.double() @ wt.double().T
+    want_t = _bf(feat[64:]).double() @ _bf(wt).double().T
     assert (part.double().sum(0) - want_t).abs().max().item() <= 2e-5 * want_t.abs().max().item()
 
 
 def test_trunk_weight_pack_and_epilogues(dev):
     """NHWC-permuted trunk weight pack; wgrad epilogue writes the reference [F][39200] order;
-    dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane."""
+    dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane; conv4's FB
+    feature output feeds both."""
     from drqv2_b200 import _lib
+    from drqv2_b200._bf16 import FB
     from drqv2_b200._lib import PLB as PLB_
     g = torch.Generator().manual_seed(9)
     Fd, Bt, K = 50, 6, 39200
     w = ((torch.rand(Fd, K, generator=g) - 0.5) * 0.02).to(dev)
-    ldf = 56
-    wp = torch.zeros(ldf, K, dtype=torch.bfloat16, device=dev)        # rows padded to 56 so MN-major N reads stay in bounds
-    _lib.call("drq_pack_linear_bf16", w.data_ptr(), wp.data_ptr(), Fd, K, K, 1, _stream())
+    wp = FB(Fd, K, dev, rpad=64)
+    _lib.call("drq_pack_trunk_fb", w.data_ptr(), wp.ptr(), Fd, wp.rpad, _stream())
     # reference order -> NHWC: column (y*35+x)*32+c holds w[:, c*1225 + y*35 + x]
     w_nhwc = w.view(Fd, 32, 1225).permute(0, 2, 1).reshape(Fd, K)
-    assert torch.equal(wp[:Fd].float(), _bf(w_nhwc))
+    assert torch.equal(wp.dense(), _bf(w_nhwc))
+    # plain Linear weight pack
+    w2 = ((torch.rand(70, 50, generator=g) - 0.5)).to(dev)
+    w2p = FB(70, 50, dev)
+    _lib.call("drq_pack_linear_fb", w2.data_ptr(), w2p.ptr(), 70, 50, w2p.rpad, _stream())
+    assert torch.equal(w2p.dense(), _bf(w2))
     feat_nchw = (torch.rand(Bt, 32, 35, 35, generator=g) - 0.4).clamp_min(0).to(dev)
-    feat = feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K).to(torch.bfloat16).contiguous()           # NHWC bf16
+    feat = _fb(feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K))           # NHWC feature order
     dz = ((torch.rand(Bt, Fd, generator=g) - 0.5) * 1e-2).to(dev)
-    dzb = _pad_bf16(dz, ldf)
+    dzb = _fb(dz)
     # wgrad: dW[f][ref(n)] = sum_b dz[b][f] feat[b][n]
     dw = torch.zeros(Fd, K, device=dev)
-    _gemm_bf16(dzb, ldf, 1, feat, K, 1, dw, K, Fd, K, Bt, 3, bn=128)
+    _gemm_bf16(dzb, 1, feat, 1, dw, K, Fd, K, Bt, 3, bn=128)
     torch.cuda.synchronize()
     want_w = _bf(dz).double().T @ _bf(feat_nchw).double().reshape(Bt, K)
     assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
     # dgrad: d4pre = (dz W) * (feat > 0) scattered to WB
     d4 = torch.zeros(_lib.lib().drq_wb_elems(Bt), dtype=torch.bfloat16, device=dev)
     cs = Bt * PLB_ + 128
-    _gemm_bf16(dzb, ldf, 0, wp, K, 1, d4, cs, Bt, K, Fd, 4, mask=feat, ldmask=K, bn=128)
+    _gemm_bf16(dzb, 0, wp, 1, d4, cs, Bt, K, Fd, 4, mask=feat, bn=128)
     torch.cuda.synchronize()
     want_d = (_bf(dz).double() @ _bf(w).double()).view(Bt, 32, 35, 35) * (feat_nchw.double() > 0)
     got = nchw_from_wb(d4.view(4, -1, 8), Bt, 35, 35).double()
