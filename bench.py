@@ -229,7 +229,7 @@ def run_ours(args, rank, world):
             acts = [a.data_ptr() for a in bw.acts]
             d = [t.data_ptr() for t in bw.dpre]
             cand = {
-                "conv3x3_tc_kernel<fwd>(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, 0, s),
+                "conv3x3_tc_kernel<fwd>(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, 0, 0, 0, s),
                                                         2 * CONV_MACS[39] * 2 * B),
                 "conv3x3_tc_kernel<dgrad>(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_bf16", d[1], st.conv_wd[0].data_ptr(), acts[0], 2 * B, d[0], B, 39, s),
                                                          2 * CONV_MACS[39] * B),

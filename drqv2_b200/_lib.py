@@ -32,25 +32,27 @@ SIGNATURES = {
     "drq_conv3x3_dgrad_f32": [P, P, P, P, I, I, P],
     "drq_conv3x3_wgrad_f32": [P, P, P, P, P, I, I, P],
     "drq_pack_conv_w_bf16": [P, P, P, P],
-    "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, L, P],
+    "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, L, I, I, P],
     "drq_conv3x3_dgrad_bf16": [P, P, P, I, P, I, I, P],
     "drq_conv3x3_wgrad_bf16": [P, I, P, P, P, P, I, I, P],
     "drq_pack_conv1_w_bf16": [P, P, I, P],
     "drq_conv1_fwd_bf16": [P, P, P, P, P, I, I, I, P],
     "drq_conv1_wgrad_bf16": [P, P, P, P, P, P, I, I, I, P],
-    "drq_gemm_bf16": [P, L, I, P, L, I, P, L, I, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, I, P],
-    "drq_pack_linear_fb": [P, P, I, I, I, P],
-    "drq_pack_trunk_fb": [P, P, I, I, P],
+    "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
+    "drq_debug_gemm_stamps": [P],
+    "drq_pack_linear_tb": [P, P, I, I, P],
+    "drq_pack_trunk_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
     "drq_splitk_reduce": [P, I, L, P, L, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
     "drq_ln_tanh_fwd": [P, I, L, P, P, P, P, L, P, P, P, L, I, I, F, P],
+    "drq_ln_tanh_fwd_multi": [P, I, I, I, F, P],
     "drq_ln_tanh_bwd": [P, L, P, L, P, P, P, P, P, P, P, L, I, I, P],
     "drq_actor_sample": [P, P, P, F, P, L, P, P, P, L, I, I, I, P],
     "drq_actor_sample_bwd": [P, L, P, P, P, L, I, I, P],
     "drq_scatter_fb": [P, L, P, L, I, I, I, P],
     "drq_colsum_fb": [P, L, P, I, I, I, L, L, P],
-    "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, P],
+    "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, I, L, P],
     "drq_q_head_bwd_bf16": [P, P, L, L, P, P, P, P, I, I, I, L, P],
     "drq_critic_loss": [P, P, P, P, P, P, P, P, P, P, I, P],
     "drq_actor_loss": [P, P, P, P, P, I, P],
@@ -74,6 +76,8 @@ EPI_NONE, EPI_RELU, EPI_MASK, EPI_MASK_WIDE = 0, 1, 2, 3
 TEPI_F32, TEPI_RELU_BF16, TEPI_MASK_BF16, TEPI_TRUNK_WGRAD, TEPI_TRUNK_DGRAD = 0, 1, 2, 3, 4
 IMG, PW, PLANE, CONV_CH, REPR_DIM = 84, 41, 1696, 32, 39200
 PLB, GUARD, WB_SLACK = 1776, 88, 128
+TB_ACT, TB_W = 128, 64
+GEMM_KK, GEMM_KMN, GEMM_MNMN = 0, 1, 2
 
 
 class DrqError(RuntimeError):

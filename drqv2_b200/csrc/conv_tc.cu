@@ -38,8 +38,8 @@ struct ConvTcArgs {
     const float* bias;                              // fwd
     const __nv_bfloat16* mask; long long cs_mask;   // dgrad: input activation (WB)
     __nv_bfloat16* out; long long cs_out;
-    int n_images, ntiles, n_pos, w_valid, nhwc_out;   // nhwc_out: 0 WB, 1 compact NHWC, 2 FB features
-    long long feat_rpad;
+    int n_images, ntiles, n_pos, w_valid, nhwc_out;   // nhwc_out: 0 WB, 1 compact NHWC, 2 TB features (feat_rpad = units per row)
+    long long feat_rpad; int feat_half, feat_half_row;   // TB features: image n >= feat_half lands at row n - feat_half + feat_half_row
 };
 
 template <bool DGRAD>
@@ -81,18 +81,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ producer
-        if (elect_one()) {
+        // ------------------------------------------------ producer: lanes 0..3 issue one channel block each
+        {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
                 mbar_wait(empty + stage, phase ^ 1);
-                mbar_arrive_expect_tx(full + stage, 4 * kWinRows * 16);
+                if (lane == 0) mbar_arrive_expect_tx(full + stage, 4 * kWinRows * 16);
+                __syncwarp();
                 const long long row0 = (long long)n * kPLB + kGuard + p0 - (DGRAD ? kHaloTC : 0);
                 uint8_t* dst = a_s + stage * kStageBytes;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    bulk_g2s(dst + c * kStageRows * 16, a.in + (c * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
+                if (lane < 4)
+                    bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
                 if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             }
         }
@@ -159,12 +159,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
                     packed[i] = pack_bf16x2(lo, hi);
                 }
                 if (a.nhwc_out == 2) {
-                    // FB feature matrix: unit (y*w + x)*4 + c/8, row = image
+                    // TB feature matrix: unit (y*w + x)*4 + c/8, row = image (128-row blocks of feat_rpad units)
                     if (x < a.w_valid) {
                         const long long u0 = ((long long)y * a.w_valid + x) * 4;
+                        const int fr = n < a.feat_half ? n : n - a.feat_half + a.feat_half_row;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(a.out + ((u0 + c) * a.feat_rpad + n) * 8) =
+                            *reinterpret_cast<uint4*>(a.out + ((((long long)(fr >> 7)) * a.feat_rpad + u0 + c) * DRQ_TB_ACT + (fr & 127)) * 8) =
                                 make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
                     }
                     continue;
@@ -268,21 +269,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
-                mbar_wait(empty + stage, phase ^ 1);
-                mbar_arrive_expect_tx(full + stage, 4 * (kWinRows + kWgDRows) * 16);
-                const long long row0 = (long long)n * kPLB + kGuard + p0;
-                uint8_t* dst = st_s + stage * kWgStageBytes;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    bulk_g2s(dst + c * kStageRows * 16, a.in + (c * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
-                    bulk_g2s(dst + kStageBytes + c * kWgDRows * 16, a.d + (c * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
-                }
-                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-            }
+        // lanes 0..3: input-window channel blocks, lanes 4..7: gradient tile channel blocks
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+            mbar_wait(empty + stage, phase ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, 4 * (kWinRows + kWgDRows) * 16);
+            __syncwarp();
+            const long long row0 = (long long)n * kPLB + kGuard + p0;
+            uint8_t* dst = st_s + stage * kWgStageBytes;
+            if (lane < 4)
+                bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
+            else if (lane < 8)
+                bulk_g2s(dst + kStageBytes + (lane - 4) * kWgDRows * 16, a.d + ((lane - 4) * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(64, 32, true, true);
@@ -382,7 +382,7 @@ int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, voi
 }
 
 int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out, int N,
-                         int hout, int nhwc_out, int64_t feat_rpad, void* stream) {
+                         int hout, int nhwc_out, int64_t feat_rpad, int feat_half, int feat_half_row, void* stream) {
     DRQ_REQUIRE(in && w_fwd && bias && out, "conv3x3_fwd_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && hout > 0 && hout <= kPW - 2, "conv3x3_fwd_bf16: bad dims");
     if (int rc = ensure_smem((const void*)conv3x3_tc_kernel<false>, kConvTcSmem, "conv3x3_fwd_bf16")) return rc;
@@ -399,7 +399,9 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.w_valid = hout;
     a.nhwc_out = nhwc_out;
     a.feat_rpad = feat_rpad;
-    DRQ_REQUIRE(nhwc_out != 2 || feat_rpad >= N, "conv3x3_fwd_bf16: FB feature rpad < N");
+    a.feat_half = feat_half > 0 ? feat_half : N;
+    a.feat_half_row = feat_half_row;
+    DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
     conv3x3_tc_kernel<false><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
     return check_launch("conv3x3_tc_kernel<fwd>");
 }

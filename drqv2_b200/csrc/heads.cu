@@ -9,40 +9,42 @@ namespace drq {
 
 constexpr int kMaxFPerLane = 8;  // F <= 256
 
-// feature-blocked (FB) bf16 layout of the tensor-core heads: element (row, f) of X_fb[f/8][row][8]
-__device__ __forceinline__ long long fb_index(int f, long long row, long long rpad) {
-    return ((long long)(f >> 3) * rpad + row) * 8 + (f & 7);
+// tile-blocked (TB) bf16 activation layout of the tensor-core heads (include/drqv2_b200.h):
+// element (row, f) of X_tb[row / 128][f / 8][row % 128][f % 8]; `units` = padded features / 8
+__device__ __forceinline__ long long fb_index(int f, long long row, long long units) {
+    return (((row >> 7) * units + (f >> 3)) * DRQ_TB_ACT + (row & 127)) * 8 + (f & 7);
 }
 
-// one warp per row
+// Trunk tail for up to DRQ_LN_MAX_JOBS (network, row range) pairs in one launch: blockIdx.y = job,
+// one warp per row.  The split-K partial sums are added in a fixed order (8 loads in flight).
+struct LnJobs { drq_ln_job j[DRQ_LN_MAX_JOBS]; };
+
+template <int NF>   // features per lane: F <= 32 * NF
 __global__ void __launch_bounds__(128)
-ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_stride,
-                   const float* __restrict__ bias, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* __restrict__ h_out, long long ld_h,
-                   float* __restrict__ xhat, float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ h_bf,
-                   long long rpad_hb, int B, int F, float eps) {
+ln_tanh_fwd_kernel(const LnJobs jobs, int B, int F, float eps) {
+    const drq_ln_job& jb = jobs.j[blockIdx.y];
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
-    float z[kMaxFPerLane];
+    float z[NF];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxFPerLane; ++i) {
+    for (int i = 0; i < NF; ++i) {
         const int f = lane + 32 * i;
         float v = 0.f;
         if (f < F) {
-            const float* pp = partial + (long long)row * F + f;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;      // fixed association: 4 interleaved chains
+            const float* pp = jb.partial + (long long)row * jb.ld_partial + f;
             int s = 0;
-            for (; s + 4 <= S; s += 4) {
-                v0 += pp[(s + 0) * split_stride];
-                v1 += pp[(s + 1) * split_stride];
-                v2 += pp[(s + 2) * split_stride];
-                v3 += pp[(s + 3) * split_stride];
+#pragma unroll 1
+            for (; s + 8 <= jb.S; s += 8) {
+                float t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = pp[(s + k) * jb.split_stride];
+                v += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
             }
-            for (; s < S; ++s) v0 += pp[s * split_stride];
-            v = (v0 + v1) + (v2 + v3);
-            v += bias[f];
+#pragma unroll 1
+            for (; s < jb.S; ++s) v += pp[s * jb.split_stride];
+            v += jb.bias[f];
         }
         z[i] = v;
         sum += v;
@@ -50,26 +52,27 @@ ln_tanh_fwd_kernel(const float* __restrict__ partial, int S, long long split_str
     const float mean = warp_sum(sum) / (float)F;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxFPerLane; ++i) {
+    for (int i = 0; i < NF; ++i) {
         const int f = lane + 32 * i;
         const float d = (f < F) ? z[i] - mean : 0.f;
         sq += d * d;
     }
     const float var = warp_sum(sq) / (float)F;   // biased, as nn.LayerNorm
     const float rstd = 1.0f / sqrtf(var + eps);
+    __nv_bfloat16* h_bf = reinterpret_cast<__nv_bfloat16*>(jb.h_bf16);
 #pragma unroll
-    for (int i = 0; i < kMaxFPerLane; ++i) {
+    for (int i = 0; i < NF; ++i) {
         const int f = lane + 32 * i;
         if (f < F) {
             const float xh = (z[i] - mean) * rstd;
-            const float y = xh * gamma[f] + beta[f];
+            const float y = xh * jb.gamma[f] + jb.beta[f];
             const float hv = tanhf(y);
-            h_out[(long long)row * ld_h + f] = hv;
-            if (h_bf) h_bf[fb_index(f, row, rpad_hb)] = __float2bfloat16_rn(hv);
-            if (xhat) xhat[(long long)row * F + f] = xh;
+            jb.h_out[(long long)row * jb.ld_h + f] = hv;
+            if (h_bf) h_bf[fb_index(f, jb.row0_bf16 + row, jb.units_bf16)] = __float2bfloat16_rn(hv);
+            if (jb.xhat) jb.xhat[(long long)row * F + f] = xh;
         }
     }
-    if (rstd_out && lane == 0) rstd_out[row] = rstd;
+    if (jb.rstd && lane == 0) jb.rstd[row] = rstd;
 }
 
 // per row: dy = dh*(1-h^2); dxhat = dy*gamma; dz = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)).
@@ -247,7 +250,7 @@ actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
     if (metrics && threadIdx.x == 0) metrics[0] = -(t / (float)B);   // drqv2.py:216
 }
 
-// ---------------------------------------------------------------- bf16-mode helpers (FB layout)
+// ---------------------------------------------------------------- bf16-mode helpers (TB layout; `rpad` = units per row)
 __global__ void scatter_fb_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
                                   long long rpad, int feat_off, int rows, int cols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,10 +265,10 @@ colsum_fb_kernel(const __nv_bfloat16* __restrict__ X, long long rpad, float* __r
                  long long bs_x, long long bs_out) {
     __shared__ float red[256][9];
     const int u = blockIdx.x, z = blockIdx.y;
-    const __nv_bfloat16* Xu = X + z * bs_x + (long long)u * rpad * 8;
+    const __nv_bfloat16* Xz = X + z * bs_x;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < M; b += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(Xu + (long long)b * 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(Xz + fb_index(u * 8, b, rpad));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -287,29 +290,42 @@ colsum_fb_kernel(const __nv_bfloat16* __restrict__ X, long long rpad, float* __r
 }
 
 // q[z][b] = c2[z][b][:] . w3[z][:] + b3[z]   (the Linear(hidden, 1) of drqv2.py:106,111) on an FB
-// activation; thread per row, w3 staged in shared memory
-__global__ void __launch_bounds__(128)
+// activation.  Block = 32 rows x 8 unit groups: lane = row (one coalesced 512-byte read per unit and
+// warp), warp g sums units g, g+8, ...; the 8 partial sums are combined in fixed order.
+__global__ void __launch_bounds__(256)
 q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, long long rpad, long long bs_c2,
                   const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q, int B, int H,
-                  long long w_stride) {
+                  long long w_stride, int heads_inner, long long w_stride_outer) {
     extern __shared__ float w_s[];
+    __shared__ float part[8][33];
     const int z = blockIdx.y;
-    for (int k = threadIdx.x; k < H; k += 128) w_s[k] = w3[z * w_stride + k];
+    const long long woff = (z % heads_inner) * w_stride + (z / heads_inner) * w_stride_outer;
+    for (int k = threadIdx.x; k < H; k += 256) w_s[k] = w3[woff + k];
     __syncthreads();
-    const int b = blockIdx.x * 128 + threadIdx.x;
-    if (b >= B) return;
-    const __nv_bfloat16* x = c2 + z * bs_c2 + (long long)b * 8;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
     float s0 = 0.f, s1 = 0.f;
-    for (int u = 0; u < H / 8; ++u) {
-        const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)u * rpad * 8);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (b < B) {
+        const __nv_bfloat16* x = c2 + z * bs_c2 + fb_index(0, b, rpad);
+#pragma unroll 4
+        for (int u = grp; u < H / 8; u += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s0 = fmaf(__uint_as_float(w[j] << 16), w_s[u * 8 + 2 * j], s0);
-            s1 = fmaf(__uint_as_float(w[j] & 0xFFFF0000u), w_s[u * 8 + 2 * j + 1], s1);
+            for (int j = 0; j < 4; ++j) {
+                s0 = fmaf(__uint_as_float(w[j] << 16), w_s[u * 8 + 2 * j], s0);
+                s1 = fmaf(__uint_as_float(w[j] & 0xFFFF0000u), w_s[u * 8 + 2 * j + 1], s1);
+            }
         }
     }
-    q[(long long)z * B + b] = (s0 + s1) + b3[z * w_stride];
+    part[grp][lane] = s0 + s1;
+    __syncthreads();
+    if (grp == 0 && b < B) {
+        float t = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < 8; ++g2) t += part[g2][lane];
+        q[(long long)z * B + b] = t + b3[woff];
+    }
 }
 
 // dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0) (FB bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
@@ -321,13 +337,14 @@ q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict_
     __shared__ float red[256][9];
     const int u = blockIdx.x, z = blockIdx.y;
     const float* dqz = dq + (long long)z * B;
-    const long long base = z * bs_c2 + (long long)u * rpad * 8;
+    const long long base = z * bs_c2;
     float w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = w3[z * w_stride + u * 8 + j];
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < B; b += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(c2 + base + (long long)b * 8);
+        const long long at = base + fb_index(u * 8, b, rpad);
+        const uint4 v = *reinterpret_cast<const uint4*>(c2 + at);
         const uint32_t cw[4] = {v.x, v.y, v.z, v.w};
         const float g = dqz[b];
         uint32_t pk[4];
@@ -339,7 +356,7 @@ q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict_
             const __nv_bfloat162 t = __floats2bfloat162_rn(a0 > 0.f ? g * w[2 * j] : 0.f, a1 > 0.f ? g * w[2 * j + 1] : 0.f);
             pk[j] = *reinterpret_cast<const uint32_t*>(&t);
         }
-        *reinterpret_cast<uint4*>(dc2 + base + (long long)b * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dc2 + at) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     if (dw3) {
 #pragma unroll
@@ -367,16 +384,32 @@ using namespace drq;
 
 extern "C" {
 
+int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float eps, void* stream) {
+    DRQ_REQUIRE(jobs && njobs >= 1 && njobs <= DRQ_LN_MAX_JOBS, "ln_tanh_fwd: 1..%d jobs", DRQ_LN_MAX_JOBS);
+    DRQ_REQUIRE(B >= 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_fwd: bad dims (F<=256)");
+    LnJobs js{};
+    for (int i = 0; i < njobs; ++i) {
+        js.j[i] = jobs[i];
+        DRQ_REQUIRE(jobs[i].partial && jobs[i].bias && jobs[i].gamma && jobs[i].beta && jobs[i].h_out && jobs[i].S >= 1,
+                    "ln_tanh_fwd: null pointer in job %d", i);
+    }
+    if (B == 0) return DRQ_OK;
+    const dim3 grid((B + 3) / 4, njobs);
+    cudaStream_t s = as_stream(stream);
+    if (F <= 64) ln_tanh_fwd_kernel<2><<<grid, 128, 0, s>>>(js, B, F, eps);
+    else if (F <= 128) ln_tanh_fwd_kernel<4><<<grid, 128, 0, s>>>(js, B, F, eps);
+    else ln_tanh_fwd_kernel<8><<<grid, 128, 0, s>>>(js, B, F, eps);
+    return check_launch("ln_tanh_fwd_kernel");
+}
+
 int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
                     const float* gamma, const float* beta, float* h_out, int64_t ld_h, float* xhat,
                     float* rstd, uint16_t* h_bf16, int64_t rpad_hb, int B, int F, float eps, void* stream) {
-    DRQ_REQUIRE(partial && bias && gamma && beta && h_out, "ln_tanh_fwd: null pointer");
-    DRQ_REQUIRE(B >= 0 && F > 0 && F <= 32 * kMaxFPerLane && S >= 1, "ln_tanh_fwd: bad dims (F<=256)");
-    if (B == 0) return DRQ_OK;
-    ln_tanh_fwd_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(
-        partial, S, split_stride, bias, gamma, beta, h_out, ld_h, xhat, rstd,
-        reinterpret_cast<__nv_bfloat16*>(h_bf16), rpad_hb, B, F, eps);
-    return check_launch("ln_tanh_fwd_kernel");
+    drq_ln_job j{};
+    j.partial = partial; j.ld_partial = F; j.split_stride = split_stride; j.S = S;
+    j.bias = bias; j.gamma = gamma; j.beta = beta; j.h_out = h_out; j.ld_h = ld_h; j.xhat = xhat; j.rstd = rstd;
+    j.h_bf16 = h_bf16; j.units_bf16 = rpad_hb; j.row0_bf16 = 0;
+    return drq_ln_tanh_fwd_multi(&j, 1, B, F, eps, stream);
 }
 
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, const float* xhat,
@@ -442,10 +475,11 @@ int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int
 }
 
 int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
-                        float* q, int B, int H, int heads, int64_t w_stride, void* stream) {
-    DRQ_REQUIRE(c2 && w3 && b3 && q && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_fwd: bad args");
-    q_head_fwd_kernel<<<dim3((B + 127) / 128, heads), 128, H * sizeof(float), as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, b3, q, B, H, w_stride);
+                        float* q, int B, int H, int heads, int64_t w_stride, int heads_inner, int64_t w_stride_outer,
+                        void* stream) {
+    DRQ_REQUIRE(c2 && w3 && b3 && q && B > 0 && H > 0 && H % 8 == 0 && heads > 0 && heads_inner > 0, "q_head_fwd: bad args");
+    q_head_fwd_kernel<<<dim3((B + 31) / 32, heads), 256, H * sizeof(float), as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, b3, q, B, H, w_stride, heads_inner, w_stride_outer);
     return check_launch("q_head_fwd_kernel");
 }
 

@@ -3,7 +3,6 @@
 // descriptors (no-swizzle canonical layouts).  Inline PTX only.
 #pragma once
 #include <cuda_bf16.h>
-#include <stdio.h>
 
 #include "common.cuh"
 
@@ -34,10 +33,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  Kept tiny: the
+// wait is inlined at every use and cold instruction fetch dominates the short kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -48,7 +49,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) return;
     }
-    printf("drq: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
     __trap();
 }
 

@@ -173,10 +173,13 @@ int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, voi
 
 /* conv2..4 (drqv2.py:56-59) + bias + ReLU on tcgen05 tensor cores, bf16 in / fp32 accumulate
  * (TMEM) / bf16 out.  in, out: WB buffers of N images.  nhwc_out == 1: out is the compact NHWC
- * feature matrix [N][hout*hout][32]; nhwc_out == 2: out is the FB feature matrix the tensor-core
- * trunk consumes (feature (y*hout+x)*32+c, row = image, feat_rpad rows per unit block). */
+ * feature matrix [N][hout*hout][32]; nhwc_out == 2: out is the TB feature matrix the tensor-core
+ * trunk consumes (feature (y*hout+x)*32+c, feat_rpad = units per row = hout*hout*4); image n is row n
+ * for n < feat_half and row n - feat_half + feat_half_row after it (the next_obs half of an update starts
+ * on its own 128-row block); feat_half <= 0: row = image. */
 int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out,
-                         int N, int hout, int nhwc_out, int64_t feat_rpad, void* stream);
+                         int N, int hout, int nhwc_out, int64_t feat_rpad, int feat_half, int feat_half_row,
+                         void* stream);
 
 /* data gradient on tensor cores; dout/din: WB buffers of N images (zero guard rows);
  * act_in: WB buffer of n_act >= N images holding the layer's input activation (ReLU mask). */
@@ -203,33 +206,49 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void);
 
 /* ------------------------------------------------------------------ dense, bf16 tensor cores */
 
-/* Feature-blocked "FB" layout of every bf16 matrix the tensor-core heads touch (activations,
- * gradients, packed weights):  X_fb[f/8][row][8] - 16-byte units of 8 consecutive features, `rpad`
- * rows per unit block; rows and features are zero padded (features to a multiple of 16, rows to a
- * multiple of 128).  The same buffer is a K-major operand when the contraction runs over the
- * feature dim and an MN-major operand when it runs over the rows (weight gradients). */
+/* Tile-blocked "TB" layout of every bf16 matrix the tensor-core heads touch (activations, gradients,
+ * packed weights):  X_tb[row / R][feature / 8][row % R][feature % 8]  - 16-byte units of 8 consecutive
+ * features, R rows per unit block, the `units` (= padded features / 8, features padded to a multiple
+ * of 16) unit blocks of one row block adjacent; rows zero padded to a multiple of R.  R = DRQ_TB_ACT
+ * for activations / gradients, DRQ_TB_W for weights.  The same buffer is a K-major operand when the
+ * contraction runs over the feature dim and an MN-major operand when it runs over the rows (weight
+ * and data gradients), and every operand tile is one contiguous span (one bulk-async copy). */
+#define DRQ_TB_ACT 128
+#define DRQ_TB_W 64
+
+/* operand modes of drq_gemm_bf16 */
+#define DRQ_GEMM_KK 0    /* A activation, contraction over its features; B weight, over its features (Linear forward)   */
+#define DRQ_GEMM_KMN 1   /* A activation, over its features; B weight, contraction over its rows (data gradient)         */
+#define DRQ_GEMM_MNMN 2  /* A and B activations, contraction over their rows (weight gradient: M = A features)          */
 
 /* epilogues of drq_gemm_bf16 */
 #define DRQ_TEPI_F32 0          /* C(fp32 row-major, stride ldc) = acc (+bias) (+C if accumulate)   */
-#define DRQ_TEPI_RELU_BF16 1    /* C(FB bf16, rpad = ldc) = relu(acc + bias)                          */
-#define DRQ_TEPI_MASK_BF16 2    /* C(FB bf16) = acc * (mask > 0), mask FB with rpad_mask              */
+#define DRQ_TEPI_RELU_BF16 1    /* C(TB bf16 activation, units = ldc) = relu(acc + bias)             */
+#define DRQ_TEPI_MASK_BF16 2    /* C(TB bf16) = acc * (mask > 0), mask TB activation with units_mask  */
 #define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: NHWC feature column -> reference order   */
-#define DRQ_TEPI_TRUNK_DGRAD 4  /* C(WB bf16 of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows; mask = FB features */
+#define DRQ_TEPI_TRUNK_DGRAD 4  /* C(WB bf16 of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows; mask = TB features */
 
-/* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 FB operands, fp32 accumulate (TMEM).
- * a_mn_major == 0: A is blocked over k (rows = m); != 0: A is blocked over m (rows = k).  Same for B.
- * rpad_a / rpad_b: rows per unit block.  FB outputs write feature columns [0, max(N, n_store)) with
- * zeros beyond N.  batch / split-K as drq_gemm_f32 (strides in elements).  bn = N tile (32, 64, 128). */
-int drq_gemm_bf16(const uint16_t* A, int64_t rpad_a, int a_mn_major, const uint16_t* B, int64_t rpad_b,
-                  int b_mn_major, void* C, int64_t ldc, int n_store, const float* bias, const uint16_t* mask,
-                  int64_t rpad_mask, int M, int N, int K, int epilogue, int accumulate, int batch, int64_t bs_a,
-                  int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask, int splitk, int bn, void* stream);
+/* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 TB operands, fp32 accumulate (TMEM).
+ * units_a / units_b: units per row of the operand buffers.  TB outputs write feature columns
+ * [0, max(N, n_store)) with zeros beyond N.  batch > 1: grid z = zo * batch_inner + zi, operand z at
+ * offset zi * strides[0..4] + zo * strides[5..9] (elements; a, b, c, bias, mask; strides == NULL: 0;
+ * strides has 11 entries).  splitk > 1 (DRQ_GEMM_KK, fp32): plane s of C (stride strides[10]) receives
+ * the partial sum of K chunk s (bias is not applied); grid z = batch entry * splitk + s.
+ * bn = N tile: 64 (all modes) or 128 (KMN, MNMN). */
+int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b, int mode, void* C, int64_t ldc,
+                  int n_store, const float* bias, const uint16_t* mask, int units_mask, int M, int N, int K,
+                  int epilogue, int accumulate, int batch, int batch_inner, const int64_t* strides, int splitk,
+                  int bn, void* stream);
 
-/* fp32 nn.Linear weight [rows][cols] -> FB bf16 [ceil16(cols)/8][rpad][8]. */
-int drq_pack_linear_fb(const float* w, uint16_t* out, int rows, int cols, int rpad, void* stream);
-/* trunk Linear(39200->rows) weight -> FB bf16 in the NHWC feature order (y*35+x)*32+c of the bf16
- * feature layout (reference column c*1225+y*35+x, drqv2.py:66). */
-int drq_pack_trunk_fb(const float* w, uint16_t* out, int rows, int rpad, void* stream);
+/* debug aid: clock64 timeline of block (0,0,0) of every later drq_gemm_bf16 launch into buf (>= 16
+ * int64, device memory); NULL switches it off. */
+int drq_debug_gemm_stamps(int64_t* buf);
+
+/* fp32 nn.Linear weight [rows][cols] -> TB(DRQ_TB_W) bf16 [ceil(rows/64)][ceil16(cols)/8][64][8]. */
+int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* stream);
+/* trunk Linear(39200->rows) weight -> TB(DRQ_TB_W) bf16 in the NHWC feature order (y*35+x)*32+c of the
+ * bf16 feature layout (reference column c*1225+y*35+x, drqv2.py:66). */
+int drq_pack_trunk_tb(const float* w, uint16_t* out, int rows, void* stream);
 
 /* ------------------------------------------------------------------ dense, fp32 */
 
@@ -258,12 +277,23 @@ int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int bat
 /* trunk tail: z = sum_s partial[s] + bias; LayerNorm(F, eps) affine; tanh
  * (drqv2.py:74-75,100-101).  h written at h_out[b*ld_h + f] (so it can land in
  * the [h, action] concat buffer of drqv2.py:117).  xhat [B][F] and rstd [B]
- * are saved for backward when non-NULL; h_bf16 (nullable, FB layout with rpad_hb rows per unit
- * block) receives a bf16 copy of h for the tensor-core heads. */
+ * are saved for backward when non-NULL; h_bf16 (nullable, TB activation layout, rpad_hb = units per row) receives a bf16 copy of h for the tensor-core heads. */
 int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const float* bias,
                     const float* gamma, const float* beta, float* h_out, int64_t ld_h,
                     float* xhat, float* rstd, uint16_t* h_bf16, int64_t rpad_hb, int B, int F, float eps,
                     void* stream);
+
+/* the same for several (network, row range) pairs in one launch - the five trunk forwards of an
+ * update (drqv2.py:182-184,187,210,213) read only two feature matrices.  partial row stride is
+ * ld_partial (the job's columns start at `partial`); the bf16 copy lands at TB rows row0_bf16 + b. */
+#define DRQ_LN_MAX_JOBS 4
+typedef struct {
+    const float* partial; int64_t ld_partial; int64_t split_stride; int32_t S;
+    const float* bias; const float* gamma; const float* beta;
+    float* h_out; int64_t ld_h; float* xhat; float* rstd;
+    uint16_t* h_bf16; int64_t units_bf16; int64_t row0_bf16;
+} drq_ln_job;
+int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float eps, void* stream);
 
 /* backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
  * output), dgamma[F], dbeta[F].  h is the saved tanh output (ld_h).
@@ -307,7 +337,7 @@ int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, flo
 int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
                    void* stream);
 
-/* bf16-mode helpers of the heads (FB layout) */
+/* bf16-mode helpers of the heads (TB activation layout; every `rpad` argument = units per row) */
 /* dst_fb[(feat_off + c)][r] = src[r*ld_src + c]  (the action half of torch.cat([h, action]), drqv2.py:117) */
 int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
                    int cols, void* stream);
@@ -317,7 +347,8 @@ int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int
 /* final Linear(hidden,1) of the Q heads (drqv2.py:106,111) on an FB hidden activation c2 (head z at
  * c2 + z*bs_c2): q[z][b] = c2[z][b].w3[z] + b3[z]; w3/b3 of head z at w3 + z*w_stride / b3 + z*w_stride. */
 int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
-                        float* q, int B, int H, int heads, int64_t w_stride, void* stream);
+                        float* q, int B, int H, int heads, int64_t w_stride, int heads_inner, int64_t w_stride_outer,
+                        void* stream);
 /* its backward: dc2 = dq w3 (c2 > 0) as FB bf16; dw3 / db3 (nullable) in fp32 at the same strides. */
 int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
                         uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,

@@ -44,7 +44,7 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
     xin = wb_from_nchw(x)
     wf, _ = _pack_w(w, dev)
     out = torch.zeros(_lib.lib().drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
-    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), out.data_ptr(), N, hout, 0, 0, _stream())
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), out.data_ptr(), N, hout, 0, 0, 0, 0, _stream())
     torch.cuda.synchronize()
     want = torch.relu(torch.nn.functional.conv2d(_bf(x).double(), _bf(w).double(), b.double()))
     got = nchw_from_wb(out.view(4, -1, 8), N, hout, hout).double()
@@ -52,16 +52,19 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
     assert err <= 2 ** -8 * want.abs().max().item() + 1e-6, err
     # compact NHWC feature output
     feat = torch.zeros(N, hout * hout, 32, dtype=torch.bfloat16, device=dev)
-    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), feat.data_ptr(), N, hout, 1, 0, _stream())
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), feat.data_ptr(), N, hout, 1, 0, 0, 0, _stream())
     torch.cuda.synchronize()
     got2 = feat.float().view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
     assert torch.equal(got2, got)
-    # FB feature matrix (rows = images, features in NHWC order)
-    from drqv2_b200._bf16 import FB
-    fb = FB(N, hout * hout * 32, dev)
-    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), fb.ptr(), N, hout, 2, fb.rpad, _stream())
+    # TB feature matrix (rows = images, features in NHWC order); the second "half" starts on its own row block
+    from drqv2_b200._bf16 import TB
+    half = N // 2
+    fb = TB(128 + N, hout * hout * 32, dev)
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), fb.ptr(), N, hout, 2, fb.units,
+              half, 128, _stream())
     torch.cuda.synchronize()
-    got3 = fb.dense().view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
+    rows = torch.cat([fb.view()[:half], fb.view()[128:128 + N - half]]).float()
+    got3 = rows[:, :hout * hout * 32].view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
     assert torch.equal(got3, got)
 
 
@@ -110,130 +113,148 @@ def test_conv3x3_wgrad_bf16(dev, hout, N):
     assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7
 
 
-def _fb(x, rpad=None):
-    """[rows][feats] (or [batch][rows][feats]) fp32 -> FB bf16 buffer object (drqv2_b200._bf16.FB)."""
-    from drqv2_b200._bf16 import FB
+def _tb(x, rblk=128):
+    """[rows][feats] (or [batch][rows][feats]) fp32 -> TB bf16 buffer object (drqv2_b200._bf16.TB)."""
+    from drqv2_b200._bf16 import TB
     x3 = x if x.dim() == 3 else x.unsqueeze(0)
-    fb = FB(x3.shape[1], x3.shape[2], x.device, batch=x3.shape[0], rpad=rpad)
-    v = fb.buf.view(fb.batch, fb.units, fb.rpad, 8)
-    pad = torch.zeros(fb.batch, fb.rpad, fb.units * 8, dtype=torch.bfloat16, device=x.device)
-    pad[:, :x3.shape[1], :x3.shape[2]] = x3.to(torch.bfloat16)
-    v.copy_(pad.view(fb.batch, fb.rpad, fb.units, 8).permute(0, 2, 1, 3))
-    return fb
+    tb = TB(x3.shape[1], x3.shape[2], x.device, batch=x3.shape[0], rblk=rblk)
+    for z in range(x3.shape[0]):
+        tb.load(x3[z], z)
+    return tb
 
 
-def _gemm_bf16(A, a_mn, B, b_mn, C, ldc, M, N, K, epi, bias=None, mask=None, acc=0, batch=1, bs_c=0, bs_bias=0,
+def _gemm_bf16(A, B, mode, C, ldc, M, N, K, epi, bias=None, mask=None, acc=0, batch=1, bs_c=0, split_stride=0,
                splitk=1, bn=64, n_store=0, a_row0=0):
-    """A, B, mask: FB objects; C: FB object (bf16 epilogues) or fp32 tensor."""
+    """A, B, mask: TB objects; C: TB object (bf16 epilogues) or fp32 tensor."""
     from drqv2_b200 import _lib
-    from drqv2_b200._bf16 import FB
-    c_ptr = C.ptr() if isinstance(C, FB) else C.data_ptr()
-    _lib.call("drq_gemm_bf16", A.ptr(row=a_row0), A.rpad, a_mn, B.ptr(), B.rpad, b_mn, c_ptr, ldc, n_store,
+    from drqv2_b200._bf16 import TB, _strides
+    c_ptr = C.ptr() if isinstance(C, TB) else C.data_ptr()
+    st = _strides((A.stride if A.batch > 1 else 0, B.stride if B.batch > 1 else 0,
+                   C.stride if isinstance(C, TB) else bs_c, 0,
+                   0 if mask is None else (mask.stride if mask.batch > 1 else 0)), split=split_stride)
+    _lib.call("drq_gemm_bf16", A.ptr(row=a_row0), A.units, B.ptr(), B.units, mode, c_ptr, ldc, n_store,
               None if bias is None else bias.data_ptr(), None if mask is None else mask.ptr(),
-              0 if mask is None else mask.rpad, M, N, K, epi, acc, batch,
-              A.stride if A.batch > 1 else 0, B.stride if B.batch > 1 else 0,
-              C.stride if isinstance(C, FB) else bs_c, bs_bias,
-              0 if mask is None else (mask.stride if mask.batch > 1 else 0), splitk, bn, _stream())
+              0 if mask is None else mask.units, M, N, K, epi, acc, batch, batch, st, splitk, bn, _stream())
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(256, 1024, 56, 64), (37, 130, 1024, 32), (256, 50, 1000, 64), (300, 256, 256, 128)])
-def test_gemm_bf16_kmajor_relu_and_f32(dev, M, N, K, bn):
-    """Linear forward: y = relu(x W^T + b) (FB bf16 out) and plain fp32 out."""
-    from drqv2_b200._bf16 import FB
+KK, KMN, MNMN = 0, 1, 2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 56), (37, 130, 1024), (256, 50, 1000), (300, 256, 256)])
+def test_gemm_bf16_kmajor_relu_and_f32(dev, M, N, K):
+    """Linear forward: y = relu(x W^T + b) (TB bf16 out) and plain fp32 out."""
+    from drqv2_b200._bf16 import TB
     g = torch.Generator().manual_seed(M + N + K)
     x = (torch.rand(M, K, generator=g) - 0.5).to(dev)
     w = ((torch.rand(N, K, generator=g) - 0.5) * 0.2).to(dev)
     b = (torch.rand(N, generator=g) - 0.5).to(dev)
-    xb, wb = _fb(x), _fb(w)
+    xb, wb = _tb(x), _tb(w, 64)
     want = _bf(x).double() @ _bf(w).double().T + b.double()
-    y = FB(M, N, dev)
+    y = TB(M, N, dev)
     y.buf.fill_(7.0)
-    _gemm_bf16(xb, 0, wb, 0, y, y.rpad, M, N, K, 1, bias=b, bn=bn, n_store=y.units * 8)
+    _gemm_bf16(xb, wb, KK, y, y.units, M, N, K, 1, bias=b, n_store=y.units * 8)
     yf = torch.zeros(M, N, device=dev)
-    _gemm_bf16(xb, 0, wb, 0, yf, N, M, N, K, 0, bias=b, bn=bn)
+    _gemm_bf16(xb, wb, KK, yf, N, M, N, K, 0, bias=b)
     torch.cuda.synchronize()
     scale = want.abs().max().item()
     assert (yf.double() - want).abs().max().item() <= 2e-5 * scale
     assert (y.dense().double() - torch.relu(want)).abs().max().item() <= 2 ** -8 * scale
     # feature padding columns [N, ceil16(N)) are written as zeros
-    full = y.buf.view(y.units, y.rpad, 8).permute(1, 0, 2).reshape(y.rpad, -1)
-    assert torch.count_nonzero(full[:M, N:]) == 0
+    assert torch.count_nonzero(y.view()[:M, N:]) == 0
     # accumulate into C
-    _gemm_bf16(xb, 0, wb, 0, yf, N, M, N, K, 0, acc=1, bn=bn)
+    _gemm_bf16(xb, wb, KK, yf, N, M, N, K, 0, acc=1)
     torch.cuda.synchronize()
     assert (yf.double() - (2 * want - b.double())).abs().max().item() <= 4e-5 * scale
 
 
 def test_gemm_bf16_dgrad_wgrad_layouts(dev):
-    """dgrad: dx = (dy W) * (x_act > 0) with W as an MN-major B operand; wgrad: dW = dy^T x with both
-    operands MN-major; twin-head batching; split-K partials; row-offset A operand."""
-    from drqv2_b200._bf16 import FB
+    """dgrad: dx = (dy W) * (x_act > 0) with the weight contracted over its rows; wgrad: dW = dy^T x
+    with both activations contracted over their rows; twin-head batching; split-K partials; A rows at
+    a row-block offset."""
+    from drqv2_b200._bf16 import TB
     g = torch.Generator().manual_seed(5)
     Bt, H, I = 256, 1024, 56
     dy = ((torch.rand(2, Bt, H, generator=g) - 0.5) * 1e-2).to(dev)
     w = ((torch.rand(2, H, I, generator=g) - 0.5) * 0.2).to(dev)
     xact = (torch.rand(2, Bt, I, generator=g) - 0.5).clamp_min(0).to(dev)
-    dyb, wb, xb = _fb(dy), _fb(w), _fb(xact)
-    # dgrad, batch of 2 heads: A = dy (contraction over its features h); B(k=h, n=i) = W[h][i] -> MN-major
-    dx = FB(Bt, I, dev, batch=2)
-    _gemm_bf16(dyb, 0, wb, 1, dx, dx.rpad, Bt, I, H, 2, mask=xb, batch=2, bn=64)
+    dyb, wb, xb = _tb(dy), _tb(w, 64), _tb(xact)
+    # dgrad, batch of 2 heads
+    dx = TB(Bt, I, dev, batch=2)
+    _gemm_bf16(dyb, wb, KMN, dx, dx.units, Bt, I, H, 2, mask=xb, batch=2)
     torch.cuda.synchronize()
     want = (_bf(dy).double() @ _bf(w).double()) * (xact.double() > 0)
     got = torch.stack([dx.dense(0), dx.dense(1)]).double()
     assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item()
-    # wgrad: dW[h][i] = sum_b dy[b][h] x[b][i]: both operands contract over their rows -> MN-major
+    # the 128-wide N tile (hidden -> hidden data gradient)
+    w2 = ((torch.rand(H, 384, generator=g) - 0.5) * 0.2).to(dev)
+    m2 = (torch.rand(Bt, 384, generator=g) - 0.5).clamp_min(0).to(dev)
+    dx2 = TB(Bt, 384, dev)
+    dy0 = TB(Bt, H, dev)
+    dy0.load(dy[0])
+    _gemm_bf16(dy0, _tb(w2, 64), KMN, dx2, dx2.units, Bt, 384, H, 2, mask=_tb(m2), bn=128)
+    torch.cuda.synchronize()
+    want2 = (_bf(dy[0]).double() @ _bf(w2).double()) * (m2.double() > 0)
+    assert (dx2.dense().double() - want2).abs().max().item() <= 2 ** -8 * want2.abs().max().item()
+    # wgrad: dW[h][i] = sum_b dy[b][h] x[b][i]
     dw = torch.zeros(2, H, I, device=dev)
-    _gemm_bf16(dyb, 1, xb, 1, dw, I, H, I, Bt, 0, batch=2, bs_c=H * I, bn=64)
+    _gemm_bf16(dyb, xb, MNMN, dw, I, H, I, Bt, 0, batch=2, bs_c=H * I)
     torch.cuda.synchronize()
     want_w = _bf(dy).double().transpose(1, 2) @ _bf(xact).double()
     assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
-    # split-K partials sum to the full product; A rows taken at an offset (the "next" half of the features)
-    K = 39200
-    feat = (torch.rand(128, K, generator=g) - 0.3).clamp_min(0).to(dev)
-    wt = ((torch.rand(50, K, generator=g) - 0.5) * 0.01).to(dev)
-    fb, wtb = _fb(feat), _fb(wt, rpad=64)
-    S = 35
-    part = torch.zeros(S, 64, 50, device=dev)
-    _gemm_bf16(fb, 0, wtb, 0, part, 50, 64, 50, K, 0, splitk=S, bs_c=64 * 50, bn=64, a_row0=64)
+    # wgrad with the 128-wide N tile and K not a multiple of the row block
+    Bs = 200
+    dys, xs = dy[0, :Bs, :300].contiguous(), dy[1, :Bs, :260].contiguous()
+    dw2 = torch.zeros(300, 260, device=dev)
+    _gemm_bf16(_tb(dys), _tb(xs), MNMN, dw2, 260, 300, 260, Bs, 0, bn=128)
     torch.cuda.synchronize()
-    want_t = _bf(feat[64:]).double() @ _bf(wt).double().T
+    want_w2 = _bf(dys).double().T @ _bf(xs).double()
+    assert (dw2.double() - want_w2).abs().max().item() <= 2e-5 * want_w2.abs().max().item()
+    # split-K partials sum to the full product; A rows taken at a row-block offset (the "next" half)
+    K = 39200
+    feat = (torch.rand(256, K, generator=g) - 0.3).clamp_min(0).to(dev)
+    wt = ((torch.rand(50, K, generator=g) - 0.5) * 0.01).to(dev)
+    fb, wtb = _tb(feat), _tb(wt, 64)
+    S = 35
+    part = torch.zeros(S, 100, 50, device=dev)
+    _gemm_bf16(fb, wtb, KK, part, 50, 100, 50, K, 0, splitk=S, split_stride=100 * 50, a_row0=128)
+    torch.cuda.synchronize()
+    want_t = _bf(feat[128:228]).double() @ _bf(wt).double().T
     assert (part.double().sum(0) - want_t).abs().max().item() <= 2e-5 * want_t.abs().max().item()
 
 
 def test_trunk_weight_pack_and_epilogues(dev):
     """NHWC-permuted trunk weight pack; wgrad epilogue writes the reference [F][39200] order;
-    dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane; conv4's FB
-    feature output feeds both."""
+    dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane."""
     from drqv2_b200 import _lib
-    from drqv2_b200._bf16 import FB
+    from drqv2_b200._bf16 import TB
     from drqv2_b200._lib import PLB as PLB_
     g = torch.Generator().manual_seed(9)
     Fd, Bt, K = 50, 6, 39200
     w = ((torch.rand(Fd, K, generator=g) - 0.5) * 0.02).to(dev)
-    wp = FB(Fd, K, dev, rpad=64)
-    _lib.call("drq_pack_trunk_fb", w.data_ptr(), wp.ptr(), Fd, wp.rpad, _stream())
+    wp = TB(Fd, K, dev, rblk=64)
+    _lib.call("drq_pack_trunk_tb", w.data_ptr(), wp.ptr(), Fd, _stream())
     # reference order -> NHWC: column (y*35+x)*32+c holds w[:, c*1225 + y*35 + x]
     w_nhwc = w.view(Fd, 32, 1225).permute(0, 2, 1).reshape(Fd, K)
     assert torch.equal(wp.dense(), _bf(w_nhwc))
-    # plain Linear weight pack
+    # plain Linear weight pack (more than one 64-row block)
     w2 = ((torch.rand(70, 50, generator=g) - 0.5)).to(dev)
-    w2p = FB(70, 50, dev)
-    _lib.call("drq_pack_linear_fb", w2.data_ptr(), w2p.ptr(), 70, 50, w2p.rpad, _stream())
+    w2p = TB(70, 50, dev, rblk=64)
+    _lib.call("drq_pack_linear_tb", w2.data_ptr(), w2p.ptr(), 70, 50, _stream())
     assert torch.equal(w2p.dense(), _bf(w2))
     feat_nchw = (torch.rand(Bt, 32, 35, 35, generator=g) - 0.4).clamp_min(0).to(dev)
-    feat = _fb(feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K))           # NHWC feature order
+    feat = _tb(feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K))           # NHWC feature order
     dz = ((torch.rand(Bt, Fd, generator=g) - 0.5) * 1e-2).to(dev)
-    dzb = _fb(dz)
+    dzb = _tb(dz)
     # wgrad: dW[f][ref(n)] = sum_b dz[b][f] feat[b][n]
     dw = torch.zeros(Fd, K, device=dev)
-    _gemm_bf16(dzb, 1, feat, 1, dw, K, Fd, K, Bt, 3, bn=128)
+    _gemm_bf16(dzb, feat, MNMN, dw, K, Fd, K, Bt, 3, bn=128)
     torch.cuda.synchronize()
     want_w = _bf(dz).double().T @ _bf(feat_nchw).double().reshape(Bt, K)
     assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item()
     # dgrad: d4pre = (dz W) * (feat > 0) scattered to WB
     d4 = torch.zeros(_lib.lib().drq_wb_elems(Bt), dtype=torch.bfloat16, device=dev)
     cs = Bt * PLB_ + 128
-    _gemm_bf16(dzb, 0, wp, 1, d4, cs, Bt, K, Fd, 4, mask=feat, bn=128)
+    _gemm_bf16(dzb, wp, KMN, d4, cs, Bt, K, Fd, 4, mask=feat, bn=128)
     torch.cuda.synchronize()
     want_d = (_bf(dz).double() @ _bf(w).double()).view(Bt, 32, 35, 35) * (feat_nchw.double() > 0)
     got = nchw_from_wb(d4.view(4, -1, 8), Bt, 35, 35).double()
