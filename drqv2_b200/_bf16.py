@@ -189,7 +189,7 @@ class Bf16Workspace:
         self.wg_ws = zf(max(L.drq_conv_wgrad_bf16_ws_floats(), L.drq_conv1_wgrad_bf16_ws_floats()))
         FP = st.FP
         self.NT = 2 * FP                                             # columns of one trunk GEMM half
-        ntiles = (RB // TB_ACT) * (self.NT // 64)
+        ntiles = (RB // TB_ACT) * (self.NT // 128)
         self.S2 = splitk_for(2 * ntiles)                             # merged (2 halves) trunk forward
         self.S1 = splitk_for((RB // TB_ACT) * (FP // 64))            # single trunk forward (actor pass)
         self.partial = zf(max(self.S2 * 2 * B * self.NT, self.S1 * B * FP))
@@ -205,7 +205,8 @@ class Bf16Workspace:
         self.dp1, self.dp2 = TB(B, H, dev), TB(B, H, dev)
         self.dz = TB(B, Fd, dev)
         self.dmu = TB(B, A, dev)
-        self.dxf = zf(B, Fd + A)
+        self.SX = 8 if H % 1024 == 0 else 1                          # split-K of the Q heads' first-layer data gradient
+        self.dxf = zf(2 * self.SX, B, Fd + A)                        # partial planes [split][head]
 
 
 def encode(agent, ws, bw):
@@ -266,7 +267,7 @@ def critic_pass(agent, ws, bw):
     # ---- all four trunk forwards on this batch's features: z = 0 obs rows x [actor | critic], z = 1 next rows x
     # [target | actor]  (slots of the merged trunk weight are [target | actor | critic])
     gemm(feat.ptr(), feat.units, st.trunk_ptr(st.ACTOR), st.trunk.units, GEMM_KK, part.data_ptr(), NT, B, NT, REPR_DIM,
-         TEPI_F32, batch=2, batch_inner=1, splitk=S,
+         TEPI_F32, batch=2, batch_inner=1, splitk=S, bn=128,
          strides=_strides(outer=(feat.off(row=RB), -st.trunk.off(row=FP), B * NT, 0, 0), split=2 * B * NT))
     pz = lambda z, col: part.data_ptr() + F32 * (z * B * NT + col)
     job = lambda p, net_p, names, h_out, ld_h, xhat, rstd, tb, row0: LnJob(
@@ -305,12 +306,14 @@ def critic_pass(agent, ws, bw):
     gemm(dc1.ptr(), U, xC.ptr(0), xC.units, GEMM_MNMN, gc("Q1.0.weight"), Fd + A, H, Fd + A, B, TEPI_F32, batch=2,
          strides=_strides((HS, 0, qs_f, 0, 0)))
     call("drq_colsum_fb", dc1.ptr(), U, gc("Q1.0.bias"), B, H, 2, HS, qs_f, s)
-    gemm(dc1.ptr(0), U, w0.ptr(0), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd, H, TEPI_F32)
-    gemm(dc1.ptr(1), U, w0.ptr(1), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd, H, TEPI_F32, acc=1)
+    # d[h] = sum over heads and K chunks of dc1 @ W0[:, :F]: partial planes, summed by the consumer
+    PS = B * (Fd + A)
+    gemm(dc1.ptr(), U, w0.ptr(), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd, H, TEPI_F32, batch=2,
+         splitk=bw.SX, strides=_strides((HS, w0.stride, PS, 0, 0), split=2 * PS))
     # ---- trunk backward
     call("drq_ln_tanh_bwd", bw.dxf.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
          ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), gc("trunk.1.weight"), gc("trunk.1.bias"),
-         bw.dz.ptr(), bw.dz.units, B, Fd, s)
+         bw.dz.ptr(), bw.dz.units, B, Fd, 2 * bw.SX, PS, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, gc("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
     call("drq_colsum_f32", ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 1, 0, 0, s)
@@ -371,10 +374,11 @@ def actor_pass(agent, ws, bw):
          B, H, 2, qs_f, s)
     gemm(dc2.ptr(), U, w2.ptr(), w2.units, GEMM_KMN, dc1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=c1.ptr(), units_mask=U,
          batch=2, strides=_strides((HS, w2.stride, HS, 0, HS)))
-    gemm(dc1.ptr(0), U, w0.ptr(0), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd + A, H, TEPI_F32)
-    gemm(dc1.ptr(1), U, w0.ptr(1), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd + A, H, TEPI_F32, acc=1)
+    PS = B * (Fd + A)
+    gemm(dc1.ptr(), U, w0.ptr(), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd + A, H, TEPI_F32, batch=2,
+         splitk=bw.SX, strides=_strides((HS, w0.stride, PS, 0, 0), split=2 * PS))
     call("drq_actor_sample_bwd", bw.dxf.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(),
-         bw.dmu.ptr(), bw.dmu.units, B, A, s)
+         bw.dmu.ptr(), bw.dmu.units, B, A, 2 * bw.SX, PS, s)
     # actor MLP backward (activations of the obs rows, saved by the forward in the critic pass)
     dmu, hA, p1, p2, dp1, dp2 = bw.dmu, bw.hA, bw.p1, bw.p2, bw.dp1, bw.dp2
     a0, a2, a4 = st.p0, st.p2, st.p4
@@ -390,7 +394,7 @@ def actor_pass(agent, ws, bw):
     gemm(dp1.ptr(), U, a0.ptr(), a0.units, GEMM_KMN, ws.dhA.data_ptr(), Fd, B, Fd, H, TEPI_F32)
     call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
          pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"), ga("trunk.1.bias"), bw.dz.ptr(), bw.dz.units,
-         B, Fd, s)
+         B, Fd, 1, 0, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, ga("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
     call("drq_colsum_f32", ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 1, 0, 0, s)

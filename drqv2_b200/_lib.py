@@ -40,6 +40,7 @@ SIGNATURES = {
     "drq_conv1_wgrad_bf16": [P, P, P, P, P, P, I, I, I, P],
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
     "drq_debug_gemm_stamps": [P],
+    "drq_debug_conv_stamps": [P],
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
@@ -47,9 +48,9 @@ SIGNATURES = {
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
     "drq_ln_tanh_fwd": [P, I, L, P, P, P, P, L, P, P, P, L, I, I, F, P],
     "drq_ln_tanh_fwd_multi": [P, I, I, I, F, P],
-    "drq_ln_tanh_bwd": [P, L, P, L, P, P, P, P, P, P, P, L, I, I, P],
+    "drq_ln_tanh_bwd": [P, L, P, L, P, P, P, P, P, P, P, L, I, I, I, L, P],
     "drq_actor_sample": [P, P, P, F, P, L, P, P, P, L, I, I, I, P],
-    "drq_actor_sample_bwd": [P, L, P, P, P, L, I, I, P],
+    "drq_actor_sample_bwd": [P, L, P, P, P, L, I, I, I, L, P],
     "drq_scatter_fb": [P, L, P, L, I, I, I, P],
     "drq_colsum_fb": [P, L, P, I, I, I, L, L, P],
     "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, I, L, P],

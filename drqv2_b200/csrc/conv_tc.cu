@@ -39,8 +39,12 @@ struct ConvTcArgs {
     const __nv_bfloat16* mask; long long cs_mask;   // dgrad: input activation (WB)
     __nv_bfloat16* out; long long cs_out;
     int n_images, ntiles, n_pos, w_valid, nhwc_out;   // nhwc_out: 0 WB, 1 compact NHWC, 2 TB features (feat_rpad = units per row)
+    long long* stamps;        // debug: per-role wait / work cycle totals of block 0, or null
     long long feat_rpad; int feat_half, feat_half_row;   // TB features: image n >= feat_half lands at row n - feat_half + feat_half_row
 };
+
+static long long* g_conv_stamps = nullptr;
+#define CV_T() (a.stamps ? clock64() : 0ll)
 
 template <bool DGRAD>
 __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a) {
@@ -84,9 +88,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
         // ------------------------------------------------ producer: lanes 0..3 issue one channel block each
         {
             int stage = 0; uint32_t phase = 0;
+            long long w_empty = 0;
+            const long long t_begin = CV_T();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
+                const long long c0 = CV_T();
                 mbar_wait(empty + stage, phase ^ 1);
+                w_empty += CV_T() - c0;
                 if (lane == 0) mbar_arrive_expect_tx(full + stage, 4 * kWinRows * 16);
                 __syncwarp();
                 const long long row0 = (long long)n * kPLB + kGuard + p0 - (DGRAD ? kHaloTC : 0);
@@ -95,29 +103,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
                     bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
                 if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             }
+            if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[0] = w_empty; a.stamps[1] = CV_T() - t_begin; }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ UMMA issuer
+        // ------------------------------------------------ UMMA issuer.  One thread issues 18 UMMAs per tile; the
+        // descriptors are a per-stage base plus compile-time (address >> 4) offsets so that the issue
+        // loop is two adds and the instruction per UMMA (a dependent ALU op costs the lone thread ~4
+        // cycles; the M128 N32 K16 UMMA itself retires every ~45 cycles, tools/ub/ub_mma.cu).
         constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        const uint32_t w_addr = smem_u32(w_s);
+        const uint64_t da0 = make_smem_desc(smem_u32(a_s), kStageRows * 16, 128);
+        const uint64_t db0 = make_smem_desc(smem_u32(w_s), 512, 128);
+        long long w_tempty = 0, w_full = 0;
+        const long long t_begin = CV_T();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const long long c0 = CV_T();
             mbar_wait(tempty + acc, acc_phase ^ 1);
+            const long long c1 = CV_T();
             mbar_wait(full + stage, phase);
+            const long long c2 = CV_T();
+            w_tempty += c1 - c0; w_full += c2 - c1;
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a_addr = smem_u32(a_s + stage * kStageBytes);
+                const uint64_t da = da0 + (uint64_t)(stage * (kStageBytes >> 4));
                 const uint32_t d_tmem = tmem_base + acc * 32;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int off = (tap / 3) * kPW + (tap % 3);
                     const int o = DGRAD ? kHaloTC - off : off;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint64_t da = make_smem_desc(a_addr + o * 16 + h * 2 * kStageRows * 16, kStageRows * 16, 128);
-                        const uint64_t db = make_smem_desc(w_addr + (tap * 4 + h * 2) * 512, 512, 128);
-                        umma_bf16(d_tmem, da, db, idesc, (tap | h) ? 1u : 0u);
-                    }
+                    for (int h = 0; h < 2; ++h)
+                        umma_bf16(d_tmem, da + (uint64_t)(o + h * 2 * kStageRows), db0 + (uint64_t)((tap * 4 + h * 2) * 32), idesc,
+                                  (tap | h) ? 1u : 0u);
                 }
                 umma_commit(empty + stage);    // smem stage reusable once these UMMAs retire
                 umma_commit(tfull + acc);      // accumulator ready for the epilogue
@@ -126,20 +143,33 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
             if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[2] = w_tempty; a.stamps[3] = w_full; a.stamps[4] = CV_T() - t_begin; }
     } else {
         // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        uint4 mk[4], mk_next[4];
+        auto load_mask = [&](int t, uint4 (&m4)[4]) {     // ReLU mask (the layer's input activation) of tile t
+            const int n = t / a.ntiles, p = (t - n * a.ntiles) * kTM + q * 32 + lane;
+            if (t < total_tiles && p < a.n_pos) {
+                const long long row = (long long)n * kPLB + kGuard + p;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) m4[c] = __ldg(reinterpret_cast<const uint4*>(a.mask + (c * a.cs_mask + row) * 8));
+            }
+        };
+        if (DGRAD) load_mask(blockIdx.x, mk_next);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
             const int p = p0 + q * 32 + lane;
             const long long row = (long long)n * kPLB + kGuard + p;
-            uint4 mk[4];
-            if (DGRAD && p < a.n_pos) {       // ReLU-mask loads in flight while the accumulator is being produced
+            if (DGRAD) {        // this tile's mask was fetched one tile ago; start the next tile's loads now
 #pragma unroll
-                for (int c = 0; c < 4; ++c) mk[c] = __ldg(reinterpret_cast<const uint4*>(a.mask + (c * a.cs_mask + row) * 8));
+                for (int c = 0; c < 4; ++c) mk[c] = mk_next[c];
+                load_mask(t + gridDim.x, mk_next);
             }
+            const long long e0 = CV_T();
             mbar_wait(tfull + acc, acc_phase);
+            if (a.stamps && blockIdx.x == 0 && threadIdx.x == 64) a.stamps[5] += CV_T() - e0;
             tc_fence_after();
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, v);
@@ -288,24 +318,24 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         constexpr uint32_t idesc = make_idesc_bf16(64, 32, true, true);
         int stage = 0; uint32_t phase = 0;
         bool first = true;
-        const uint32_t ones_addr = smem_u32(ones_s);
+        // descriptors = per-stage base + compile-time (address >> 4) offsets (cheap issue loop)
+        const uint64_t da0 = make_smem_desc(smem_u32(st_s), 128, kStageRows * 16);
+        const uint64_t db0 = make_smem_desc(smem_u32(st_s) + kStageBytes, 128, kWgDRows * 16);
+        const uint64_t d1 = make_smem_desc(smem_u32(ones_s), 128, 256);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a_addr = smem_u32(st_s + stage * kWgStageBytes);
-                const uint32_t d_addr = a_addr + kStageBytes;
+                const uint64_t so = (uint64_t)(stage * (kWgStageBytes >> 4));
 #pragma unroll 1
                 for (int ks = 0; ks < kTM / 16; ++ks) {
-                    const uint64_t db = make_smem_desc(d_addr + ks * 256, 128, kWgDRows * 16);
+                    const uint64_t db = db0 + so + (uint64_t)(ks * 16);
+                    const uint64_t da = da0 + so + (uint64_t)(ks * 16);
+                    const uint32_t accum = (first && ks == 0) ? 0u : 1u;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int off = (tap / 3) * kPW + (tap % 3);
-                        const uint64_t da = make_smem_desc(a_addr + (off + ks * 16) * 16, 128, kStageRows * 16);
-                        umma_bf16(tmem_base + tap * 32, da, db, idesc, (first && ks == 0) ? 0u : 1u);
-                    }
-                    const uint64_t d1 = make_smem_desc(ones_addr, 128, 256);
-                    umma_bf16(tmem_base + 9 * 32, d1, db, idesc, (first && ks == 0) ? 0u : 1u);
+                    for (int tap = 0; tap < 9; ++tap)
+                        umma_bf16(tmem_base + tap * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
+                    umma_bf16(tmem_base + 9 * 32, d1, db, idesc, accum);
                 }
                 umma_commit(empty + stage);
             }
@@ -372,6 +402,8 @@ using namespace drq;
 
 extern "C" {
 
+int drq_debug_conv_stamps(int64_t* buf) { g_conv_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
+
 int64_t drq_wb_elems(int n_images) { return 4ll * ((long long)n_images * kPLB + kSlack) * 8; }
 
 int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream) {
@@ -399,6 +431,7 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.w_valid = hout;
     a.nhwc_out = nhwc_out;
     a.feat_rpad = feat_rpad;
+    a.stamps = g_conv_stamps;
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
@@ -425,6 +458,7 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.ntiles = (a.n_pos + kTM - 1) / kTM;
     a.w_valid = hin;
     a.nhwc_out = 0;
+    a.stamps = g_conv_stamps;
     conv3x3_tc_kernel<true><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
 }

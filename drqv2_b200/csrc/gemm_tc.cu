@@ -53,8 +53,10 @@ struct GemmCfg {
     static constexpr int A_BYTES = MODE == MODE_MNMN ? 16 * RA * 16 : 8 * RA * 16;
     static constexpr int B_BYTES = MODE == MODE_KK ? 8 * BN * 16 : (MODE == MODE_KMN ? (BN / 8) * RW * 16 : (BN / 8) * RA * 16);
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int STAGES = (192 * 1024) / STAGE > 6 ? 6 : (192 * 1024) / STAGE;
+    static constexpr int EPI_BYTES = BN * 4 + 4 * 32 * 33 * 4;             // bias row + one 32x33 fp32 transpose tile per epilogue warp
+    static constexpr int B_COPIES = (MODE == MODE_KK && BN == 128) ? 2 : 1;   // K-major weight tiles are 64-row blocks
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE + EPI_BYTES + (2 * STAGES + 1) * 8 + 16;
 };
 
 // element offset of TB element (row, unit) with R rows per block
@@ -67,7 +69,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     using Cfg = GemmCfg<MODE, BN>;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int STAGES = Cfg::STAGES, STAGE = Cfg::STAGE, A_BYTES = Cfg::A_BYTES, BK = Cfg::BK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE);
+    float* xpose_s = bias_s + BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE + Cfg::EPI_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* done = bars + 2 * STAGES;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     const long long off_bias = zi * g.bs[3] + zo * g.bs[8];
     const long long off_mask = zi * g.bs[4] + zo * g.bs[9];
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 2); mbar_init(empty + i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1 + Cfg::B_COPIES); mbar_init(empty + i, 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     if (warp == 0) {
         // ------------------------------------------------ producer: lane 0 copies A tiles, lane 1 B tiles;
         // each announces its own byte count (full[] counts two arrivals)
-        if (lane < 2) {
+        if (lane < 1 + Cfg::B_COPIES) {
             const __nv_bfloat16* src;
             long long kstep;                 // elements between consecutive k blocks
             uint32_t bytes = 0;              // MN-major: constant bytes per stage
@@ -125,8 +129,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                     unit_bytes = RA * 16; units_left = (k_end - k_begin + 15) / 16 * 2;
                 }
             } else {
-                if (MODE == MODE_KK) {       // weight [row block n0/64][units k/8 ..][64][8]
-                    src = g.B + off_b + ((long long)(n0 / RW) * g.units_b + k_begin / 8) * RW * 8;
+                if (MODE == MODE_KK) {       // weight [row block n0/64 (+1)][units k/8 ..][64][8]
+                    src = g.B + off_b + ((long long)(n0 / RW + lane - 1) * g.units_b + k_begin / 8) * RW * 8;
                     kstep = 8ll * RW * 8;
                     unit_bytes = RW * 16; units_left = (k_end - k_begin + 15) / 16 * 2;
                 } else if (MODE == MODE_KMN) {   // weight [row block kb (64 k rows)][units n0/8 ..][64][8]
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                     bytes = min(BN / 8, g.units_b - n0 / 8) * RA * 16;
                 }
             }
-            const uint32_t dst_off = lane == 0 ? 0 : A_BYTES;
+            const uint32_t dst_off = lane == 0 ? 0 : A_BYTES + (lane - 1) * (8 * RW * 16);
             int stage = 0; uint32_t phase = 0;
 #pragma unroll 1
             for (int kb = 0; kb < nk; ++kb) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         if (lane == 0) GT_STAMP(3);
     } else if (warp == 1) {
         // ------------------------------------------------ UMMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(GT_BM, BN, MODE == MODE_MNMN, MODE != MODE_KK);
+        constexpr uint32_t idesc = make_idesc_bf16(GT_BM, BN / Cfg::B_COPIES, MODE == MODE_MNMN, MODE != MODE_KK);
         int stage = 0; uint32_t phase = 0;
 #pragma unroll 1
         for (int kb = 0; kb < nk; ++kb) {
@@ -173,6 +177,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                                        : MODE == MODE_KMN ? make_smem_desc(b_addr + ks * 256, 128, RW * 16)
                                                           : make_smem_desc(b_addr + ks * 256, 128, RA * 16);
                     umma_bf16(tmem_base, da, db, idesc, (kb | ks) ? 1u : 0u);
+                    if (Cfg::B_COPIES == 2)
+                        umma_bf16(tmem_base + 64, da, make_smem_desc(b_addr + 8 * RW * 16 + ks * 2 * RW * 16, RW * 16, 128), idesc,
+                                  (kb | ks) ? 1u : 0u);
                 }
                 umma_commit(empty + stage);
                 if (kb == nk - 1) umma_commit(done);
@@ -181,49 +188,72 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------ epilogue
+        // ------------------------------------------------ epilogue.  While the main loop runs these warps stage
+        // the bias row in shared memory and pull their ReLU-mask rows into registers.
         const int q = warp & 3;
+        const int et = tid - 64;                                // 0..127
         const int m = m0 + q * 32 + lane;
         const long long mblk = m / RA, mrow = m % RA;          // TB row block / row inside it
         const float* bias = g.bias ? g.bias + off_bias : nullptr;
         const __nv_bfloat16* mask = g.mask ? g.mask + off_mask : nullptr;
         constexpr bool TB_OUT = EPI == DRQ_TEPI_RELU_BF16 || EPI == DRQ_TEPI_MASK_BF16;
+        constexpr bool MASKED = EPI == DRQ_TEPI_MASK_BF16 || EPI == DRQ_TEPI_TRUNK_DGRAD;
+        if (EPI == DRQ_TEPI_F32 || EPI == DRQ_TEPI_RELU_BF16) {
+            for (int j = et; j < BN; j += 128) bias_s[j] = (bias && n0 + j < g.N) ? __ldg(bias + n0 + j) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        uint4 mk[MASKED ? BN / 8 : 1];
+        if (MASKED && m < g.M) {
+#pragma unroll
+            for (int u = 0; u < BN / 8; ++u)
+                mk[u] = (n0 + 8 * u < g.units_mask * 8)
+                            ? __ldg(reinterpret_cast<const uint4*>(mask + ((mblk * g.units_mask + n0 / 8 + u) * RA + mrow) * 8))
+                            : make_uint4(0, 0, 0, 0);
+        }
+        float* xp = xpose_s + q * (32 * 33);
         mbar_wait(done, 0);
         tc_fence_after();
         if (tid == 64) GT_STAMP(6);
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             const int nb = n0 + c0;
             if (nb >= (TB_OUT ? g.n_store : g.N)) break;
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-            if (m >= g.M) continue;
             if (EPI == DRQ_TEPI_F32) {
-                float* crow = g.Cf + off_c + m * g.ldc + nb;
-                const int nv = g.N - nb;
+                // warp-local transpose through shared memory: every store instruction writes one row's 32
+                // consecutive floats (128 B) instead of 32 rows' single floats
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nv) {
-                        float x = v[j];
-                        if (bias) x += __ldg(bias + nb + j);
-                        if (g.accumulate) x += crow[j];
-                        crow[j] = x;
+                for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = v[j] + bias_s[c0 + j];
+                __syncwarp();
+                const int n = nb + lane;
+                const int rows = min(32, g.M - (m0 + q * 32));
+                float* cbase = g.Cf + off_c + (long long)(m0 + q * 32) * g.ldc + n;
+                if (n < g.N) {
+#pragma unroll 4
+                    for (int r = 0; r < rows; ++r) {
+                        float x = xp[r * 33 + lane];
+                        if (g.accumulate) x += cbase[r * g.ldc];
+                        cbase[r * g.ldc] = x;
                     }
                 }
-            } else if (EPI == DRQ_TEPI_TRUNK_WGRAD) {
+                continue;
+            }
+            if (m >= g.M) continue;
+            if (EPI == DRQ_TEPI_TRUNK_WGRAD) {
                 // columns nb..nb+31 = the 32 channels of NHWC feature pixel yx -> reference column c*1225 + yx
                 float* crow = g.Cf + off_c + m * g.ldc + (nb >> 5);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) crow[j * 1225] = v[j];
             } else if (EPI == DRQ_TEPI_TRUNK_DGRAD) {
-                // mask by feature > 0 (TB feature buffer: units nb/8 .. +3, row m) and scatter into conv4's WB gradient
+                // mask by feature > 0 and scatter into conv4's WB gradient
                 const int yx = nb >> 5;
                 const int yy = yx / 35, xx = yx - yy * 35;
                 const long long row = (long long)m * DRQ_PLB + DRQ_GUARD + yy * DRQ_PW + xx;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const uint4 mv = __ldg(reinterpret_cast<const uint4*>(
-                        mask + ((mblk * g.units_mask + nb / 8 + c) * RA + mrow) * 8));
+                    const uint4 mv = mk[MASKED ? c0 / 8 + c : 0];
                     const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
                     uint32_t pk[4];
 #pragma unroll
@@ -238,9 +268,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                 for (int c = 0; c < 4; ++c) {
                     const int n8 = nb + 8 * c;
                     if (n8 < g.n_store) {
-                        uint4 mv = make_uint4(0, 0, 0, 0);
-                        if (EPI == DRQ_TEPI_MASK_BF16)
-                            mv = __ldg(reinterpret_cast<const uint4*>(mask + ((mblk * g.units_mask + n8 / 8) * RA + mrow) * 8));
+                        const uint4 mv = mk[MASKED ? c0 / 8 + c : 0];
                         const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
                         uint32_t pk[4];
 #pragma unroll
@@ -248,8 +276,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                             float lo = v[8 * c + 2 * j], hi = v[8 * c + 2 * j + 1];
                             const int n = n8 + 2 * j;
                             if (EPI == DRQ_TEPI_RELU_BF16) {
-                                lo = n < g.N ? fmaxf(lo + __ldg(bias + n), 0.f) : 0.f;
-                                hi = n + 1 < g.N ? fmaxf(hi + __ldg(bias + n + 1), 0.f) : 0.f;
+                                lo = n < g.N ? fmaxf(lo + bias_s[c0 + 8 * c + 2 * j], 0.f) : 0.f;
+                                hi = n + 1 < g.N ? fmaxf(hi + bias_s[c0 + 8 * c + 2 * j + 1], 0.f) : 0.f;
                             } else {
                                 lo = (n < g.N && bf16_lo(mw[j]) > 0.f) ? lo : 0.f;
                                 hi = (n + 1 < g.N && bf16_hi(mw[j]) > 0.f) ? hi : 0.f;
@@ -344,8 +372,9 @@ int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b
     DRQ_REQUIRE(epilogue >= DRQ_TEPI_F32 && epilogue <= DRQ_TEPI_TRUNK_DGRAD, "gemm_bf16: bad epilogue");
     DRQ_REQUIRE(!((epilogue == DRQ_TEPI_MASK_BF16 || epilogue == DRQ_TEPI_TRUNK_DGRAD) && !mask), "gemm_bf16: mask missing");
     DRQ_REQUIRE(!(epilogue == DRQ_TEPI_RELU_BF16 && !bias), "gemm_bf16: bias missing");
-    DRQ_REQUIRE(!(splitk > 1 && (epilogue != DRQ_TEPI_F32 || mode != MODE_KK)), "gemm_bf16: split-K is for K-major fp32 partials");
-    DRQ_REQUIRE(!(mode == MODE_KK && bn != 64), "gemm_bf16: K-major weights are tiled 64 rows at a time (bn = 64)");
+    DRQ_REQUIRE(!(splitk > 1 && (epilogue != DRQ_TEPI_F32 || mode == MODE_MNMN)), "gemm_bf16: split-K writes fp32 partials (modes KK, KMN)");
+    DRQ_REQUIRE(!(mode == MODE_KK && bn == 128 && ((N + RW - 1) / RW) % 2 != 0),
+                "gemm_bf16: K-major bn = 128 reads pairs of 64-row weight blocks (N = %d)", N);
     // the blocked extents must cover what the tiles touch
     if (mode == MODE_MNMN) {
         DRQ_REQUIRE(units_a * 8 >= M && units_b * 8 >= N, "gemm_bf16: MN-major units smaller than M / N");
@@ -380,6 +409,8 @@ int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b
     if (mode == MODE_ && bn == BN_ && epilogue == EPI_) return launch_gemm_tc<MODE_, BN_, EPI_>(g, batch, s);
     GT_CASE(MODE_KK, 64, DRQ_TEPI_F32)
     GT_CASE(MODE_KK, 64, DRQ_TEPI_RELU_BF16)
+    GT_CASE(MODE_KK, 128, DRQ_TEPI_F32)
+    GT_CASE(MODE_KK, 128, DRQ_TEPI_RELU_BF16)
     GT_CASE(MODE_KMN, 64, DRQ_TEPI_F32)
     GT_CASE(MODE_KMN, 64, DRQ_TEPI_MASK_BF16)
     GT_CASE(MODE_KMN, 128, DRQ_TEPI_MASK_BF16)

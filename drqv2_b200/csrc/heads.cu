@@ -82,7 +82,7 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
                        long long ld_h, const float* __restrict__ xhat,
                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                        float* __restrict__ dz, float* __restrict__ dy_out, __nv_bfloat16* __restrict__ dz_bf,
-                       long long rpad_zb, int B, int F) {
+                       long long rpad_zb, int B, int F, int n_planes, long long plane_stride) {
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -94,7 +94,9 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
         dxh[i] = 0.f; xh[i] = 0.f;
         if (f < F) {
             const float hv = h[(long long)row * ld_h + f];
-            const float dy = dh[(long long)row * ld_dh + f] * (1.0f - hv * hv);
+            float dhv = 0.f;                                   // dh = sum of the split-K / per-head partial planes
+            for (int pl = 0; pl < n_planes; ++pl) dhv += dh[pl * plane_stride + (long long)row * ld_dh + f];
+            const float dy = dhv * (1.0f - hv * hv);
             dy_out[(long long)row * F + f] = dy;
             xh[i] = xhat[(long long)row * F + f];
             dxh[i] = dy * gamma[f];
@@ -191,12 +193,15 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
 
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long ld_da,
                                         const float* __restrict__ mu, float* __restrict__ dmu_pre,
-                                        __nv_bfloat16* __restrict__ dmu_bf, long long rpad_mb, int B, int A) {
+                                        __nv_bfloat16* __restrict__ dmu_bf, long long rpad_mb, int B, int A,
+                                        int n_planes, long long plane_stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * A) return;
     const int b = i / A, j = i - b * A;
     const float m = mu[i];
-    const float g = da[(long long)b * ld_da + j] * (1.0f - m * m);
+    float dav = 0.f;
+    for (int pl = 0; pl < n_planes; ++pl) dav += da[pl * plane_stride + (long long)b * ld_da + j];
+    const float g = dav * (1.0f - m * m);
     dmu_pre[i] = g;
     if (dmu_bf) dmu_bf[fb_index(j, b, rpad_mb)] = __float2bfloat16_rn(g);
 }
@@ -414,14 +419,16 @@ int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const flo
 
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, const float* xhat,
                     const float* rstd, const float* gamma, float* dz, float* dgamma, float* dbeta,
-                    uint16_t* dz_bf16, int64_t rpad_zb, int B, int F, void* stream) {
-    DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && dgamma && dbeta, "ln_tanh_bwd: null pointer");
+                    uint16_t* dz_bf16, int64_t rpad_zb, int B, int F, int n_planes, int64_t plane_stride,
+                    void* stream) {
+    DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && dgamma && dbeta && n_planes >= 1, "ln_tanh_bwd: null pointer");
     DRQ_REQUIRE(B > 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_bwd: bad dims (F<=256)");
     // dy = dh * tanh' is staged in the second half of the caller's 2*B*F buffer
     float* dy = dz + (long long)B * F;
     ln_tanh_bwd_row_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(dh, ld_dh, h, ld_h, xhat, rstd,
                                                                       gamma, dz, dy,
-                                                                      reinterpret_cast<__nv_bfloat16*>(dz_bf16), rpad_zb, B, F);
+                                                                      reinterpret_cast<__nv_bfloat16*>(dz_bf16), rpad_zb, B, F,
+                                                                      n_planes, plane_stride);
     if (int rc = check_launch("ln_tanh_bwd_row_kernel")) return rc;
     ln_param_grad_kernel<<<F, 256, 0, as_stream(stream)>>>(dy, xhat, dgamma, dbeta, B, F);
     return check_launch("ln_param_grad_kernel");
@@ -440,11 +447,13 @@ int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev
 }
 
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
-                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, void* stream) {
-    DRQ_REQUIRE(daction && mu && dmu_pre && B > 0 && A > 0, "actor_sample_bwd: bad args");
+                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, int n_planes, int64_t plane_stride,
+                         void* stream) {
+    DRQ_REQUIRE(daction && mu && dmu_pre && B > 0 && A > 0 && n_planes >= 1, "actor_sample_bwd: bad args");
     actor_sample_bwd_kernel<<<(B * A + 255) / 256, 256, 0, as_stream(stream)>>>(daction, ld_da, mu,
                                                                                 dmu_pre,
-                                                                                reinterpret_cast<__nv_bfloat16*>(dmu_bf16), rpad_mb, B, A);
+                                                                                reinterpret_cast<__nv_bfloat16*>(dmu_bf16), rpad_mb, B, A,
+                                                                                n_planes, plane_stride);
     return check_launch("actor_sample_bwd_kernel");
 }
 

@@ -728,7 +728,7 @@ class DrQV2Agent:
         # --- trunk backward: tanh, LayerNorm, Linear
         call("drq_ln_tanh_bwd", ws.dx.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
              ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), gc("trunk.1.weight"),
-             gc("trunk.1.bias"), None, 0, B, Fd, s)
+             gc("trunk.1.bias"), None, 0, B, Fd, 1, 0, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, gc("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd)
         if encoder_grad:
@@ -795,7 +795,7 @@ class DrQV2Agent:
         _linear_dgrad(dc2, H, pc("Q1.2.weight"), dc1, H, B, H, H, mask=c1, ldmask=H, batch=2, bs=(BH, qs, BH, 0, BH))
         _linear_dgrad(dc1, H, pc("Q1.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A)
         _linear_dgrad(dc1 + F32 * BH, H, pc("Q2.0.weight"), ws.dact.data_ptr(), A, B, H, Fd + A, w_col0=Fd, n_cols=A, acc=1)
-        call("drq_actor_sample_bwd", ws.dact.data_ptr(), A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(), None, 0, B, A, s)
+        call("drq_actor_sample_bwd", ws.dact.data_ptr(), A, ws.mu.data_ptr(), ws.dmu_pre.data_ptr(), None, 0, B, A, 1, 0, s)
         # actor MLP backward
         dmu, p1, p2, dp1, dp2 = (t.data_ptr() for t in (ws.dmu_pre, ws.p1, ws.p2, ws.dp1, ws.dp2))
         _linear_wgrad(dmu, A, p2, H, ga("policy.4.weight"), B, A, H)
@@ -809,7 +809,7 @@ class DrQV2Agent:
         _linear_dgrad(dp1, H, pa("policy.0.weight"), ws.dhA.data_ptr(), Fd, B, H, Fd)
         call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(),
              ws.rstdA.data_ptr(), pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"),
-             ga("trunk.1.bias"), None, 0, B, Fd, s)
+             ga("trunk.1.bias"), None, 0, B, Fd, 1, 0, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, ga("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd)
         # actor_opt.step() fused with the soft target update of the (already stepped) critic

@@ -243,6 +243,9 @@ int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b
 /* debug aid: clock64 timeline of block (0,0,0) of every later drq_gemm_bf16 launch into buf (>= 16
  * int64, device memory); NULL switches it off. */
 int drq_debug_gemm_stamps(int64_t* buf);
+/* the same for drq_conv3x3_{fwd,dgrad}_bf16: [0] producer wait-for-empty, [1] producer total, [2] issuer
+ * wait-for-accumulator, [3] issuer wait-for-data, [4] issuer total, [5] epilogue wait-for-accumulator (cycles). */
+int drq_debug_conv_stamps(int64_t* buf);
 
 /* fp32 nn.Linear weight [rows][cols] -> TB(DRQ_TB_W) bf16 [ceil(rows/64)][ceil16(cols)/8][64][8]. */
 int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* stream);
@@ -295,13 +298,15 @@ typedef struct {
 } drq_ln_job;
 int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float eps, void* stream);
 
-/* backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
+/* dh may arrive as n_planes partial planes (plane_stride floats apart) that are summed on the fly - the
+ * per-head / split-K partial products of the Q heads' first-layer data gradient.
+ * backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
  * output), dgamma[F], dbeta[F].  h is the saved tanh output (ld_h).
  * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) is scratch. */
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h,
                     const float* xhat, const float* rstd, const float* gamma, float* dz,
                     float* dgamma, float* dbeta, uint16_t* dz_bf16, int64_t rpad_zb, int B, int F,
-                    void* stream);
+                    int n_planes, int64_t plane_stride, void* stream);
 
 /* ------------------------------------------------------------------ heads */
 
@@ -317,7 +322,8 @@ int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev
 
 /* d(mu_pre) = d(action) * (1 - mu^2)   (straight-through clamp, utils.py:113-116) */
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,
-                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, void* stream);
+                         uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, int n_planes, int64_t plane_stride,
+                         void* stream);
 
 /* TD target + critic loss (drqv2.py:185-189): tq = r + d*min(tq1,tq2);
  * loss = mean((q1-tq)^2) + mean((q2-tq)^2); dq1 = 2(q1-tq)/B, dq2 likewise.

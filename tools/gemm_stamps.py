@@ -32,6 +32,6 @@ run("wgrad 2x(1024x1024x256) bn64", lambda: gemm(x.ptr(), x.units, y.ptr(), y.un
 x56 = TB(Bt, 56, dev); w56 = TB(H, 56, dev, rblk=64)
 run("fwd K=56", lambda: gemm(x56.ptr(), x56.units, w56.ptr(), w56.units, GEMM_KK, y.ptr(), y.units, Bt, H, 56, TEPI_RELU_BF16, bias=bias.data_ptr()))
 feat = TB(512, 39200, dev); wt = TB(192, 39200, dev, rblk=64)
-S = 62
+S = 37
 part = torch.zeros(S * 2 * 256 * 128, device=dev)
-run("trunk fwd merged (2 x 256 x 128, splitk 62)", lambda: gemm(feat.ptr(), feat.units, wt.ptr(row=64), wt.units, GEMM_KK, part.data_ptr(), 128, 256, 128, 39200, TEPI_F32, batch=2, batch_inner=1, splitk=S, strides=_strides(outer=(feat.off(row=256), -wt.off(row=64), 256 * 128, 0, 0), split=2 * 256 * 128)))
+run("trunk fwd merged (2 x 256 x 128, splitk 37, bn 128)", lambda: gemm(feat.ptr(), feat.units, wt.ptr(row=64), wt.units, GEMM_KK, part.data_ptr(), 128, 256, 128, 39200, TEPI_F32, batch=2, batch_inner=1, bn=128, splitk=S, strides=_strides(outer=(feat.off(row=256), -wt.off(row=64), 256 * 128, 0, 0), split=2 * 256 * 128)))
