@@ -275,12 +275,66 @@ def run_ours(args, rank, world):
     return out
 
 
+def _load_reference():
+    """The unmodified reference modules from baseline/_ref (baseline/install_ref.py), or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "drqv2.py")):
+        return None
+    import types
+    for name in ("hydra", "omegaconf"):                     # imported by the reference, unused on this path
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if not hasattr(sys.modules["omegaconf"], "OmegaConf"):
+        sys.modules["omegaconf"].OmegaConf = object
+    import importlib.util
+    mods = {}
+    for name in ("utils", "drqv2"):
+        spec = importlib.util.spec_from_file_location(f"_ref_{name}", os.path.join(ref, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        if name == "drqv2":
+            saved = sys.modules.get("utils")
+            sys.modules["utils"] = mods["utils"]            # the reference's `import utils`
+            try:
+                spec.loader.exec_module(m)
+            finally:
+                if saved is None:
+                    sys.modules.pop("utils", None)
+                else:
+                    sys.modules["utils"] = saved
+        else:
+            spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["drqv2"]
+
+
 def cpu_baseline(args, steps=2, warm=1):
-    """The oracle port of the reference's update (torch CPU, all host threads) on a bounded
-    sample: `steps` updates of the same B=256 workload."""
-    from oracle import drq_oracle as O
+    """The reference's own agent.update (unmodified sources in baseline/_ref, device 'cpu', all host
+    threads) on a bounded sample: `steps` updates of the same B=256 workload from pre-collated tensors.
+    Falls back to the oracle port of the same path when the reference sources are not present."""
     torch.set_num_threads(os.cpu_count())
     B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    ref = _load_reference()
+    if ref is not None:
+        torch.manual_seed(0)
+        agent = ref.DrQV2Agent((9, 84, 84), (A,), "cpu", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False)
+        g = torch.Generator().manual_seed(1)
+        batch = (torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g),
+                 torch.rand(B, A, generator=g) * 2 - 1, torch.rand(B, 1, generator=g),
+                 torch.full((B, 1), 0.970299065), torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g))
+
+        def it():
+            while True:
+                yield batch
+        ri = it()
+        for i in range(warm):
+            agent.update(ri, 2 * i)
+        t = time.perf_counter()
+        for i in range(steps):
+            agent.update(ri, 2 * (i + warm))
+        dt = (time.perf_counter() - t) / steps
+        return {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{steps} updates (after {warm} warm-up) of the reference's DrQV2Agent.update on CPU, B={B}, "
+                          "pre-collated synthetic tensors"}
+    from oracle import drq_oracle as O
     params = O.synthetic_params(9, A, Fd, H, seed=0)
     agent = O.OracleAgent(params, 1e-4, 0.01, SCHED, 0.3, dtype=torch.float32, aug="grid")
     b = O.synthetic_batch(B, A, seed=1)
@@ -308,7 +362,7 @@ def run_reference(args, rank, world):
             "unit": "updates/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[0]: reference's CPU update path (oracle port, torch CPU), B={B}, A={A}, "
+            "config": {"workload": f"configs[0]: reference's CPU update path ({cpu['kind']}, torch CPU), B={B}, A={A}, "
                                    f"F={Fd}, H={H}"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
