@@ -125,7 +125,7 @@ class Bf16State:
         assert d % F32 == 0
         self.target_minus_critic = d // F32
         # encoder: conv1 packed + (fwd, dgrad) operands of conv2..4
-        self.conv1_w = torch.zeros(12 * 32 * 8, dtype=torch.bfloat16, device=dev)
+        self.conv1_w = torch.zeros(_lib.lib().drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)   # fp16 weights + fused bias
         self.conv_wf = [torch.zeros(36 * 32 * 8, dtype=torch.bfloat16, device=dev) for _ in range(3)]
         self.conv_wd = [torch.zeros(36 * 32 * 8, dtype=torch.bfloat16, device=dev) for _ in range(3)]
 
@@ -134,7 +134,8 @@ class Bf16State:
 
     def repack_encoder(self):
         ag, s = self.agent, _stream()
-        call("drq_pack_conv1_w_bf16", ag._p("encoder", "convnet.0.weight"), self.conv1_w.data_ptr(), ag.obs_shape[0], s)
+        call("drq_pack_conv1_w_bf16", ag._p("encoder", "convnet.0.weight"), ag._p("encoder", "convnet.0.bias"),
+             self.conv1_w.data_ptr(), ag.obs_shape[0], s)
         for i, k in enumerate((2, 4, 6)):
             call("drq_pack_conv_w_bf16", ag._p("encoder", f"convnet.{k}.weight"), self.conv_wf[i].data_ptr(),
                  self.conv_wd[i].data_ptr(), s)
@@ -214,7 +215,7 @@ def encode(agent, ws, bw):
     st, B, s = agent._bf16, ws.B, _stream()
     be = lambda i: agent._p("encoder", f"convnet.{i}.bias")
     acts = [a.data_ptr() for a in bw.acts]
-    call("drq_conv1_fwd_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), st.conv1_w.data_ptr(), be(0), acts[0],
+    call("drq_conv1_fwd_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), st.conv1_w.data_ptr(), acts[0],
          2 * B, agent.obs_shape[0], agent.aug.pad, s)
     call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), be(2), acts[1], 2 * B, 39, 0, 0, 0, 0, s)
     call("drq_conv3x3_fwd_bf16", acts[1], st.conv_wf[1].data_ptr(), be(4), acts[2], 2 * B, 37, 0, 0, 0, 0, s)
@@ -431,7 +432,7 @@ def act_body(agent, w, n, sample):
     be = lambda i: agent._p("encoder", f"convnet.{i}.bias")
     acts = [a.data_ptr() for a in w["acts_b"]]
     feat = w["feat_b"]
-    call("drq_conv1_fwd_bf16", w["obs"].data_ptr(), None, st.conv1_w.data_ptr(), be(0), acts[0], n,
+    call("drq_conv1_fwd_bf16", w["obs"].data_ptr(), None, st.conv1_w.data_ptr(), acts[0], n,
          agent.obs_shape[0], agent.aug.pad, s)
     call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), be(2), acts[1], n, 39, 0, 0, 0, 0, s)
     call("drq_conv3x3_fwd_bf16", acts[1], st.conv_wf[1].data_ptr(), be(4), acts[2], n, 37, 0, 0, 0, 0, s)

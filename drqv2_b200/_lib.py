@@ -35,12 +35,13 @@ SIGNATURES = {
     "drq_conv3x3_fwd_bf16": [P, P, P, P, I, I, I, L, I, I, P],
     "drq_conv3x3_dgrad_bf16": [P, P, P, I, P, I, I, P],
     "drq_conv3x3_wgrad_bf16": [P, I, P, P, P, P, I, I, P],
-    "drq_pack_conv1_w_bf16": [P, P, I, P],
-    "drq_conv1_fwd_bf16": [P, P, P, P, P, I, I, I, P],
+    "drq_pack_conv1_w_bf16": [P, P, P, I, P],
+    "drq_conv1_fwd_bf16": [P, P, P, P, I, I, I, P],
     "drq_conv1_wgrad_bf16": [P, P, P, P, P, P, I, I, I, P],
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_conv_stamps": [P],
+    "drq_debug_conv1_stamps": [P],
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
@@ -71,6 +72,7 @@ SPECIAL = {
     "drq_wb_elems": (L, [I]),
     "drq_conv_wgrad_bf16_ws_floats": (L, []),
     "drq_conv1_wgrad_bf16_ws_floats": (L, []),
+    "drq_conv1_w_packed_elems": (L, []),
 }
 
 EPI_NONE, EPI_RELU, EPI_MASK, EPI_MASK_WIDE = 0, 1, 2, 3

@@ -1,16 +1,30 @@
 // conv1 of the encoder (drqv2.py:55: Cin->32, k3, stride 2) on tensor cores, with
 // RandomShiftsAug (integer shift, drqv2.py:19-45) and obs/255-0.5 (drqv2.py:64) fused into
-// the loader: builder warps gather the augmented, normalised 3x3xCin patch of every output
-// position straight from the uint8 frame stack into an im2col tile in shared memory (canonical
+// the loader: builder warps gather the augmented 3x3xCin patch of every output position
+// straight from the uint8 frame stack into an im2col tile in shared memory (canonical
 // no-swizzle UMMA layout [K unit][position][16 B]); the augmented image never exists in HBM.
 //
-//   forward : out[p][co] = relu(b[co] + sum_k im2col[p][k] * W[co][k])     M=128 pos, N=32, K=96
-//   wgrad   : dW[co][k]  = sum_p d[p][co] * im2col[p][k]                   M=64(co), N=96, K=pos
-// K = cin*9 is padded to 96; slot k = cin*9 holds the constant 1.0 so that the weight-gradient
-// GEMM's column cin*9 is the bias gradient (the forward weight there is zero).
+//   forward : out[p][co] = relu(b'[co] + (1/255) sum_k im2col[p][k] * W[co][k])   M=128 pos, N=32, K=96
+//   wgrad   : S[co][k]   = sum_p d[p][co] * im2col[p][k]                          M=64(co), N=96, K=pos
 //
-// Warp roles (416 threads): warps 0..7 build im2col tiles, warp 8 issues UMMAs (and bulk-loads
-// the gradient tile in wgrad), warps 9..12 run the epilogue.
+// The im2col entries are the exact integers x - 128 in bf16 (|x - 128| <= 128 has at most 8 significant
+// bits, so no rounding of the pixels): a byte permute with 0x4B000000 turns a uint8 into the float
+// 2^23 + x, one subtract centres it, one cvt packs two of them.  The affine map x/255 - 0.5 = (x - 128)/255 + (128/255 - 0.5) moves to the epilogues:
+//   forward : b'[co] = b[co] + (128/255 - 0.5) sum_k bf16(W[co][k])   (pack kernel), accumulator scaled by 1/255
+//   wgrad   : dW[co][k] = S[co][k]/255 + (128/255 - 0.5) db[co],  db[co] = S[co][cin*9]
+// K = cin*9 is padded to 96; slot k = cin*9 holds the constant 1.0 so that column cin*9 of the
+// weight-gradient GEMM is the bias gradient (the forward weight there is zero).  (kind::f16 needs both
+// operands in the same 16-bit format - mixing an fp16 im2col with the bf16 gradient tile traps - hence
+// bf16 rather than the cheaper fp16 construction.)
+//
+// Loader: the (vertically clamped) source rows of a tile are staged per channel as replicate-padded
+// rows [4 | 84 | 4] bytes, so the horizontal shift is an address offset and the three kx taps of one
+// (channel, ky) are three consecutive bytes: two aligned 32-bit loads + a funnel shift per group of
+// three K entries instead of a byte load and a table lookup per entry.
+//
+// Warp roles (704 threads): warps 0..15 re-pitch the rows + build im2col tiles (4 threads per output
+// position), warp 16 issues UMMAs (and bulk-loads the gradient tile in wgrad), warps 17..20 run the
+// epilogue, warp 21 bulk-copies the source rows of the next tiles (4 stages ahead).
 #include "tc_common.cuh"
 
 namespace drq {
@@ -21,28 +35,42 @@ constexpr int kC1K = 96, kC1Units = kC1K / 8;
 constexpr int kC1Tile = 128;
 constexpr int kC1ABytes = kC1Units * kC1Tile * 16;     // 24576
 constexpr int kC1Stages = 3;
-constexpr int kC1WBytes = kC1Units * 32 * 16;          // weights [12][32][16 B]
-constexpr int kC1Threads = 13 * 32;
+constexpr int kC1WBytes = kC1Units * 32 * 16;          // weights [12][32][16 B] (+ 32 fused biases behind them)
+constexpr int kC1Builders = 512;                        // 16 builder warps: 4 threads per output position
+constexpr int kC1Threads = kC1Builders + 6 * 32;       // + UMMA warp, 4 epilogue warps, row producer warp
 constexpr int kC1DBytes = 4 * kC1Tile * 16;            // wgrad: d tile [4 blocks][128][16 B]
 constexpr int kC1Acc = 4;
+constexpr float kC1Scale = 1.0f / 255.0f;
+constexpr float kC1Shift = 128.0f / 255.0f - 0.5f;     // (x - 128)/255 + kC1Shift == x/255 - 0.5
 
 struct Conv1TcArgs {
     const uint8_t* obs; const int* shift; int cin, pad;
-    const __nv_bfloat16* w;       // fwd: packed [12][32][8]
-    const float* bias;
+    const __nv_bfloat16* w;       // fwd: packed bf16 [12][32][8], then float bias'[32]
     __nv_bfloat16* out; long long cs_out;          // fwd: WB output
     const __nv_bfloat16* d; long long cs_d;        // wgrad: WB gradient (N images)
     float* partial;                                // wgrad: [grid][32][96]
     int n_images;
+    long long* stamps;                             // debug: builder cycle totals of block 0 (or null)
 };
 
-// Input rows of one tile staged in shared memory: per channel the contiguous byte range of the
-// (clamped) source rows [rlo, rhi], at most 11 rows x 84 B = 231 words.
-constexpr int kC1RowWords = kImg / 4;                 // 21
-constexpr int kC1ChWords = 11 * kC1RowWords;          // 231
-constexpr int kC1ChBytes = 928;                       // 231 words padded to 16 B
-constexpr int kC1StageWords = 10;                     // ceil(10 ch * 231 / 256) words per builder thread (cin <= 10)
-constexpr int kC1InBytes = 10 * kC1ChBytes;           // one staging buffer
+static long long* g_c1_stamps = nullptr;
+#ifdef DRQ_STAMPS
+#define C1_T() (a.stamps ? clock64() : 0ll)
+#else
+#define C1_T() 0ll
+#endif
+
+// Input rows of one tile staged in shared memory: per channel up to 11 (clamped) source rows, each as a
+// replicate-padded row of kC1RowBytes.
+constexpr int kC1RowWords = kImg / 4;                 // 21 source words per row
+constexpr int kC1MaxRows = 11;
+constexpr int kC1RowBytes = 96;                       // [4 pad | 84 | 4 pad | 4 slack]
+constexpr int kC1ChBytes = kC1MaxRows * kC1RowBytes;  // 1056
+constexpr int kC1ChWords = kC1MaxRows * kC1RowWords;  // 231 source words per channel
+constexpr int kC1InBytes = 10 * kC1ChBytes;           // one padded-row buffer (cin <= 10)
+constexpr int kC1RawSlot = 960;                       // raw rows of one channel: <= 15 + 11 * 84 bytes, 16-byte granular
+constexpr int kC1RawBytes = 10 * kC1RawSlot;          // one raw stage
+constexpr int kC1RawStages = 4;
 
 struct TileGeom { int n, p0, rlo, nrows; };
 
@@ -60,73 +88,103 @@ __device__ __forceinline__ TileGeom tile_geom(int t, const int* __restrict__ shi
     return g;
 }
 
-// each builder thread fetches up to kC1StageWords 4-byte words of the tile's input rows
-__device__ __forceinline__ void fetch_rows(uint32_t (&regs)[kC1StageWords], const uint8_t* __restrict__ obs,
-                                           const TileGeom& g, int cin, int b) {
-    const uint32_t* img = reinterpret_cast<const uint32_t*>(obs + (long long)g.n * cin * kImg * kImg);
-    const int nwords = g.nrows * kC1RowWords;
-#pragma unroll
-    for (int i = 0; i < kC1StageWords; ++i) {
-        const int w = b + 256 * i;
-        const int ci = w / kC1ChWords, j = w - ci * kC1ChWords;
-        regs[i] = (ci < cin && j < nwords) ? __ldg(img + ci * (kImg * kImg / 4) + g.rlo * kC1RowWords + j) : 0u;
-    }
-}
-__device__ __forceinline__ void store_rows(const uint32_t (&regs)[kC1StageWords], uint8_t* stage, int b) {
-#pragma unroll
-    for (int i = 0; i < kC1StageWords; ++i) {
-        const int w = b + 256 * i;
-        const int ci = w / kC1ChWords, j = w - ci * kC1ChWords;
-        if (ci < 10) *reinterpret_cast<uint32_t*>(stage + ci * kC1ChBytes + 4 * j) = regs[i];
+// The row producer warp lands the tile's (vertically clamped) source rows of every channel in shared
+// memory with one bulk-async copy per channel (the rows of a channel are contiguous in the frame stack);
+// the builders then re-pitch them as replicate-padded rows (drqv2.py:26 F.pad(mode='replicate'),
+// horizontally).  Thread (channel ci, word jw) walks the rows: no index arithmetic in the loop.
+__device__ __forceinline__ void pad_rows(const uint8_t* __restrict__ raw, uint8_t* __restrict__ stage, int off0, int nrows,
+                                         int cin, int b) {
+    constexpr int RW = kC1RowBytes / 4;
+    if (b < cin * kC1RowWords) {
+        // thread (channel ci, word jw): copy the 84 pixel bytes of every row to byte 4 of the padded row
+        const int ci = b / kC1RowWords, jw = b - ci * kC1RowWords;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + ci * kC1RawSlot + off0) + jw;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(stage + ci * kC1ChBytes) + 1 + jw;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) dst[r * RW] = src[r * kC1RowWords];
+    } else if (b < cin * kC1RowWords + 2 * cin) {
+        // thread (channel ci, side): the replicate pad words - pixel 0 x4 on the left, pixel 83 x4 on the right
+        const int e = b - cin * kC1RowWords, ci = e >> 1, side = e & 1;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + ci * kC1RawSlot + off0) + (side ? kC1RowWords - 1 : 0);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(stage + ci * kC1ChBytes) + (side ? 1 + kC1RowWords : 0);
+        const uint32_t sel = side ? 0x3333u : 0x0000u;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) dst[r * RW] = __byte_perm(src[r * kC1RowWords], 0, sel);
     }
 }
 
-// one builder thread: position r of the tile, K range [K0, K0+48); pixels come from the staged
-// rows, the u8 -> bf16(x/255 - 0.5) map (drqv2.py:64) from a 256-entry table
-template <int K0>
-__device__ __forceinline__ void build_half(uint8_t* tile, const uint8_t* __restrict__ stage,
-                                           const uint16_t* __restrict__ lut, int cin, int r, bool valid,
-                                           const int (&off9)[9]) {
-    const int kmax = cin * 9;
+// bf16 pair (x_A - 128, x_B - 128) from byte bA of group word gA (low half) and byte bB of gB (high half):
+// a byte permute with 0x4B000000 makes the float 2^23 + x, subtracting 2^23 + 128 is exact, and so is the
+// conversion to bf16 (|x - 128| <= 128 has at most 8 significant bits).
+__device__ __forceinline__ float centred(uint32_t g, int b) {
+    return __uint_as_float(__byte_perm(g, 0x4B000000u, (uint32_t)b | 0x7650u)) - 8388736.0f;
+}
+__device__ __forceinline__ uint32_t pair_from(uint32_t gA, int bA, uint32_t gB, int bB) {
+    return pack_bf16x2(centred(gA, bA), centred(gB, bB));
+}
+__device__ __forceinline__ uint32_t one_from(uint32_t gA, int bA) {              // low half x - 128, high half 0
+    return pack_bf16x2(centred(gA, bA), 0.f);
+}
+
+// One builder thread: position r of the tile, K units [U0, U0 + 3).  K entry k = 9*c + 3*ky + kx; group
+// i = k / 3 = 3*c + ky is three consecutive bytes of channel c's staged row ky at byte offset g.
+template <int U0, int CIN>                             // CIN = compile-time channel count, 0 = use cin
+__device__ __forceinline__ void build_part(uint8_t* tile, const uint8_t* __restrict__ stage, int cin, int r,
+                                           const int (&rowoff)[3], int g) {
+    constexpr int G0 = U0 * 8 / 3;                     // first group of this quarter (0, 8, 16, 24)
+    constexpr int NG = 8;                              // 24 K entries = 8 groups
+    const int kmax = CIN ? CIN * 9 : cin * 9;
+    uint32_t grp[NG];
+    const int sh = (g & 3) * 8;
+    const uint8_t* base[3];
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
+    for (int ky = 0; ky < 3; ++ky) base[ky] = stage + rowoff[ky] + (g & ~3);
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+        const int gi = G0 + i, c = gi / 3, ky = gi % 3;
+        uint32_t v = 0;
+        if (gi * 3 < kmax) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(base[ky] + c * kC1ChBytes);
+            v = __funnelshift_r(p[0], p[1], sh);
+        }
+        grp[i] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            uint32_t hv[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = K0 + u * 8 + e * 2 + h;
-                const int ci = k / 9, t = k % 9;
-                uint32_t v = 0;
-                if (valid) {
-                    if (k < kmax) v = lut[stage[ci * kC1ChBytes + off9[t]]];
-                    else if (k == kmax) v = 0x3F80u;       // bf16 1.0: the bias-gradient column
-                }
-                hv[h] = v;
-            }
-            w[e] = hv[0] | (hv[1] << 16);
+            const int kA = (U0 + u) * 8 + 2 * e, kB = kA + 1;
+            const int iA = kA / 3 - G0, iB = kB / 3 - G0;
+            uint32_t v = 0;
+            if (kB < kmax) v = pair_from(grp[iA], kA % 3, grp[iB], kB % 3);
+            else if (kA < kmax) v = one_from(grp[iA], kA % 3) | (kB == kmax ? 0x3F800000u : 0u);   // data | 1.0
+            else if (kA == kmax) v = 0x00003F80u;                                                    // 1.0 | 0
+            w[e] = v;
         }
-        *reinterpret_cast<uint4*>(tile + (K0 / 8 + u) * (kC1Tile * 16) + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(tile + (U0 + u) * (kC1Tile * 16) + r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
-template <bool WGRAD>
+template <bool WGRAD, int CIN>
 __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int STAGE = kC1ABytes + (WGRAD ? kC1DBytes : 0);
-    uint8_t* w_s = smem;                                    // fwd only
-    uint8_t* in_s = smem + kC1WBytes;                       // 2 x staged input rows
-    uint16_t* lut_s = reinterpret_cast<uint16_t*>(in_s + 2 * kC1InBytes);
-    uint8_t* st_s = in_s + 2 * kC1InBytes + 512;
+    uint8_t* w_s = smem;                                    // fwd only: packed weights
+    float* bias_s = reinterpret_cast<float*>(smem + kC1WBytes);   // fwd only: fused bias'
+    uint8_t* in_s = smem + kC1WBytes + 128;                 // 2 builder groups x 2 padded-row buffers
+    uint8_t* raw_s = in_s + 4 * kC1InBytes;                 // kC1RawStages x raw rows (bulk-copy destinations)
+    uint8_t* st_s = raw_s + kC1RawStages * kC1RawBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kC1Stages * STAGE + (WGRAD ? kC1DBytes : 0));
-    uint64_t* full = bars;                     // builders (256 arrivals) [+ d-tile tx in wgrad: separate barrier]
+    uint64_t* full = bars;                     // one builder group (256 arrivals)
     uint64_t* empty = bars + kC1Stages;
     uint64_t* dfull = bars + 2 * kC1Stages;    // wgrad: bulk copy of the d tile
     uint64_t* tfull = bars + 3 * kC1Stages;
     uint64_t* tempty = bars + 3 * kC1Stages + kC1Acc;
     uint64_t* done = bars + 3 * kC1Stages + 2 * kC1Acc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    uint64_t* rfull = done + 1;                // raw rows landed (cin producer lanes announce their bytes)
+    uint64_t* rempty = rfull + kC1RawStages;   // raw stage re-pitched by the 256 builders of a group
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kC1RawStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int TILES_PER_IMG = (kPW * kPW + kC1Tile - 1) / kC1Tile;   // 14
@@ -135,18 +193,16 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     if (!WGRAD) {
         const uint4* src = reinterpret_cast<const uint4*>(a.w);
         uint4* dst = reinterpret_cast<uint4*>(w_s);
-        for (int i = threadIdx.x; i < kC1WBytes / 16; i += kC1Threads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < (kC1WBytes + 128) / 16; i += kC1Threads) dst[i] = __ldg(src + i);
     }
-    if (threadIdx.x < 256)
-        lut_s[threadIdx.x] = __bfloat16_as_ushort(__float2bfloat16_rn(
-            __fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f)));          // drqv2.py:64, then bf16
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kC1Stages; ++i) { mbar_init(full + i, 256); mbar_init(empty + i, 1); mbar_init(dfull + i, 1); }
+        for (int i = 0; i < kC1Stages; ++i) { mbar_init(full + i, kC1Builders / 2); mbar_init(empty + i, 1); mbar_init(dfull + i, 1); }
         for (int i = 0; i < kC1Acc; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
         mbar_init(done, 1);
+        for (int i = 0; i < kC1RawStages; ++i) { mbar_init(rfull + i, a.cin); mbar_init(rempty + i, kC1Builders / 2); }
         fence_barrier_init();
     }
-    if (warp == 8) {
+    if (warp == 16) {
         tmem_alloc(tmem_slot, 128);
         tmem_relinquish();
     }
@@ -156,48 +212,56 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
-        // ------------------------------------------------ im2col builders
-        const int b = threadIdx.x, r = b & 127, half = b >> 7;
-        int stage = 0; uint32_t phase = 0; int buf = 0;
-        uint32_t regs[kC1StageWords];
-        TileGeom g = tile_geom(blockIdx.x, a.shift, a.pad);
-        if ((int)blockIdx.x < total_tiles) fetch_rows(regs, a.obs, g, a.cin, b);
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            uint8_t* stg = in_s + buf * kC1InBytes;
-            store_rows(regs, stg, b);
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // staged rows visible to all builders
-            const TileGeom cur = g;
-            const int tn = t + gridDim.x;
-            if (tn < total_tiles) {                              // prefetch the next tile's rows (in flight during the build)
-                g = tile_geom(tn, a.shift, a.pad);
-                fetch_rows(regs, a.obs, g, a.cin, b);
-            }
-            const int p = cur.p0 + r;
-            const bool valid = p < kPW * kPW;
+    if (warp < 16) {
+        // ------------------------------------------------ row re-pitch + im2col builders
+        // Two groups of 8 warps work on alternate tiles (group 0: tiles 0, 2, 4, ... of this CTA; group 1: 1, 3, ...)
+        // so that one group's re-pitch / barrier latency overlaps the other's build.  Ring positions follow
+        // from the tile ordinal.
+        const int group = warp >> 3, gb = threadIdx.x & 255, r = gb & 127, half = gb >> 7;
+        int it = 0;
+        for (int ord = group; blockIdx.x + ord * (int)gridDim.x < total_tiles; ord += 2, ++it) {
+            const int t = blockIdx.x + ord * gridDim.x;
+            const int stage = ord % kC1Stages; const uint32_t phase = (ord / kC1Stages) & 1;
+            const int rs = ord % kC1RawStages; const uint32_t rphase = (ord / kC1RawStages) & 1;
+            const TileGeom cur = tile_geom(t, a.shift, a.pad);
+            uint8_t* stg = in_s + (group * 2 + (it & 1)) * kC1InBytes;
+            mbar_wait(rfull + rs, rphase);
+            pad_rows(raw_s + rs * kC1RawBytes, stg, (cur.rlo * kImg) & 15, cur.nrows, a.cin, gb);
+            mbar_arrive(rempty + rs);
+            if (group == 0) asm volatile("bar.sync 1, 256;" ::: "memory");      // padded rows visible to the group
+            else            asm volatile("bar.sync 2, 256;" ::: "memory");
+            // Positions past the image (last tile) build from clamped, valid addresses in the forward (their rows
+            // are never stored); in wgrad their im2col rows are zeroed below (the gradient tile's rows there
+            // belong to the next image).
+            const int p = min(cur.p0 + r, kPW * kPW - 1);
+            const bool live = !WGRAD || cur.p0 + r < kPW * kPW;
             const int oy = p / kPW, ox = p - oy * kPW;
             const int sx = a.shift ? a.shift[2 * cur.n] : a.pad, sy = a.shift ? a.shift[2 * cur.n + 1] : a.pad;
-            int off9[9];
+            int rowoff[3];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int sr = clampi(2 * oy + ky + sy - a.pad, 0, kImg - 1) - cur.rlo;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-                    off9[ky * 3 + kx] = valid ? sr * kImg + clampi(2 * ox + kx + sx - a.pad, 0, kImg - 1) : 0;
-            }
+            for (int ky = 0; ky < 3; ++ky)
+                rowoff[ky] = (clampi(2 * oy + ky + sy - a.pad, 0, kImg - 1) - cur.rlo) * kC1RowBytes;
+            // aug column j = src[clamp(j + sx - pad)] = padded[j + sx + (4 - pad)]; the three kx taps start at j = 2*ox
+            const int gofs = 2 * ox + sx + (4 - a.pad);
             mbar_wait(empty + stage, phase ^ 1);
             uint8_t* tile = st_s + stage * STAGE;
-            if (half == 0) build_half<0>(tile, stg, lut_s, a.cin, r, valid, off9);
-            else           build_half<48>(tile, stg, lut_s, a.cin, r, valid, off9);
+            if (!live) {
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    *reinterpret_cast<uint4*>(tile + (half * 6 + u) * (kC1Tile * 16) + r * 16) = make_uint4(0, 0, 0, 0);
+            } else if (half == 0) {
+                build_part<0, CIN>(tile, stg, a.cin, r, rowoff, gofs);
+                build_part<3, CIN>(tile, stg, a.cin, r, rowoff, gofs);
+            } else {
+                build_part<6, CIN>(tile, stg, a.cin, r, rowoff, gofs);
+                build_part<9, CIN>(tile, stg, a.cin, r, rowoff, gofs);
+            }
             fence_proxy_async();
             mbar_arrive(full + stage);
-            if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
-            buf ^= 1;
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // ------------------------------------------------ UMMA issuer (+ d-tile producer in wgrad)
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        const uint32_t w_addr = smem_u32(w_s);
         bool first = true;
         if (WGRAD && elect_one()) {
             // prefetch the d tiles of the first kC1Stages tiles
@@ -211,33 +275,33 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
             }
         }
         __syncwarp();
+        // descriptors: per-stage base + compile-time (address >> 4) offsets
+        const uint64_t da0 = WGRAD ? make_smem_desc(smem_u32(st_s) + kC1ABytes, 128, kC1Tile * 16)     // d^T, MN-major
+                                   : make_smem_desc(smem_u32(st_s), kC1Tile * 16, 128);               // im2col, K-major
+        const uint64_t db0 = WGRAD ? make_smem_desc(smem_u32(st_s), 128, kC1Tile * 16)                 // im2col, MN-major
+                                   : make_smem_desc(smem_u32(w_s), 512, 128);                         // weights, K-major
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             if (!WGRAD) mbar_wait(tempty + acc, acc_phase ^ 1);
             mbar_wait(full + stage, phase);
             if (WGRAD) mbar_wait(dfull + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a_addr = smem_u32(st_s + stage * STAGE);
+                const uint64_t so = (uint64_t)(stage * (STAGE >> 4));
                 if (!WGRAD) {
                     constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false);
 #pragma unroll
-                    for (int ks = 0; ks < kC1K / 16; ++ks) {
-                        const uint64_t da = make_smem_desc(a_addr + ks * 2 * kC1Tile * 16, kC1Tile * 16, 128);
-                        const uint64_t db = make_smem_desc(w_addr + ks * 2 * 512, 512, 128);
-                        umma_bf16(tmem_base + acc * 32, da, db, idesc, ks ? 1u : 0u);
-                    }
+                    for (int ks = 0; ks < kC1K / 16; ++ks)
+                        umma_bf16(tmem_base + acc * 32, da0 + so + (uint64_t)(ks * 2 * kC1Tile), db0 + (uint64_t)(ks * 2 * 32), idesc,
+                                  ks ? 1u : 0u);
                     umma_commit(empty + stage);
                     umma_commit(tfull + acc);
                 } else {
-                    // D[co (64)][k (96)] += d^T[co][pos] * im2col[pos][k]; both operands MN-major, K = 16 positions
+                    // S[co (64)][k (96)] += d^T[co][pos] * im2col[pos][k]; both operands MN-major, K = 16 positions
                     constexpr uint32_t idesc = make_idesc_bf16(64, kC1K, true, true);
-                    const uint32_t d_addr = a_addr + kC1ABytes;
 #pragma unroll
-                    for (int ks = 0; ks < kC1Tile / 16; ++ks) {
-                        const uint64_t da = make_smem_desc(d_addr + ks * 256, 128, kC1Tile * 16);
-                        const uint64_t db = make_smem_desc(a_addr + ks * 256, 128, kC1Tile * 16);
-                        umma_bf16(tmem_base, da, db, idesc, (first && ks == 0) ? 0u : 1u);
-                    }
+                    for (int ks = 0; ks < kC1Tile / 16; ++ks)
+                        umma_bf16(tmem_base, da0 + so + (uint64_t)(ks * 16), db0 + so + (uint64_t)(ks * 16), idesc,
+                                  (first && ks == 0) ? 0u : 1u);
                     umma_commit(empty + stage);
                 }
             }
@@ -263,8 +327,23 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
             if (elect_one()) umma_commit(done);
             __syncwarp();
         }
+    } else if (warp == 21) {
+        // ------------------------------------------------ row producer: lane c copies channel c's rows of the tile
+        if (lane < a.cin) {
+            int rs = 0; uint32_t rphase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileGeom g = tile_geom(t, a.shift, a.pad);
+                const uint8_t* src = a.obs + ((long long)g.n * a.cin + lane) * (kImg * kImg) + g.rlo * kImg;
+                const int off0 = (g.rlo * kImg) & 15;            // every channel plane starts 16-byte aligned
+                const uint32_t nbytes = (uint32_t)((off0 + g.nrows * kImg + 15) & ~15);
+                mbar_wait(rempty + rs, rphase ^ 1);
+                mbar_arrive_expect_tx(rfull + rs, nbytes);
+                bulk_g2s(raw_s + rs * kC1RawBytes + lane * kC1RawSlot, src - off0, nbytes, rfull + rs);
+                if (++rs == kC1RawStages) { rs = 0; rphase ^= 1; }
+            }
+        }
     } else {
-        // ------------------------------------------------ epilogue warps 9..12 -> lane quarters 1,2,3,0
+        // ------------------------------------------------ epilogue warps 17..20 -> lane quarters 1,2,3,0
         const int q = warp & 3;
         if (!WGRAD) {
             int acc = 0; uint32_t acc_phase = 0;
@@ -284,8 +363,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
                 uint32_t packed[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    packed[i] = pack_bf16x2(fmaxf(v[2 * i] + __ldg(a.bias + 2 * i), 0.f),
-                                            fmaxf(v[2 * i + 1] + __ldg(a.bias + 2 * i + 1), 0.f));
+                    packed[i] = pack_bf16x2(fmaxf(fmaf(v[2 * i], kC1Scale, bias_s[2 * i]), 0.f),
+                                            fmaxf(fmaf(v[2 * i + 1], kC1Scale, bias_s[2 * i + 1]), 0.f));
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<uint4*>(a.out + (c * a.cs_out + row) * 8) =
@@ -311,34 +390,53 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 128);
+    if (warp == 16) tmem_dealloc(tmem_base, 128);
 }
 
-// fp32 conv1 weight [32][cin][3][3] -> bf16 [12 K units][32 co][8] (zero padded to K = 96)
-__global__ void pack_conv1_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kC1Units * 32 * 8) return;
-    const int u = i / 256, co = (i / 8) % 32, e = i % 8;
-    const int k = u * 8 + e;
-    out[i] = __float2bfloat16_rn(k < cin * 9 ? w[co * cin * 9 + k] : 0.f);
+// fp32 conv1 weight [32][cin][3][3] + bias -> bf16 [12 K units][32 co][8] (zero padded to K = 96) followed by
+// the fused forward bias b'[co] = b[co] + (128/255 - 0.5) * sum_k bf16(W[co][k])   (one block of 32 x 8 threads)
+__global__ void __launch_bounds__(256)
+pack_conv1_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int cin) {
+    __shared__ float part[32][9];
+    const int co = threadIdx.x >> 3, e = threadIdx.x & 7;
+    float s = 0.f;
+    for (int u = 0; u < kC1Units; ++u) {
+        const int k = u * 8 + e;
+        const __nv_bfloat16 h = __float2bfloat16_rn(k < cin * 9 ? w[co * cin * 9 + k] : 0.f);
+        out[(u * 32 + co) * 8 + e] = h;
+        s += __bfloat162float(h);
+    }
+    part[co][e] = s;
+    __syncthreads();
+    if (e == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += part[co][j];
+        reinterpret_cast<float*>(out + kC1Units * 32 * 8)[co] = bias[co] + kC1Shift * t;
+    }
 }
 
-// dw[co][k] (k < cin*9) and db[co] (column cin*9) from per-CTA partials [32][96]
+// dw[co][k] = S[co][k]/255 + (128/255 - 0.5) db[co] (k < cin*9), db[co] = S[co][cin*9], S = sum of the per-CTA
+// partials [32][96] in fixed order
 __global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin,
                                           float* __restrict__ dw, float* __restrict__ db) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * kC1K) return;
     const int co = i / kC1K, k = i - co * kC1K;
     if (k > cin * 9) return;
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += partial[(long long)g * (32 * kC1K) + i];
-    if (k < cin * 9) dw[co * cin * 9 + k] = s; else db[co] = s;
+    float s = 0.f, sb = 0.f;
+    for (int g = 0; g < G; ++g) {
+        s += partial[(long long)g * (32 * kC1K) + i];
+        sb += partial[(long long)g * (32 * kC1K) + co * kC1K + cin * 9];
+    }
+    if (k < cin * 9) dw[co * cin * 9 + k] = fmaf(s, kC1Scale, kC1Shift * sb); else db[co] = s;
 }
 
-constexpr size_t kConv1FwdSmem = kC1WBytes + 2 * kC1InBytes + 512 + kC1Stages * kC1ABytes + (3 * kC1Stages + 2 * kC1Acc + 1) * 8 + 16;
+constexpr size_t kConv1FwdSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * kC1ABytes +
+                                 (3 * kC1Stages + 2 * kC1Acc + 1 + 2 * kC1RawStages) * 8 + 16;
 // wgrad: + one extra d-tile worth of tail padding (rows 32..63 of the M=64 operand read 4 blocks past the tile)
-constexpr size_t kConv1WgSmem = kC1WBytes + 2 * kC1InBytes + 512 + kC1Stages * (kC1ABytes + kC1DBytes) + kC1DBytes +
-                                (3 * kC1Stages + 2 * kC1Acc + 1) * 8 + 16;
+constexpr size_t kConv1WgSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * (kC1ABytes + kC1DBytes) +
+                                kC1DBytes + (3 * kC1Stages + 2 * kC1Acc + 1 + 2 * kC1RawStages) * 8 + 16;
 
 }  // namespace drq
 
@@ -346,27 +444,33 @@ using namespace drq;
 
 extern "C" {
 
-int drq_pack_conv1_w_bf16(const float* w, uint16_t* out, int cin, void* stream) {
-    DRQ_REQUIRE(w && out && cin > 0 && cin * 9 + 1 <= kC1K, "pack_conv1_w: bad args (cin <= 10)");
-    pack_conv1_w_kernel<<<(kC1Units * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
-        w, reinterpret_cast<__nv_bfloat16*>(out), cin);
+int drq_debug_conv1_stamps(int64_t* buf) { g_c1_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
+
+int64_t drq_conv1_w_packed_elems(void) { return kC1Units * 32 * 8 + 64; }
+
+int drq_pack_conv1_w_bf16(const float* w, const float* bias, uint16_t* out, int cin, void* stream) {
+    DRQ_REQUIRE(w && bias && out && cin > 0 && cin * 9 + 1 <= kC1K, "pack_conv1_w: bad args (cin <= 10)");
+    pack_conv1_w_kernel<<<1, 256, 0, as_stream(stream)>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(out), cin);
     return check_launch("pack_conv1_w_kernel");
 }
 
-int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, const float* bias,
-                       uint16_t* out, int N, int cin, int pad, void* stream) {
-    DRQ_REQUIRE(obs && w_packed && bias && out, "conv1_fwd_bf16: null pointer");
-    DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0, "conv1_fwd_bf16: bad dims (cin <= 10)");
-    if (int rc = ensure_smem((const void*)conv1_tc_kernel<false>, kConv1FwdSmem, "conv1_fwd_bf16")) return rc;
+int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, uint16_t* out, int N,
+                       int cin, int pad, void* stream) {
+    DRQ_REQUIRE(obs && w_packed && out, "conv1_fwd_bf16: null pointer");
+    DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0 && pad <= 4, "conv1_fwd_bf16: bad dims (cin <= 10, pad <= 4)");
+    if (int rc = ensure_smem((const void*)conv1_tc_kernel<false, 9>, kConv1FwdSmem, "conv1_fwd_bf16")) return rc;
+    if (int rc = ensure_smem((const void*)conv1_tc_kernel<false, 0>, kConv1FwdSmem, "conv1_fwd_bf16")) return rc;
     Conv1TcArgs a{};
     a.obs = obs; a.shift = shift; a.cin = cin; a.pad = pad;
     a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed);
-    a.bias = bias;
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
     a.cs_out = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
     a.n_images = N;
+    a.stamps = g_c1_stamps;
     const int tiles = N * 14;
-    conv1_tc_kernel<false><<<tiles < 148 ? tiles : 148, kC1Threads, kConv1FwdSmem, as_stream(stream)>>>(a);
+    const int G = tiles < 148 ? tiles : 148;
+    if (cin == 9) conv1_tc_kernel<false, 9><<<G, kC1Threads, kConv1FwdSmem, as_stream(stream)>>>(a);
+    else conv1_tc_kernel<false, 0><<<G, kC1Threads, kConv1FwdSmem, as_stream(stream)>>>(a);
     return check_launch("conv1_tc_kernel<fwd>");
 }
 
@@ -375,8 +479,9 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void) { return 148ll * 32 * kC1K; }
 int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
                          float* dw, float* db, int N, int cin, int pad, void* stream) {
     DRQ_REQUIRE(obs && dpre && partial && dw && db, "conv1_wgrad_bf16: null pointer");
-    DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0, "conv1_wgrad_bf16: bad dims (cin <= 10)");
-    if (int rc = ensure_smem((const void*)conv1_tc_kernel<true>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
+    DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0 && pad <= 4, "conv1_wgrad_bf16: bad dims (cin <= 10, pad <= 4)");
+    if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 9>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
+    if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 0>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
     Conv1TcArgs a{};
     a.obs = obs; a.shift = shift; a.cin = cin; a.pad = pad;
     a.d = reinterpret_cast<const __nv_bfloat16*>(dpre);
@@ -385,7 +490,8 @@ int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_
     a.n_images = N;
     const int tiles = N * 14;
     const int G = tiles < 148 ? tiles : 148;
-    conv1_tc_kernel<true><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
+    if (cin == 9) conv1_tc_kernel<true, 9><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
+    else conv1_tc_kernel<true, 0><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
     if (int rc = check_launch("conv1_tc_kernel<wgrad>")) return rc;
     conv1_wgrad_reduce_kernel<<<(32 * kC1K + 127) / 128, 128, 0, as_stream(stream)>>>(partial, G, cin, dw, db);
     return check_launch("conv1_wgrad_reduce_kernel");

@@ -44,7 +44,13 @@ struct ConvTcArgs {
 };
 
 static long long* g_conv_stamps = nullptr;
+#ifdef DRQ_STAMPS
 #define CV_T() (a.stamps ? clock64() : 0ll)
+#define CV_STAMPS(x) x
+#else
+#define CV_T() 0ll
+#define CV_STAMPS(x)
+#endif
 
 template <bool DGRAD>
 __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a) {
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
                     bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
                 if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             }
-            if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[0] = w_empty; a.stamps[1] = CV_T() - t_begin; }
+            CV_STAMPS(if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[0] = w_empty; a.stamps[1] = CV_T() - t_begin; })
         }
     } else if (warp == 1) {
         // ------------------------------------------------ UMMA issuer.  One thread issues 18 UMMAs per tile; the
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
             if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
-        if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[2] = w_tempty; a.stamps[3] = w_full; a.stamps[4] = CV_T() - t_begin; }
+        CV_STAMPS(if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[2] = w_tempty; a.stamps[3] = w_full; a.stamps[4] = CV_T() - t_begin; })
     } else {
         // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int q = warp & 3;
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
             }
             const long long e0 = CV_T();
             mbar_wait(tfull + acc, acc_phase);
-            if (a.stamps && blockIdx.x == 0 && threadIdx.x == 64) a.stamps[5] += CV_T() - e0;
+            CV_STAMPS(if (a.stamps && blockIdx.x == 0 && threadIdx.x == 64) a.stamps[5] += CV_T() - e0;)
             tc_fence_after();
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, v);

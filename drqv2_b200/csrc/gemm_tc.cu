@@ -45,7 +45,11 @@ struct GemmTcArgs {
 };
 
 static long long* g_stamps = nullptr;
+#ifdef DRQ_STAMPS
 #define GT_STAMP(i) do { if (g.stamps && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) g.stamps[i] = clock64(); } while (0)
+#else
+#define GT_STAMP(i) do { } while (0)
+#endif
 
 template <int MODE, int BN>
 struct GemmCfg {

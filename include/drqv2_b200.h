@@ -193,12 +193,15 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
                            float* db, int N, int hout, void* stream);
 int64_t drq_conv_wgrad_bf16_ws_floats(void);
 
-/* conv1 (drqv2.py:55, stride 2) on tensor cores with RandomShiftsAug + obs/255-0.5 fused into an
- * in-shared-memory im2col loader; output WB bf16 of N images.  w_packed from drq_pack_conv1_w_bf16.
- * cin*9+1 <= 96. */
-int drq_pack_conv1_w_bf16(const float* w, uint16_t* out, int cin, void* stream);
-int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, const float* bias,
-                       uint16_t* out, int N, int cin, int pad, void* stream);
+/* conv1 (drqv2.py:55, stride 2) with RandomShiftsAug + obs/255-0.5 fused into the loader, tensor
+ * cores.  The im2col entries are the exact integers x-128 in bf16 (built from the uint8 pixels by byte
+ * permutes); the affine map x/255-0.5 is applied in the epilogue: out = relu(acc/255 + b'),
+ * b' = b + (128/255-0.5) sum_k bf16(W[co][k]).  w_packed: drq_conv1_w_packed_elems() uint16 elements =
+ * bf16 weights [12 K units][32][8] (K = cin*9 padded to 96) followed by float b'[32].  cin*9+1 <= 96. */
+int64_t drq_conv1_w_packed_elems(void);
+int drq_pack_conv1_w_bf16(const float* w, const float* bias, uint16_t* out, int cin, void* stream);
+int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, uint16_t* out, int N,
+                       int cin, int pad, void* stream);
 /* conv1 weight + bias gradient (fp32, reference layout) from dpre (WB bf16 of N images). */
 int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
                          float* dw, float* db, int N, int cin, int pad, void* stream);
@@ -246,6 +249,9 @@ int drq_debug_gemm_stamps(int64_t* buf);
 /* the same for drq_conv3x3_{fwd,dgrad}_bf16: [0] producer wait-for-empty, [1] producer total, [2] issuer
  * wait-for-accumulator, [3] issuer wait-for-data, [4] issuer total, [5] epilogue wait-for-accumulator (cycles). */
 int drq_debug_conv_stamps(int64_t* buf);
+/* drq_conv1_fwd_bf16 builders (threads 0 / 128 of block 0 at [0..4] / [8..12]): wait-for-rows, re-pitch,
+ * barrier, wait-for-free-tile, build (cycles). */
+int drq_debug_conv1_stamps(int64_t* buf);
 
 /* fp32 nn.Linear weight [rows][cols] -> TB(DRQ_TB_W) bf16 [ceil(rows/64)][ceil16(cols)/8][64][8]. */
 int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* stream);

@@ -261,44 +261,45 @@ def test_trunk_weight_pack_and_epilogues(dev):
     assert (got - want_d).abs().max().item() <= 2 ** -8 * want_d.abs().max().item()
 
 
-@pytest.mark.parametrize("N", [3, 40])
-def test_conv1_bf16_fwd_and_wgrad(dev, N):
-    """conv1 with fused integer-shift augmentation + normalisation, tensor-core path."""
+@pytest.mark.parametrize("N,cin", [(3, 9), (40, 9), (5, 3)])
+def test_conv1_bf16_fwd_and_wgrad(dev, N, cin):
+    """conv1 with fused integer-shift augmentation + normalisation, tensor-core path.  The kernel feeds
+    the exact pixels (x - 128 in bf16) and bf16 weights, so the reference is fp64 math on exact inputs,
+    bf16-rounded weights and (wgrad) the bf16-rounded gradient."""
     from drqv2_b200 import _lib
     from oracle import drq_oracle as O
     g = torch.Generator().manual_seed(N)
-    obs = torch.randint(0, 256, (N, 9, 84, 84), dtype=torch.uint8, generator=g)
+    obs = torch.randint(0, 256, (N, cin, 84, 84), dtype=torch.uint8, generator=g)
     shift = torch.randint(0, 9, (N, 2), dtype=torch.int32, generator=g)
-    w = ((torch.rand(32, 9, 3, 3, generator=g) - 0.5) * 0.3).to(dev)
+    w = ((torch.rand(32, cin, 3, 3, generator=g) - 0.5) * 0.3).to(dev)
     b = ((torch.rand(32, generator=g) - 0.5) * 0.1).to(dev)
-    wp = torch.zeros(12 * 32 * 8, dtype=torch.bfloat16, device=dev)
-    _lib.call("drq_pack_conv1_w_bf16", w.data_ptr(), wp.data_ptr(), 9, _stream())
+    wp = torch.zeros(_lib.lib().drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)
+    _lib.call("drq_pack_conv1_w_bf16", w.data_ptr(), b.data_ptr(), wp.data_ptr(), cin, _stream())
     out = torch.zeros(_lib.lib().drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
     obs_d, shift_d = obs.to(dev), shift.to(dev)
-    _lib.call("drq_conv1_fwd_bf16", obs_d.data_ptr(), shift_d.data_ptr(), wp.data_ptr(), b.data_ptr(), out.data_ptr(),
-              N, 9, 4, _stream())
+    _lib.call("drq_conv1_fwd_bf16", obs_d.data_ptr(), shift_d.data_ptr(), wp.data_ptr(), out.data_ptr(), N, cin, 4, _stream())
     torch.cuda.synchronize()
-    x = O.random_shift_exact(obs.float(), shift) / 255.0 - 0.5
-    xb = _bf(x).double().to(dev)
-    want = torch.relu(torch.nn.functional.conv2d(xb, _bf(w).double(), b.double(), stride=2))
+    w16 = _bf(w).double()
+    x = (O.random_shift_exact(obs.float(), shift).double() / 255.0 - 0.5).to(dev)
+    want = torch.relu(torch.nn.functional.conv2d(x, w16, b.double(), stride=2))
     got = nchw_from_wb(out.view(4, -1, 8), N, 41, 41).double()
     assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6
     # no augmentation (act path): shift = NULL == identity
-    _lib.call("drq_conv1_fwd_bf16", obs_d.data_ptr(), None, wp.data_ptr(), b.data_ptr(), out.data_ptr(), N, 9, 4, _stream())
+    _lib.call("drq_conv1_fwd_bf16", obs_d.data_ptr(), None, wp.data_ptr(), out.data_ptr(), N, cin, 4, _stream())
     torch.cuda.synchronize()
-    x0 = _bf(obs.float() / 255.0 - 0.5).double().to(dev)
-    want0 = torch.relu(torch.nn.functional.conv2d(x0, _bf(w).double(), b.double(), stride=2))
+    x0 = (obs.double() / 255.0 - 0.5).to(dev)
+    want0 = torch.relu(torch.nn.functional.conv2d(x0, w16, b.double(), stride=2))
     assert (nchw_from_wb(out.view(4, -1, 8), N, 41, 41).double() - want0).abs().max().item() <= 2 ** -8 * want0.abs().max().item() + 1e-6
     # weight / bias gradient
     d = ((torch.rand(N, 32, 41, 41, generator=g) - 0.5) * 1e-2).to(dev)
     d_wb = wb_from_nchw(d)
     ws = torch.zeros(_lib.lib().drq_conv1_wgrad_bf16_ws_floats(), device=dev)
-    dw, db = torch.zeros(32, 9, 3, 3, device=dev), torch.zeros(32, device=dev)
+    dw, db = torch.zeros(32, cin, 3, 3, device=dev), torch.zeros(32, device=dev)
     _lib.call("drq_conv1_wgrad_bf16", obs_d.data_ptr(), shift_d.data_ptr(), d_wb.data_ptr(), ws.data_ptr(),
-              dw.data_ptr(), db.data_ptr(), N, 9, 4, _stream())
+              dw.data_ptr(), db.data_ptr(), N, cin, 4, _stream())
     torch.cuda.synchronize()
     dr = _bf(d).double()
-    want_w = torch.nn.grad.conv2d_weight(xb, (32, 9, 3, 3), dr, stride=2)
+    want_w = torch.nn.grad.conv2d_weight(x, (32, cin, 3, 3), dr, stride=2)
     want_b = dr.sum(dim=(0, 2, 3))
     assert (dw.double() - want_w).abs().max().item() <= 1e-5 * want_w.abs().max().item() + 1e-7
     assert (db.double() - want_b).abs().max().item() <= 1e-5 * want_b.abs().max().item() + 1e-7

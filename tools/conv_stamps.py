@@ -27,3 +27,23 @@ def run(tag, fn):
     print(tag, "| %.1f us |" % (e0.elapsed_time(e1) * 100), ", ".join(f"{n}={v[i]}" for i, n in enumerate(names)))
 run("fwd N=512 h39", lambda: _lib.call("drq_conv3x3_fwd_bf16", xw.data_ptr(), wf.data_ptr(), b1.data_ptr(), yw.data_ptr(), 2 * Bt, 39, 0, 0, 0, 0, s))
 run("dgrad N=256 h39", lambda: _lib.call("drq_conv3x3_dgrad_bf16", dd.data_ptr(), wf.data_ptr(), xw.data_ptr(), 2 * Bt, d2.data_ptr(), Bt, 39, s))
+
+# conv1 forward builders
+obs = torch.randint(0, 256, (2 * Bt, 9, 84, 84), dtype=torch.uint8, device=dev)
+shift = torch.randint(0, 9, (2 * Bt, 2), dtype=torch.int32, device=dev)
+w1 = torch.zeros(L.drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)
+a1 = torch.zeros(L.drq_wb_elems(2 * Bt), dtype=torch.bfloat16, device=dev)
+_lib.call("drq_debug_conv_stamps", None)
+_lib.call("drq_debug_conv1_stamps", st.data_ptr())
+f1 = lambda: _lib.call("drq_conv1_fwd_bf16", obs.data_ptr(), shift.data_ptr(), w1.data_ptr(), a1.data_ptr(), 2 * Bt, 9, 4, s)
+for _ in range(3):
+    st.zero_(); f1(); torch.cuda.synchronize()
+v = st.tolist()
+print("conv1 fwd N=512 builder thread 0  : rows-wait %d pad %d bar %d tile-wait %d build %d" % tuple(v[:5]))
+print("conv1 fwd N=512 builder thread 128: rows-wait %d pad %d bar %d tile-wait %d build %d" % tuple(v[8:13]))
+_lib.call("drq_debug_conv1_stamps", None)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+f1(); e0.record()
+for _ in range(10): f1()
+e1.record(); torch.cuda.synchronize()
+print("conv1 fwd %.1f us" % (e0.elapsed_time(e1) * 100))
