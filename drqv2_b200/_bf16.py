@@ -95,6 +95,29 @@ class LnJob(C.Structure):
                 ("h_bf16", C.c_void_p), ("units_bf16", C.c_int64), ("row0_bf16", C.c_int64)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("reserved", C.c_int32),
+                ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
+
+
+PACK_LINEAR, PACK_TRUNK, PACK_CONV, PACK_CONV1 = 0, 1, 2, 3
+
+
+def pack_multi(jobs):
+    arr = (PackJob * len(jobs))(*jobs)
+    call("drq_pack_multi", arr, len(jobs), _stream())
+
+
+class ColsumJob(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("ld", C.c_int64), ("out", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
+                ("tb", C.c_int32), ("reserved", C.c_int32)]
+
+
+def colsum_multi(jobs):
+    arr = (ColsumJob * len(jobs))(*jobs)
+    call("drq_colsum_multi", arr, len(jobs), _stream())
+
+
 def ln_tanh_multi(jobs, B, Fd):
     arr = (LnJob * len(jobs))(*jobs)
     call("drq_ln_tanh_fwd_multi", arr, len(jobs), B, Fd, 1e-5, _stream())
@@ -132,43 +155,48 @@ class Bf16State:
     def trunk_ptr(self, slot):
         return self.trunk.ptr(row=slot * self.FP)
 
-    def repack_encoder(self):
-        ag, s = self.agent, _stream()
-        call("drq_pack_conv1_w_bf16", ag._p("encoder", "convnet.0.weight"), ag._p("encoder", "convnet.0.bias"),
-             self.conv1_w.data_ptr(), ag.obs_shape[0], s)
+    # ---- bf16 operand refresh: one launch per optimiser phase
+    def _encoder_jobs(self):
+        ag = self.agent
+        jobs = [PackJob(PACK_CONV1, 0, ag.obs_shape[0], 0, ag._p("encoder", "convnet.0.weight"),
+                        ag._p("encoder", "convnet.0.bias"), self.conv1_w.data_ptr(), None)]
         for i, k in enumerate((2, 4, 6)):
-            call("drq_pack_conv_w_bf16", ag._p("encoder", f"convnet.{k}.weight"), self.conv_wf[i].data_ptr(),
-                 self.conv_wd[i].data_ptr(), s)
+            jobs.append(PackJob(PACK_CONV, 0, 0, 0, ag._p("encoder", f"convnet.{k}.weight"), None,
+                                self.conv_wf[i].data_ptr(), self.conv_wd[i].data_ptr()))
+        return jobs
 
-    def _repack_critic_like(self, src_ptr, slot, z0):
-        ag, s = self.agent, _stream()
+    def _critic_like_jobs(self, src_ptr, slot, z0):
+        ag = self.agent
         A, Fd, H = ag.action_dim, ag.feature_dim, ag.hidden_dim
         qs = ag._q_strides()
-        call("drq_pack_trunk_tb", src_ptr + F32 * self.c_off["trunk.0.weight"], self.trunk_ptr(slot), Fd, s)
+        jobs = [PackJob(PACK_TRUNK, Fd, REPR_DIM, 0, src_ptr + F32 * self.c_off["trunk.0.weight"], None, self.trunk_ptr(slot), None)]
         for z in range(2):
-            call("drq_pack_linear_tb", src_ptr + F32 * (self.c_off["Q1.0.weight"] + z * qs), self.q0.ptr(z0 + z), H, Fd + A, s)
-            call("drq_pack_linear_tb", src_ptr + F32 * (self.c_off["Q1.2.weight"] + z * qs), self.q2.ptr(z0 + z), H, H, s)
+            jobs.append(PackJob(PACK_LINEAR, H, Fd + A, 0, src_ptr + F32 * (self.c_off["Q1.0.weight"] + z * qs), None,
+                                self.q0.ptr(z0 + z), None))
+            jobs.append(PackJob(PACK_LINEAR, H, H, 0, src_ptr + F32 * (self.c_off["Q1.2.weight"] + z * qs), None,
+                                self.q2.ptr(z0 + z), None))
+        return jobs
 
-    def repack_critic(self):
-        self._repack_critic_like(self.agent._arena.ptr("params", "critic"), self.CRITIC, 0)
-
-    def repack_target(self):
-        self._repack_critic_like(self.agent._arena.target.data_ptr(), self.TARGET, 2)
-
-    def repack_actor(self):
-        ag, s = self.agent, _stream()
+    def _actor_jobs(self):
+        ag = self.agent
         A, Fd, H = ag.action_dim, ag.feature_dim, ag.hidden_dim
         pa = lambda k: ag._p("actor", k)
-        call("drq_pack_trunk_tb", pa("trunk.0.weight"), self.trunk_ptr(self.ACTOR), Fd, s)
-        call("drq_pack_linear_tb", pa("policy.0.weight"), self.p0.ptr(), H, Fd, s)
-        call("drq_pack_linear_tb", pa("policy.2.weight"), self.p2.ptr(), H, H, s)
-        call("drq_pack_linear_tb", pa("policy.4.weight"), self.p4.ptr(), A, H, s)
+        return [PackJob(PACK_TRUNK, Fd, REPR_DIM, 0, pa("trunk.0.weight"), None, self.trunk_ptr(self.ACTOR), None),
+                PackJob(PACK_LINEAR, H, Fd, 0, pa("policy.0.weight"), None, self.p0.ptr(), None),
+                PackJob(PACK_LINEAR, H, H, 0, pa("policy.2.weight"), None, self.p2.ptr(), None),
+                PackJob(PACK_LINEAR, A, H, 0, pa("policy.4.weight"), None, self.p4.ptr(), None)]
+
+    def repack_critic_encoder(self):
+        """after critic_opt.step() / encoder_opt.step() (drqv2.py:201-202)"""
+        pack_multi(self._critic_like_jobs(self.agent._arena.ptr("params", "critic"), self.CRITIC, 0) + self._encoder_jobs())
+
+    def repack_actor_target(self):
+        """after actor_opt.step() and the soft target update (drqv2.py:221,259-260)"""
+        pack_multi(self._actor_jobs() + self._critic_like_jobs(self.agent._arena.target.data_ptr(), self.TARGET, 2))
 
     def repack_all(self):
-        self.repack_encoder()
-        self.repack_critic()
-        self.repack_actor()
-        self.repack_target()
+        self.repack_critic_encoder()
+        self.repack_actor_target()
 
 
 class Bf16Workspace:
@@ -301,12 +329,10 @@ def critic_pass(agent, ws, bw):
          gc("Q1.4.weight"), gc("Q1.4.bias"), B, H, 2, qs_f, s)
     gemm(dc2.ptr(), U, c1.ptr(), U, GEMM_MNMN, gc("Q1.2.weight"), H, H, H, B, TEPI_F32, batch=2,
          strides=_strides((HS, HS, qs_f, 0, 0)), bn=128)
-    call("drq_colsum_fb", dc2.ptr(), U, gc("Q1.2.bias"), B, H, 2, HS, qs_f, s)
     gemm(dc2.ptr(), U, w2.ptr(), w2.units, GEMM_KMN, dc1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=c1.ptr(), units_mask=U,
          batch=2, strides=_strides((HS, w2.stride, HS, 0, HS)))
     gemm(dc1.ptr(), U, xC.ptr(0), xC.units, GEMM_MNMN, gc("Q1.0.weight"), Fd + A, H, Fd + A, B, TEPI_F32, batch=2,
          strides=_strides((HS, 0, qs_f, 0, 0)))
-    call("drq_colsum_fb", dc1.ptr(), U, gc("Q1.0.bias"), B, H, 2, HS, qs_f, s)
     # d[h] = sum over heads and K chunks of dc1 @ W0[:, :F]: partial planes, summed by the consumer
     PS = B * (Fd + A)
     gemm(dc1.ptr(), U, w0.ptr(), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd, H, TEPI_F32, batch=2,
@@ -317,7 +343,10 @@ def critic_pass(agent, ws, bw):
          bw.dz.ptr(), bw.dz.units, B, Fd, 2 * bw.SX, PS, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, gc("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
-    call("drq_colsum_f32", ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 1, 0, 0, s)
+    # all bias gradients of the critic backward in one launch
+    colsum_multi([ColsumJob(dc2.ptr(0), U, gc("Q1.2.bias"), B, H, 1, 0), ColsumJob(dc2.ptr(1), U, gc("Q2.2.bias"), B, H, 1, 0),
+                  ColsumJob(dc1.ptr(0), U, gc("Q1.0.bias"), B, H, 1, 0), ColsumJob(dc1.ptr(1), U, gc("Q2.0.bias"), B, H, 1, 0),
+                  ColsumJob(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 0, 0)])
     # ---- encoder backward
     d = [t.data_ptr() for t in bw.dpre]
     acts = [t.data_ptr() for t in bw.acts]
@@ -338,8 +367,7 @@ def critic_pass(agent, ws, bw):
     off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
     call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
          a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(), s)
-    st.repack_critic()
-    st.repack_encoder()
+    st.repack_critic_encoder()
 
 
 def actor_pass(agent, ws, bw):
@@ -384,21 +412,20 @@ def actor_pass(agent, ws, bw):
     dmu, hA, p1, p2, dp1, dp2 = bw.dmu, bw.hA, bw.p1, bw.p2, bw.dp1, bw.dp2
     a0, a2, a4 = st.p0, st.p2, st.p4
     gemm(dmu.ptr(), dmu.units, p2.ptr(), U, GEMM_MNMN, ga("policy.4.weight"), H, A, H, B, TEPI_F32, bn=128)
-    call("drq_colsum_f32", ws.dmu_pre.data_ptr(), A, ga("policy.4.bias"), B, A, 1, 0, 0, s)
     gemm(dmu.ptr(), dmu.units, a4.ptr(), a4.units, GEMM_KMN, dp2.ptr(), U, B, H, A, TEPI_MASK_BF16, mask=p2.ptr(),
          units_mask=U)
     gemm(dp2.ptr(), U, p1.ptr(), U, GEMM_MNMN, ga("policy.2.weight"), H, H, H, B, TEPI_F32, bn=128)
-    call("drq_colsum_fb", dp2.ptr(), U, ga("policy.2.bias"), B, H, 1, 0, 0, s)
     gemm(dp2.ptr(), U, a2.ptr(), a2.units, GEMM_KMN, dp1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=p1.ptr(), units_mask=U)
     gemm(dp1.ptr(), U, hA.ptr(), hA.units, GEMM_MNMN, ga("policy.0.weight"), Fd, H, Fd, B, TEPI_F32)
-    call("drq_colsum_fb", dp1.ptr(), U, ga("policy.0.bias"), B, H, 1, 0, 0, s)
     gemm(dp1.ptr(), U, a0.ptr(), a0.units, GEMM_KMN, ws.dhA.data_ptr(), Fd, B, Fd, H, TEPI_F32)
     call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
          pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"), ga("trunk.1.bias"), bw.dz.ptr(), bw.dz.units,
          B, Fd, 1, 0, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, ga("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
-    call("drq_colsum_f32", ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 1, 0, 0, s)
+    colsum_multi([ColsumJob(ws.dmu_pre.data_ptr(), A, ga("policy.4.bias"), B, A, 0, 0),
+                  ColsumJob(dp2.ptr(), U, ga("policy.2.bias"), B, H, 1, 0), ColsumJob(dp1.ptr(), U, ga("policy.0.bias"), B, H, 1, 0),
+                  ColsumJob(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 0, 0)])
     a = agent._arena
     off, n = a.seg["actor"][0], a.seg["actor"][2]
     coff, cn = a.seg["critic"][0], a.seg["critic"][2]
@@ -406,8 +433,7 @@ def actor_pass(agent, ws, bw):
     call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
          a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(),
          a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, tau, float(1 - tau), s)
-    st.repack_actor()
-    st.repack_target()
+    st.repack_actor_target()
 
 
 def act_workspace(agent, n, dev):

@@ -42,6 +42,8 @@ SIGNATURES = {
     "drq_debug_gemm_stamps": [P],
     "drq_debug_conv_stamps": [P],
     "drq_debug_conv1_stamps": [P],
+    "drq_pack_multi": [P, I, P],
+    "drq_colsum_multi": [P, I, P],
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],

@@ -25,7 +25,7 @@
 // Warp roles (704 threads): warps 0..15 re-pitch the rows + build im2col tiles (4 threads per output
 // position), warp 16 issues UMMAs (and bulk-loads the gradient tile in wgrad), warps 17..20 run the
 // epilogue, warp 21 bulk-copies the source rows of the next tiles (4 stages ahead).
-#include "tc_common.cuh"
+#include "pack.cuh"
 
 namespace drq {
 
@@ -393,43 +393,33 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     if (warp == 16) tmem_dealloc(tmem_base, 128);
 }
 
-// fp32 conv1 weight [32][cin][3][3] + bias -> bf16 [12 K units][32 co][8] (zero padded to K = 96) followed by
-// the fused forward bias b'[co] = b[co] + (128/255 - 0.5) * sum_k bf16(W[co][k])   (one block of 32 x 8 threads)
 __global__ void __launch_bounds__(256)
 pack_conv1_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int cin) {
     __shared__ float part[32][9];
-    const int co = threadIdx.x >> 3, e = threadIdx.x & 7;
-    float s = 0.f;
-    for (int u = 0; u < kC1Units; ++u) {
-        const int k = u * 8 + e;
-        const __nv_bfloat16 h = __float2bfloat16_rn(k < cin * 9 ? w[co * cin * 9 + k] : 0.f);
-        out[(u * 32 + co) * 8 + e] = h;
-        s += __bfloat162float(h);
-    }
-    part[co][e] = s;
-    __syncthreads();
-    if (e == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t += part[co][j];
-        reinterpret_cast<float*>(out + kC1Units * 32 * 8)[co] = bias[co] + kC1Shift * t;
-    }
+    pack_conv1_w_block(w, bias, out, cin, threadIdx.x, part);
 }
 
 // dw[co][k] = S[co][k]/255 + (128/255 - 0.5) db[co] (k < cin*9), db[co] = S[co][cin*9], S = sum of the per-CTA
-// partials [32][96] in fixed order
-__global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin,
-                                          float* __restrict__ dw, float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 32 * kC1K) return;
+// partials [32][96].  Block = 32 outputs x 8 slices of the G partials, combined in fixed order.
+__global__ void __launch_bounds__(256)
+conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float red[8][33], redb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;                 // 96 = 3 x 32: a block stays inside one co
     const int co = i / kC1K, k = i - co * kC1K;
-    if (k > cin * 9) return;
     float s = 0.f, sb = 0.f;
-    for (int g = 0; g < G; ++g) {
+    for (int g = ty; g < G; g += 8) {
         s += partial[(long long)g * (32 * kC1K) + i];
         sb += partial[(long long)g * (32 * kC1K) + co * kC1K + cin * 9];
     }
-    if (k < cin * 9) dw[co * cin * 9 + k] = fmaf(s, kC1Scale, kC1Shift * sb); else db[co] = s;
+    red[ty][tx] = s; redb[ty][tx] = sb;
+    __syncthreads();
+    if (ty == 0 && k <= cin * 9) {
+        float t = red[0][tx], tb = redb[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { t += red[r][tx]; tb += redb[r][tx]; }
+        if (k < cin * 9) dw[co * cin * 9 + k] = fmaf(t, kC1Scale, kC1Shift * tb); else db[co] = t;
+    }
 }
 
 constexpr size_t kConv1FwdSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * kC1ABytes +
@@ -493,7 +483,7 @@ int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_
     if (cin == 9) conv1_tc_kernel<true, 9><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
     else conv1_tc_kernel<true, 0><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
     if (int rc = check_launch("conv1_tc_kernel<wgrad>")) return rc;
-    conv1_wgrad_reduce_kernel<<<(32 * kC1K + 127) / 128, 128, 0, as_stream(stream)>>>(partial, G, cin, dw, db);
+    conv1_wgrad_reduce_kernel<<<32 * kC1K / 32, 256, 0, as_stream(stream)>>>(partial, G, cin, dw, db);
     return check_launch("conv1_wgrad_reduce_kernel");
 }
 

@@ -13,7 +13,7 @@
 //
 // Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = UMMA issuer, warps 2..5 =
 // epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> coalesced 16-byte stores).
-#include "tc_common.cuh"
+#include "pack.cuh"
 
 namespace drq {
 
@@ -239,17 +239,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
     if (warp == 1) tmem_dealloc(tmem_base, kAccStages * 32);
 }
 
-// fp32 master conv weights [co][ci][3][3] -> bf16 UMMA B operands [tap*4 + k/8][n][k%8]:
-//   fwd  : n = co, k = ci   (out = in * W)
-//   dgrad: n = ci, k = co   (din = dout * W^T with flipped offsets)
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_fwd,
                                    __nv_bfloat16* __restrict__ w_dgrad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 32 * 32 * 9) return;
-    const int co = i / 288, ci = (i / 9) % 32, tap = i % 9;
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-    w_fwd[((tap * 4 + ci / 8) * 32 + co) * 8 + (ci & 7)] = v;
-    w_dgrad[((tap * 4 + co / 8) * 32 + ci) * 8 + (co & 7)] = v;
+    pack_conv_w_elem(w, w_fwd, w_dgrad, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 
@@ -374,20 +366,30 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co]
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G, float* __restrict__ dw,
-                                       float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 9 * 32 * 32 + 32) return;
+// dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co].  Block = 32 outputs x 8
+// slices of the G partials (fixed association), combined in fixed order.
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G, float* __restrict__ dw,
+                                                              float* __restrict__ db) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    const bool live = i < 9 * 32 * 32 + 32;
+    const int src = i < 9216 ? i : 9 * 1024 + (i - 9216);
     float s = 0.f;
-    if (i < 9216) {
-        for (int g = 0; g < G; ++g) s += partial[(long long)g * kWgPartial + i];
-        const int tap = i / 1024, ci = (i / 32) % 32, co = i % 32;
-        dw[(co * 32 + ci) * 9 + tap] = s;
-    } else {
-        const int co = i - 9216;
-        for (int g = 0; g < G; ++g) s += partial[(long long)g * kWgPartial + 9 * 1024 + co];
-        db[co] = s;
+    if (live)
+        for (int g = ty; g < G; g += 8) s += partial[(long long)g * kWgPartial + src];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && live) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += red[r][tx];
+        if (i < 9216) {
+            const int tap = i / 1024, ci = (i / 32) % 32, co = i % 32;
+            dw[(co * 32 + ci) * 9 + tap] = t;
+        } else {
+            db[i - 9216] = t;
+        }
     }
 }
 
@@ -487,7 +489,7 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     const int G = conv_tc_grid(N * a.ntiles);
     conv3x3_wgrad_tc_kernel<<<G, kThreadsTC, kWgradTcSmem, as_stream(stream)>>>(a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
-    wgrad_tc_reduce_kernel<<<(9248 + 127) / 128, 128, 0, as_stream(stream)>>>(partial, G, dw, db);
+    wgrad_tc_reduce_kernel<<<(9248 + 31) / 32, 256, 0, as_stream(stream)>>>(partial, G, dw, db);
     return check_launch("wgrad_tc_reduce_kernel");
 }
 

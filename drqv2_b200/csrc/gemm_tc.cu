@@ -20,7 +20,7 @@
 // (TMEM lane quarters 2,3,0,1).  The code is kept small on purpose (epilogue variant and operand
 // mode are template parameters, loops stay rolled): these kernels run for a few microseconds and
 // every instruction executes from a cold instruction cache.
-#include "tc_common.cuh"
+#include "pack.cuh"
 
 namespace drq {
 
@@ -62,11 +62,6 @@ struct GemmCfg {
     static constexpr int B_COPIES = (MODE == MODE_KK && BN == 128) ? 2 : 1;   // K-major weight tiles are 64-row blocks
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + EPI_BYTES + (2 * STAGES + 1) * 8 + 16;
 };
-
-// element offset of TB element (row, unit) with R rows per block
-__device__ __forceinline__ long long tb_off(long long row, int unit, int units, int R) {
-    return (((row / R) * units + unit) * R + (row % R)) * 8;
-}
 
 template <int MODE, int BN, int EPI>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs g) {
@@ -311,51 +306,15 @@ static int launch_gemm_tc(const GemmTcArgs& g, int batch, cudaStream_t s) {
     return check_launch("gemm_tc_kernel");
 }
 
-// fp32 nn.Linear weight [rows][cols] -> TB(64) bf16 [rows/64][ceil16(cols)/8][64][8] (zero padded)
 __global__ void __launch_bounds__(256)
 pack_linear_tb_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int cols, int units) {
-    const int u = blockIdx.y;
-    const int r = blockIdx.x * 256 + threadIdx.x;
-    const int rpad = (rows + RW - 1) / RW * RW;
-    if (r >= rpad) return;
-    uint32_t pk[4] = {0, 0, 0, 0};
-    if (r < rows) {
-        const float* src = w + (long long)r * cols + u * 8;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = u * 8 + 2 * j;
-            pk[j] = pack_bf16x2(c < cols ? src[2 * j] : 0.f, c + 1 < cols ? src[2 * j + 1] : 0.f);
-        }
-    }
-    *reinterpret_cast<uint4*>(out + tb_off(r, u, units, RW)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    pack_linear_tb_block(w, out, rows, cols, units, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
-// trunk weight fp32 [rows][32*1225] (reference NCHW-flatten columns c*1225+yx) -> TB(64) bf16 with NHWC
-// feature order n' = yx*32 + c: unit yx*4 + c/8.  32x32 shared-memory transpose per tile.
 __global__ void __launch_bounds__(256)
 pack_trunk_tb_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows) {
     __shared__ float tile[32][33];
-    const int r = blockIdx.y, yx0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float* wr = w + (long long)r * DRQ_REPR_DIM;
-    const bool live = r < rows;
-#pragma unroll
-    for (int c = ty; c < 32; c += 8) {
-        const int yx = yx0 + tx;
-        tile[c][tx] = (live && yx < 1225) ? wr[c * 1225 + yx] : 0.f;
-    }
-    __syncthreads();
-    // thread -> (yx = yx0 + i, channel unit cu): 32 x 4 = 128 units per tile
-    if (threadIdx.x < 128) {
-        const int i = threadIdx.x >> 2, cu = threadIdx.x & 3;
-        const int yx = yx0 + i;
-        if (yx < 1225) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(tile[cu * 8 + 2 * j][i], tile[cu * 8 + 2 * j + 1][i]);
-            *reinterpret_cast<uint4*>(out + tb_off(r, yx * 4 + cu, DRQ_REPR_DIM / 8, RW)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-    }
+    pack_trunk_tb_block(w, out, rows, blockIdx.x, blockIdx.y, threadIdx.x, tile);
 }
 
 }  // namespace drq

@@ -1,0 +1,111 @@
+// Multi-job launchers of the small per-tensor kernels of the bf16 update: one launch refreshes all bf16
+// operand copies of a network after its optimiser step (drq_pack_multi) and one launch computes all bias
+// gradients of a backward pass (drq_colsum_multi).  These kernels are microseconds of work each; as
+// separate launches their cost is launch latency and cold instruction fetch.
+#include "pack.cuh"
+
+namespace drq {
+
+struct PackJobs { drq_pack_job j[DRQ_PACK_MAX_JOBS]; int first_block[DRQ_PACK_MAX_JOBS + 1]; int n; };
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackJobs jobs) {
+    __shared__ float sm[32 * 33];
+    int ji = 0;
+    while (ji + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[ji + 1]) ++ji;
+    const drq_pack_job& jb = jobs.j[ji];
+    const int b = blockIdx.x - jobs.first_block[ji];
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(jb.out);
+    if (jb.kind == DRQ_PACK_LINEAR) {
+        const int units = (jb.cols + 15) / 16 * 2;
+        const int rblocks = ((jb.rows + DRQ_TB_W - 1) / DRQ_TB_W * DRQ_TB_W + 255) / 256;
+        pack_linear_tb_block(jb.w, out, jb.rows, jb.cols, units, b % rblocks, b / rblocks, threadIdx.x);
+    } else if (jb.kind == DRQ_PACK_TRUNK) {
+        pack_trunk_tb_block(jb.w, out, jb.rows, b % 39, b / 39, threadIdx.x, reinterpret_cast<float(*)[33]>(sm));
+    } else if (jb.kind == DRQ_PACK_CONV) {
+        pack_conv_w_elem(jb.w, out, reinterpret_cast<__nv_bfloat16*>(jb.out2), b * 256 + threadIdx.x);
+    } else {
+        pack_conv1_w_block(jb.w, jb.bias, out, jb.cols, threadIdx.x, reinterpret_cast<float(*)[9]>(sm));
+    }
+}
+
+struct ColsumJobs { drq_colsum_job j[DRQ_COLSUM_MAX_JOBS]; };
+
+// out[n] = sum_m X[m][n]; block = 32 columns x 8 row lanes, fixed-order tree.  blockIdx.y = job.
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const ColsumJobs jobs) {
+    __shared__ float red[8][33];
+    const drq_colsum_job& jb = jobs.j[blockIdx.y];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    if (blockIdx.x * 32 >= jb.N) return;
+    float s = 0.f;
+    if (n < jb.N) {
+        if (jb.tb) {
+            const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(jb.X);
+            const long long units = jb.ld;
+            for (int m = ty; m < jb.M; m += 8)
+                s += __bfloat162float(X[(((long long)(m >> 7) * units + (n >> 3)) * DRQ_TB_ACT + (m & 127)) * 8 + (n & 7)]);
+        } else {
+            const float* X = reinterpret_cast<const float*>(jb.X);
+            for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n];
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < jb.N) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += red[r][tx];
+        jb.out[n] = t;
+    }
+}
+
+}  // namespace drq
+
+using namespace drq;
+
+extern "C" {
+
+int drq_pack_multi(const drq_pack_job* jobs, int njobs, void* stream) {
+    DRQ_REQUIRE(jobs && njobs >= 1 && njobs <= DRQ_PACK_MAX_JOBS, "pack_multi: 1..%d jobs", DRQ_PACK_MAX_JOBS);
+    PackJobs pj{};
+    pj.n = njobs;
+    int blocks = 0;
+    for (int i = 0; i < njobs; ++i) {
+        const drq_pack_job& jb = jobs[i];
+        DRQ_REQUIRE(jb.w && jb.out && jb.kind >= DRQ_PACK_LINEAR && jb.kind <= DRQ_PACK_CONV1, "pack_multi: bad job %d", i);
+        pj.j[i] = jb;
+        pj.first_block[i] = blocks;
+        const int rpad = (jb.rows + DRQ_TB_W - 1) / DRQ_TB_W * DRQ_TB_W;
+        if (jb.kind == DRQ_PACK_LINEAR) {
+            DRQ_REQUIRE(jb.rows > 0 && jb.cols > 0, "pack_multi: bad linear dims in job %d", i);
+            blocks += ((rpad + 255) / 256) * ((jb.cols + 15) / 16 * 2);
+        } else if (jb.kind == DRQ_PACK_TRUNK) {
+            DRQ_REQUIRE(jb.rows > 0, "pack_multi: bad trunk rows in job %d", i);
+            blocks += 39 * rpad;
+        } else if (jb.kind == DRQ_PACK_CONV) {
+            DRQ_REQUIRE(jb.out2, "pack_multi: conv job %d needs the dgrad operand buffer", i);
+            blocks += 36;
+        } else {
+            DRQ_REQUIRE(jb.bias && jb.cols > 0 && jb.cols * 9 + 1 <= 96, "pack_multi: bad conv1 job %d", i);
+            blocks += 1;
+        }
+    }
+    pj.first_block[njobs] = blocks;
+    pack_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pj);
+    return check_launch("pack_multi_kernel");
+}
+
+int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream) {
+    DRQ_REQUIRE(jobs && njobs >= 1 && njobs <= DRQ_COLSUM_MAX_JOBS, "colsum_multi: 1..%d jobs", DRQ_COLSUM_MAX_JOBS);
+    ColsumJobs cj{};
+    int nmax = 0;
+    for (int i = 0; i < njobs; ++i) {
+        DRQ_REQUIRE(jobs[i].X && jobs[i].out && jobs[i].M > 0 && jobs[i].N > 0, "colsum_multi: bad job %d", i);
+        cj.j[i] = jobs[i];
+        nmax = jobs[i].N > nmax ? jobs[i].N : nmax;
+    }
+    colsum_multi_kernel<<<dim3((nmax + 31) / 32, njobs), 256, 0, as_stream(stream)>>>(cj);
+    return check_launch("colsum_multi_kernel");
+}
+
+}  // extern "C"

@@ -259,6 +259,24 @@ int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* 
  * bf16 feature layout (reference column c*1225+y*35+x, drqv2.py:66). */
 int drq_pack_trunk_tb(const float* w, uint16_t* out, int rows, void* stream);
 
+/* all bf16 operand re-packs of one optimiser phase in one launch.  kind LINEAR: drq_pack_linear_tb(w, out,
+ * rows, cols); TRUNK: drq_pack_trunk_tb(w, out, rows); CONV: drq_pack_conv_w_bf16(w, out, out2);
+ * CONV1: drq_pack_conv1_w_bf16(w, bias, out, cin = cols). */
+#define DRQ_PACK_LINEAR 0
+#define DRQ_PACK_TRUNK 1
+#define DRQ_PACK_CONV 2
+#define DRQ_PACK_CONV1 3
+#define DRQ_PACK_MAX_JOBS 12
+typedef struct { int32_t kind; int32_t rows; int32_t cols; int32_t reserved; const float* w; const float* bias; uint16_t* out; uint16_t* out2; } drq_pack_job;
+int drq_pack_multi(const drq_pack_job* jobs, int njobs, void* stream);
+
+/* all bias gradients (column sums over the batch rows) of one backward pass in one launch: out[n] =
+ * sum_m X[m][n], X fp32 row-major with row stride ld (tb == 0) or a TB bf16 activation with ld units per
+ * row (tb != 0). */
+#define DRQ_COLSUM_MAX_JOBS 8
+typedef struct { const void* X; int64_t ld; float* out; int32_t M; int32_t N; int32_t tb; int32_t reserved; } drq_colsum_job;
+int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream);
+
 /* ------------------------------------------------------------------ dense, fp32 */
 
 /* C[z][m][n] = epi( sum_k A[z](m,k) * B[z](k,n) + bias[z][n] ), general strides.
