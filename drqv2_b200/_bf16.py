@@ -133,7 +133,7 @@ class Bf16State:
         A, Fd, H = agent.action_dim, agent.feature_dim, agent.hidden_dim
         self.agent = agent
         self.FP = _ceil(Fd, TB_W)                                   # trunk rows per slot
-        self.trunk = TB(3 * self.FP, REPR_DIM, dev, rblk=TB_W)      # NHWC feature order
+        self.trunk = TB(3 * self.FP, REPR_DIM, dev, rblk=TB_W)      # encoder-output feature order (c/8, yx, c%8)
         self.q0 = TB(H, Fd + A, dev, batch=4, rblk=TB_W)            # [critic Q1, critic Q2, target Q1, target Q2]
         self.q2 = TB(H, H, dev, batch=4, rblk=TB_W)
         self.p0 = TB(H, Fd, dev, rblk=TB_W)
@@ -212,7 +212,7 @@ class Bf16Workspace:
         self.RB = RB = _ceil(B, TB_ACT)
         self.acts = [zb(L.drq_wb_elems(NB)) for _ in range(3)]      # conv1..3 outputs, [obs | next]
         self.cs_act = NB * PLB + WB_SLACK
-        self.feat = TB(2 * RB, REPR_DIM, dev)                        # NHWC feature order
+        self.feat = TB(2 * RB, REPR_DIM, dev)                        # feature order (c/8)*9800 + yx*8 + c%8
         self.dpre = [zb(L.drq_wb_elems(B)) for _ in range(4)]
         self.cs_d = B * PLB + WB_SLACK
         self.wg_ws = zf(max(L.drq_conv_wgrad_bf16_ws_floats(), L.drq_conv1_wgrad_bf16_ws_floats()))
@@ -239,7 +239,7 @@ class Bf16Workspace:
 
 
 def encode(agent, ws, bw):
-    """conv1 (u8 + aug + normalise fused) .. conv4 on tensor cores; features TB bf16 (NHWC order)."""
+    """conv1 (u8 + aug + normalise fused) .. conv4 on tensor cores; features TB bf16 (channel-group-major order)."""
     st, B, s = agent._bf16, ws.B, _stream()
     be = lambda i: agent._p("encoder", f"convnet.{i}.bias")
     acts = [a.data_ptr() for a in bw.acts]

@@ -7,6 +7,7 @@ entry point raises.  Build it with ``make -C drqv2_b200/csrc`` (or
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
@@ -39,6 +40,7 @@ SIGNATURES = {
     "drq_conv1_fwd_bf16": [P, P, P, P, I, I, I, P],
     "drq_conv1_wgrad_bf16": [P, P, P, P, P, P, I, I, I, P],
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
+    "drq_set_pdl": [I],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_conv_stamps": [P],
     "drq_debug_conv1_stamps": [P],
@@ -109,6 +111,8 @@ def lib():
             fn.argtypes, fn.restype = args, res
         if h.drq_abi_version() != 1:
             raise ImportError("libdrqv2_b200.so ABI version mismatch")
+        # programmatic dependent launch between the library's kernels (opt-in with DRQV2_B200_PDL=1: measured neutral without early trigger, -25 % with it)
+        h.drq_set_pdl(0 if os.environ.get("DRQV2_B200_PDL", "0") == "0" else 1)
         _lib = h
     return _lib
 

@@ -19,6 +19,29 @@ int ensure_smem(const void* kernel, size_t bytes, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (drq_set_pdl): every kernel triggers its dependents at entry and waits
+// for its predecessors (griddepcontrol.wait = all prior grids complete and flushed) before it touches
+// global memory, so the next kernel's launch latency, barrier / TMEM set-up and first instruction
+// fetches overlap the tail of the running one.  Without the launch attribute both instructions are no-ops.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef DRQ_NO_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... P, typename... A>
+inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 constexpr int kImg = DRQ_IMG;
 constexpr int kPW = DRQ_PW;
 constexpr int kPlane = DRQ_PLANE;

@@ -190,11 +190,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     constexpr int TILES_PER_IMG = (kPW * kPW + kC1Tile - 1) / kC1Tile;   // 14
     const int total_tiles = a.n_images * TILES_PER_IMG;
 
-    if (!WGRAD) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.w);
-        uint4* dst = reinterpret_cast<uint4*>(w_s);
-        for (int i = threadIdx.x; i < (kC1WBytes + 128) / 16; i += kC1Threads) dst[i] = __ldg(src + i);
-    }
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kC1Stages; ++i) { mbar_init(full + i, kC1Builders / 2); mbar_init(empty + i, 1); mbar_init(dfull + i, 1); }
         for (int i = 0; i < kC1Acc; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
@@ -205,6 +201,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
     if (warp == 16) {
         tmem_alloc(tmem_slot, 128);
         tmem_relinquish();
+    }
+    pdl_wait();                 // CTA-local set-up above overlaps the previous kernel's tail
+    if (!WGRAD) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.w);
+        uint4* dst = reinterpret_cast<uint4*>(w_s);
+        for (int i = threadIdx.x; i < (kC1WBytes + 128) / 16; i += kC1Threads) dst[i] = __ldg(src + i);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -395,6 +397,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
 
 __global__ void __launch_bounds__(256)
 pack_conv1_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int cin) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float part[32][9];
     pack_conv1_w_block(w, bias, out, cin, threadIdx.x, part);
 }
@@ -403,6 +407,8 @@ pack_conv1_w_kernel(const float* __restrict__ w, const float* __restrict__ bias,
 // partials [32][96].  Block = 32 outputs x 8 slices of the G partials, combined in fixed order.
 __global__ void __launch_bounds__(256)
 conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin, float* __restrict__ dw, float* __restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33], redb[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;                 // 96 = 3 x 32: a block stays inside one co
@@ -440,7 +446,7 @@ int64_t drq_conv1_w_packed_elems(void) { return kC1Units * 32 * 8 + 64; }
 
 int drq_pack_conv1_w_bf16(const float* w, const float* bias, uint16_t* out, int cin, void* stream) {
     DRQ_REQUIRE(w && bias && out && cin > 0 && cin * 9 + 1 <= kC1K, "pack_conv1_w: bad args (cin <= 10)");
-    pack_conv1_w_kernel<<<1, 256, 0, as_stream(stream)>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(out), cin);
+    launch_k(pack_conv1_w_kernel, 1, 256, 0, as_stream(stream), w, bias, reinterpret_cast<__nv_bfloat16*>(out), cin);
     return check_launch("pack_conv1_w_kernel");
 }
 
@@ -459,8 +465,8 @@ int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t*
     a.stamps = g_c1_stamps;
     const int tiles = N * 14;
     const int G = tiles < 148 ? tiles : 148;
-    if (cin == 9) conv1_tc_kernel<false, 9><<<G, kC1Threads, kConv1FwdSmem, as_stream(stream)>>>(a);
-    else conv1_tc_kernel<false, 0><<<G, kC1Threads, kConv1FwdSmem, as_stream(stream)>>>(a);
+    if (cin == 9) launch_k(conv1_tc_kernel<false, 9>, G, kC1Threads, kConv1FwdSmem, as_stream(stream), a);
+    else launch_k(conv1_tc_kernel<false, 0>, G, kC1Threads, kConv1FwdSmem, as_stream(stream), a);
     return check_launch("conv1_tc_kernel<fwd>");
 }
 
@@ -480,10 +486,10 @@ int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_
     a.n_images = N;
     const int tiles = N * 14;
     const int G = tiles < 148 ? tiles : 148;
-    if (cin == 9) conv1_tc_kernel<true, 9><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
-    else conv1_tc_kernel<true, 0><<<G, kC1Threads, kConv1WgSmem, as_stream(stream)>>>(a);
+    if (cin == 9) launch_k(conv1_tc_kernel<true, 9>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
+    else launch_k(conv1_tc_kernel<true, 0>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
     if (int rc = check_launch("conv1_tc_kernel<wgrad>")) return rc;
-    conv1_wgrad_reduce_kernel<<<32 * kC1K / 32, 256, 0, as_stream(stream)>>>(partial, G, cin, dw, db);
+    launch_k(conv1_wgrad_reduce_kernel, 32 * kC1K / 32, 256, 0, as_stream(stream), partial, G, cin, dw, db);
     return check_launch("conv1_wgrad_reduce_kernel");
 }
 

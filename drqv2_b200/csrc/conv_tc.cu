@@ -67,14 +67,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = a.n_images * a.ntiles;
-    if (!DGRAD && threadIdx.x < 32) bias_s[threadIdx.x] = a.bias[threadIdx.x];
-
-    // packed weights -> smem (same byte layout)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.w);
-        uint4* dst = reinterpret_cast<uint4*>(w_s);
-        for (int i = threadIdx.x; i < kWBytes / 16; i += kThreadsTC) dst[i] = __ldg(src + i);
-    }
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStagesTC; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
@@ -83,6 +76,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
     if (warp == 1) {
         tmem_alloc(tmem_slot, kAccStages * 32);
         tmem_relinquish();
+    }
+    pdl_wait();                 // CTA-local set-up above overlaps the previous kernel's tail
+    if (!DGRAD && threadIdx.x < 32) bias_s[threadIdx.x] = a.bias[threadIdx.x];
+
+    // packed weights -> smem (same byte layout)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.w);
+        uint4* dst = reinterpret_cast<uint4*>(w_s);
+        for (int i = threadIdx.x; i < kWBytes / 16; i += kThreadsTC) dst[i] = __ldg(src + i);
     }
     fence_proxy_async();      // generic-proxy smem writes (weights) -> visible to the async proxy (UMMA)
     tc_fence_before();
@@ -195,13 +197,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
                     packed[i] = pack_bf16x2(lo, hi);
                 }
                 if (a.nhwc_out == 2) {
-                    // TB feature matrix: unit (y*w + x)*4 + c/8, row = image (128-row blocks of feat_rpad units)
+                    // TB feature matrix, channel-group-major feature order: unit (c/8)*w*w + y*w + x, row = image
+                    // (128-row blocks of feat_rpad units)
                     if (x < a.w_valid) {
-                        const long long u0 = ((long long)y * a.w_valid + x) * 4;
+                        const long long hw = (long long)a.w_valid * a.w_valid;
+                        const long long u0 = (long long)y * a.w_valid + x;
                         const int fr = n < a.feat_half ? n : n - a.feat_half + a.feat_half_row;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(a.out + ((((long long)(fr >> 7)) * a.feat_rpad + u0 + c) * DRQ_TB_ACT + (fr & 127)) * 8) =
+                            *reinterpret_cast<uint4*>(a.out + ((((long long)(fr >> 7)) * a.feat_rpad + c * hw + u0) * DRQ_TB_ACT + (fr & 127)) * 8) =
                                 make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
                     }
                     continue;
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a)
 
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_fwd,
                                    __nv_bfloat16* __restrict__ w_dgrad) {
+    pdl_trigger();
+    pdl_wait();
     pack_conv_w_elem(w, w_fwd, w_dgrad, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -279,6 +285,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = a.n_images * a.ntiles;
+    pdl_trigger();
     for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kThreadsTC)
         reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;    // bf16 1.0 x2
     if (threadIdx.x == 0) {
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -370,6 +378,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
 // slices of the G partials (fixed association), combined in fixed order.
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G, float* __restrict__ dw,
                                                               float* __restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
@@ -416,7 +426,7 @@ int64_t drq_wb_elems(int n_images) { return 4ll * ((long long)n_images * kPLB + 
 
 int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream) {
     DRQ_REQUIRE(w && w_fwd && w_dgrad, "pack_conv_w: null pointer");
-    pack_conv_w_kernel<<<(9216 + 255) / 256, 256, 0, as_stream(stream)>>>(
+    launch_k(pack_conv_w_kernel, (9216 + 255) / 256, 256, 0, as_stream(stream), 
         w, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad));
     return check_launch("pack_conv_w_kernel");
 }
@@ -443,7 +453,7 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
-    conv3x3_tc_kernel<false><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
+    launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<fwd>");
 }
 
@@ -467,7 +477,7 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.w_valid = hin;
     a.nhwc_out = 0;
     a.stamps = g_conv_stamps;
-    conv3x3_tc_kernel<true><<<conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream)>>>(a);
+    launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
 }
 
@@ -487,9 +497,9 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     a.n_images = N;
     a.ntiles = (hout * kPW + kTM - 1) / kTM;
     const int G = conv_tc_grid(N * a.ntiles);
-    conv3x3_wgrad_tc_kernel<<<G, kThreadsTC, kWgradTcSmem, as_stream(stream)>>>(a);
+    launch_k(conv3x3_wgrad_tc_kernel, G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
-    wgrad_tc_reduce_kernel<<<(9248 + 31) / 32, 256, 0, as_stream(stream)>>>(partial, G, dw, db);
+    launch_k(wgrad_tc_reduce_kernel, (9248 + 31) / 32, 256, 0, as_stream(stream), partial, G, dw, db);
     return check_launch("wgrad_tc_reduce_kernel");
 }
 

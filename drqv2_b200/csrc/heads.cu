@@ -22,6 +22,8 @@ struct LnJobs { drq_ln_job j[DRQ_LN_MAX_JOBS]; };
 template <int NF>   // features per lane: F <= 32 * NF
 __global__ void __launch_bounds__(128)
 ln_tanh_fwd_kernel(const LnJobs jobs, int B, int F, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const drq_ln_job& jb = jobs.j[blockIdx.y];
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -83,6 +85,8 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                        float* __restrict__ dz, float* __restrict__ dy_out, __nv_bfloat16* __restrict__ dz_bf,
                        long long rpad_zb, int B, int F, int n_planes, long long plane_stride) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -121,6 +125,8 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
 __global__ void __launch_bounds__(256)
 ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int F) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sg[256], sb[256];
     const int f = blockIdx.x;
     float g = 0.f, b = 0.f;
@@ -157,6 +163,8 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
                     const float* __restrict__ std_dev, float clip, float* __restrict__ action_out,
                     long long ld_a, float* __restrict__ mu_out, float* __restrict__ metrics,
                     __nv_bfloat16* __restrict__ a_bf, long long rpad_ab, int feat_off, int B, int A) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[256];
     const float std = std_dev ? *std_dev : 0.f;
     const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;  // utils.py:113 (python: -1.0 + 1e-6 -> fp32)
@@ -195,6 +203,8 @@ __global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long 
                                         const float* __restrict__ mu, float* __restrict__ dmu_pre,
                                         __nv_bfloat16* __restrict__ dmu_bf, long long rpad_mb, int B, int A,
                                         int n_planes, long long plane_stride) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * A) return;
     const int b = i / A, j = i - b * A;
@@ -212,6 +222,8 @@ critic_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
                    const float* __restrict__ reward, const float* __restrict__ discount,
                    float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ tq_out,
                    float* __restrict__ metrics, int B) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[256];
     float s_r = 0.f, s_t = 0.f, s_1 = 0.f, s_2 = 0.f, s_l1 = 0.f, s_l2 = 0.f;
     const float scale = 2.0f / (float)B;
@@ -242,6 +254,8 @@ __global__ void __launch_bounds__(256)
 actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
                   float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ metrics,
                   int B) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[256];
     float s = 0.f;
     const float g = -1.0f / (float)B;
@@ -258,6 +272,8 @@ actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
 // ---------------------------------------------------------------- bf16-mode helpers (TB layout; `rpad` = units per row)
 __global__ void scatter_fb_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
                                   long long rpad, int feat_off, int rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int r = i / cols, c = i - r * cols;
@@ -268,6 +284,8 @@ __global__ void scatter_fb_kernel(const float* __restrict__ src, long long ld_sr
 __global__ void __launch_bounds__(256)
 colsum_fb_kernel(const __nv_bfloat16* __restrict__ X, long long rpad, float* __restrict__ out, int M, int N,
                  long long bs_x, long long bs_out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[256][9];
     const int u = blockIdx.x, z = blockIdx.y;
     const __nv_bfloat16* Xz = X + z * bs_x;
@@ -301,6 +319,8 @@ __global__ void __launch_bounds__(256)
 q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, long long rpad, long long bs_c2,
                   const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q, int B, int H,
                   long long w_stride, int heads_inner, long long w_stride_outer) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float w_s[];
     __shared__ float part[8][33];
     const int z = blockIdx.y;
@@ -339,6 +359,8 @@ __global__ void __launch_bounds__(256)
 q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict__ c2, long long rpad,
                   long long bs_c2, const float* __restrict__ w3, __nv_bfloat16* __restrict__ dc2,
                   float* __restrict__ dw3, float* __restrict__ db3, int B, long long w_stride) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[256][9];
     const int u = blockIdx.x, z = blockIdx.y;
     const float* dqz = dq + (long long)z * B;
@@ -401,9 +423,9 @@ int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float
     if (B == 0) return DRQ_OK;
     const dim3 grid((B + 3) / 4, njobs);
     cudaStream_t s = as_stream(stream);
-    if (F <= 64) ln_tanh_fwd_kernel<2><<<grid, 128, 0, s>>>(js, B, F, eps);
-    else if (F <= 128) ln_tanh_fwd_kernel<4><<<grid, 128, 0, s>>>(js, B, F, eps);
-    else ln_tanh_fwd_kernel<8><<<grid, 128, 0, s>>>(js, B, F, eps);
+    if (F <= 64) launch_k(ln_tanh_fwd_kernel<2>, grid, 128, 0, s, js, B, F, eps);
+    else if (F <= 128) launch_k(ln_tanh_fwd_kernel<4>, grid, 128, 0, s, js, B, F, eps);
+    else launch_k(ln_tanh_fwd_kernel<8>, grid, 128, 0, s, js, B, F, eps);
     return check_launch("ln_tanh_fwd_kernel");
 }
 
@@ -425,12 +447,12 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
     DRQ_REQUIRE(B > 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_bwd: bad dims (F<=256)");
     // dy = dh * tanh' is staged in the second half of the caller's 2*B*F buffer
     float* dy = dz + (long long)B * F;
-    ln_tanh_bwd_row_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(dh, ld_dh, h, ld_h, xhat, rstd,
+    launch_k(ln_tanh_bwd_row_kernel, (B + 3) / 4, 128, 0, as_stream(stream), dh, ld_dh, h, ld_h, xhat, rstd,
                                                                       gamma, dz, dy,
                                                                       reinterpret_cast<__nv_bfloat16*>(dz_bf16), rpad_zb, B, F,
                                                                       n_planes, plane_stride);
     if (int rc = check_launch("ln_tanh_bwd_row_kernel")) return rc;
-    ln_param_grad_kernel<<<F, 256, 0, as_stream(stream)>>>(dy, xhat, dgamma, dbeta, B, F);
+    launch_k(ln_param_grad_kernel, F, 256, 0, as_stream(stream), dy, xhat, dgamma, dbeta, B, F);
     return check_launch("ln_param_grad_kernel");
 }
 
@@ -440,7 +462,7 @@ int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev
     DRQ_REQUIRE(mu_pre && action_out, "actor_sample: null pointer");
     DRQ_REQUIRE(!(eps && !std_dev), "actor_sample: eps without std");
     DRQ_REQUIRE(B > 0 && A > 0, "actor_sample: bad dims");
-    actor_sample_kernel<<<1, 256, 0, as_stream(stream)>>>(mu_pre, eps, std_dev, clip, action_out, ld_a,
+    launch_k(actor_sample_kernel, 1, 256, 0, as_stream(stream), mu_pre, eps, std_dev, clip, action_out, ld_a,
                                                           mu_out, metrics,
                                                           reinterpret_cast<__nv_bfloat16*>(action_bf16), rpad_ab, feat_off, B, A);
     return check_launch("actor_sample_kernel");
@@ -450,7 +472,7 @@ int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, f
                          uint16_t* dmu_bf16, int64_t rpad_mb, int B, int A, int n_planes, int64_t plane_stride,
                          void* stream) {
     DRQ_REQUIRE(daction && mu && dmu_pre && B > 0 && A > 0 && n_planes >= 1, "actor_sample_bwd: bad args");
-    actor_sample_bwd_kernel<<<(B * A + 255) / 256, 256, 0, as_stream(stream)>>>(daction, ld_da, mu,
+    launch_k(actor_sample_bwd_kernel, (B * A + 255) / 256, 256, 0, as_stream(stream), daction, ld_da, mu,
                                                                                 dmu_pre,
                                                                                 reinterpret_cast<__nv_bfloat16*>(dmu_bf16), rpad_mb, B, A,
                                                                                 n_planes, plane_stride);
@@ -462,7 +484,7 @@ int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const fl
                     float* target_q_out, float* metrics, int B, void* stream) {
     DRQ_REQUIRE(q1 && q2 && tq1 && tq2 && reward && discount && dq1 && dq2, "critic_loss: null pointer");
     DRQ_REQUIRE(B > 0, "critic_loss: bad dims");
-    critic_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(q1, q2, tq1, tq2, reward, discount, dq1, dq2,
+    launch_k(critic_loss_kernel, 1, 256, 0, as_stream(stream), q1, q2, tq1, tq2, reward, discount, dq1, dq2,
                                                          target_q_out, metrics, B);
     return check_launch("critic_loss_kernel");
 }
@@ -470,7 +492,7 @@ int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const fl
 int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
                    int cols, void* stream) {
     DRQ_REQUIRE(src && dst && rows > 0 && cols > 0 && feat_off >= 0, "scatter_fb: bad args");
-    scatter_fb_kernel<<<(rows * cols + 255) / 256, 256, 0, as_stream(stream)>>>(
+    launch_k(scatter_fb_kernel, (rows * cols + 255) / 256, 256, 0, as_stream(stream), 
         src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), rpad, feat_off, rows, cols);
     return check_launch("scatter_fb_kernel");
 }
@@ -478,7 +500,7 @@ int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad
 int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int batch, int64_t bs_x,
                   int64_t bs_out, void* stream) {
     DRQ_REQUIRE(X && out && M > 0 && N > 0 && batch > 0, "colsum_fb: bad args");
-    colsum_fb_kernel<<<dim3((N + 7) / 8, batch), 256, 0, as_stream(stream)>>>(
+    launch_k(colsum_fb_kernel, dim3((N + 7) / 8, batch), 256, 0, as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16*>(X), rpad, out, M, N, bs_x, bs_out);
     return check_launch("colsum_fb_kernel");
 }
@@ -487,7 +509,7 @@ int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const f
                         float* q, int B, int H, int heads, int64_t w_stride, int heads_inner, int64_t w_stride_outer,
                         void* stream) {
     DRQ_REQUIRE(c2 && w3 && b3 && q && B > 0 && H > 0 && H % 8 == 0 && heads > 0 && heads_inner > 0, "q_head_fwd: bad args");
-    q_head_fwd_kernel<<<dim3((B + 31) / 32, heads), 256, H * sizeof(float), as_stream(stream)>>>(
+    launch_k(q_head_fwd_kernel, dim3((B + 31) / 32, heads), 256, H * sizeof(float), as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, b3, q, B, H, w_stride, heads_inner, w_stride_outer);
     return check_launch("q_head_fwd_kernel");
 }
@@ -496,7 +518,7 @@ int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64
                         uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
                         void* stream) {
     DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_bwd: bad args");
-    q_head_bwd_kernel<<<dim3(H / 8, heads), 256, 0, as_stream(stream)>>>(
+    launch_k(q_head_bwd_kernel, dim3(H / 8, heads), 256, 0, as_stream(stream), 
         dq, reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3,
         db3, B, w_stride);
     return check_launch("q_head_bwd_kernel");
@@ -505,7 +527,7 @@ int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64
 int drq_actor_loss(const float* q1, const float* q2, float* dq1, float* dq2, float* metrics, int B,
                    void* stream) {
     DRQ_REQUIRE(q1 && q2 && dq1 && dq2 && B > 0, "actor_loss: bad args");
-    actor_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(q1, q2, dq1, dq2, metrics, B);
+    launch_k(actor_loss_kernel, 1, 256, 0, as_stream(stream), q1, q2, dq1, dq2, metrics, B);
     return check_launch("actor_loss_kernel");
 }
 

@@ -9,6 +9,8 @@ namespace drq {
 struct PackJobs { drq_pack_job j[DRQ_PACK_MAX_JOBS]; int first_block[DRQ_PACK_MAX_JOBS + 1]; int n; };
 
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJobs jobs) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[32 * 33];
     int ji = 0;
     while (ji + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[ji + 1]) ++ji;
@@ -32,6 +34,8 @@ struct ColsumJobs { drq_colsum_job j[DRQ_COLSUM_MAX_JOBS]; };
 
 // out[n] = sum_m X[m][n]; block = 32 columns x 8 row lanes, fixed-order tree.  blockIdx.y = job.
 __global__ void __launch_bounds__(256) colsum_multi_kernel(const ColsumJobs jobs) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33];
     const drq_colsum_job& jb = jobs.j[blockIdx.y];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -91,7 +95,7 @@ int drq_pack_multi(const drq_pack_job* jobs, int njobs, void* stream) {
         }
     }
     pj.first_block[njobs] = blocks;
-    pack_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pj);
+    launch_k(pack_multi_kernel, blocks, 256, 0, as_stream(stream), pj);
     return check_launch("pack_multi_kernel");
 }
 
@@ -104,7 +108,7 @@ int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream) {
         cj.j[i] = jobs[i];
         nmax = jobs[i].N > nmax ? jobs[i].N : nmax;
     }
-    colsum_multi_kernel<<<dim3((nmax + 31) / 32, njobs), 256, 0, as_stream(stream)>>>(cj);
+    launch_k(colsum_multi_kernel, dim3((nmax + 31) / 32, njobs), 256, 0, as_stream(stream), cj);
     return check_launch("colsum_multi_kernel");
 }
 

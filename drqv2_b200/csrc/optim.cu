@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256)
 adam_ema_kernel(float* p, const float* g, float* m, float* v, long long n_adam, const float* sc,
                 const float* ema_src, float* ema_dst, long long n_ema, float tau, float omt,
                 int adam_blocks) {
+    pdl_trigger();
+    pdl_wait();
     if ((int)blockIdx.x < adam_blocks) {
         adam_range(p, g, m, v, n_adam, sc, blockIdx.x * 256ll + threadIdx.x, adam_blocks * 256ll);
     } else {
@@ -99,7 +101,7 @@ int drq_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n_ad
                 "adam_ema: ema arenas must be 16-byte aligned");
     const int ab = n_adam ? blocks_for(n_adam) : 0;
     const int eb = n_ema ? blocks_for(n_ema) : 0;
-    adam_ema_kernel<<<ab + eb, 256, 0, as_stream(stream)>>>(p, g, m, v, n_adam, scalars, ema_src, ema_dst,
+    launch_k(adam_ema_kernel, ab + eb, 256, 0, as_stream(stream), p, g, m, v, n_adam, scalars, ema_src, ema_dst,
                                                             n_ema, tau, one_minus_tau, ab);
     return check_launch("adam_ema_kernel");
 }

@@ -8,6 +8,7 @@
 namespace drq {
 
 static thread_local char g_err[512] = "";
+int g_pdl = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -54,6 +55,8 @@ ring_gather_kernel(const uint8_t* __restrict__ frames, const float* __restrict__
                    float gamma, uint8_t* __restrict__ obs_out, uint8_t* __restrict__ next_out,
                    float* __restrict__ action_out, float* __restrict__ reward_out,
                    float* __restrict__ discount_out) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const int y = blockIdx.y;
     const long long start = ep_start[b];
@@ -94,6 +97,8 @@ ring_gather_kernel(const uint8_t* __restrict__ frames, const float* __restrict__
 __global__ void ring_sample_kernel(const int* __restrict__ ep_table, const int* __restrict__ n_episodes, int nstep,
                                    unsigned long long seed, const unsigned long long* counter,
                                    int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     uint32_t r[4];
@@ -113,6 +118,8 @@ __global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned 
                                         int pad, int* __restrict__ shift_obs,
                                         int* __restrict__ shift_next, float* __restrict__ eps_c,
                                         float* __restrict__ eps_a, int B, int A) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long c = *counter;
     const unsigned range = 2 * pad + 1;
@@ -151,6 +158,8 @@ __global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned 
 // out[i] ~ N(0,1): stream 5, Box-Muller on pair (i >> 1)
 __global__ void rng_normal_kernel(unsigned long long seed, const unsigned long long* counter,
                                   float* __restrict__ out, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t r[4];
@@ -163,11 +172,15 @@ __global__ void rng_normal_kernel(unsigned long long seed, const unsigned long l
     out[i] = (i & 1) ? rad * s : rad * co;
 }
 
-__global__ void counter_advance_kernel(unsigned long long* counter) { *counter += 1ull; }
+__global__ void counter_advance_kernel(unsigned long long* counter) {
+    pdl_trigger();
+    pdl_wait(); *counter += 1ull; }
 
 // out[n,c,r,col] = in[n,c,clamp(r+sy-pad),clamp(col+sx-pad)]
 __global__ void random_shift_f32_kernel(const float* __restrict__ in, const int* __restrict__ shift,
                                         float* __restrict__ out, int C, int H, int W, int pad) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.y;
     const int sx = shift[2 * n], sy = shift[2 * n + 1];
     const long long per = (long long)C * H * W;
@@ -183,6 +196,8 @@ __global__ void random_shift_f32_kernel(const float* __restrict__ in, const int*
 
 __global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
                               long long ld_dst, int rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int r = i / cols, c = i - r * cols;
@@ -194,6 +209,8 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, f
 using namespace drq;
 
 extern "C" {
+
+int drq_set_pdl(int on) { g_pdl = on ? 1 : 0; return DRQ_OK; }
 
 int drq_abi_version(void) { return DRQ_ABI_VERSION; }
 const char* drq_last_error(void) { return drq::g_err; }
@@ -224,7 +241,7 @@ int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const floa
                     ((uintptr_t)obs_out % 16) == 0 && ((uintptr_t)next_obs_out % 16) == 0,
                 "ring_gather: frames must be 16-byte aligned");
     dim3 grid(B, 2 * stack + 1);
-    ring_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+    launch_k(ring_gather_kernel, grid, 256, 0, as_stream(stream), 
         frames, action, reward, discount, (long long)capacity, frame_bytes, stack, A, ep_start, idx,
         nstep, gamma, obs_out, next_obs_out, action_out, reward_out, discount_out);
     return check_launch("ring_gather_kernel");
@@ -234,7 +251,7 @@ int drq_ring_sample(const int32_t* ep_table, const int32_t* n_episodes, int nste
                     const uint64_t* counter, int32_t* ep_start_out, int32_t* idx_out, int B, void* stream) {
     DRQ_REQUIRE(ep_table && n_episodes && counter && ep_start_out && idx_out, "ring_sample: null pointer");
     DRQ_REQUIRE(nstep > 0 && B > 0, "ring_sample: bad dims");
-    ring_sample_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(
+    launch_k(ring_sample_kernel, (B + 127) / 128, 128, 0, as_stream(stream), 
         ep_table, n_episodes, nstep, (unsigned long long)seed, (const unsigned long long*)counter,
         ep_start_out, idx_out, B);
     return check_launch("ring_sample_kernel");
@@ -246,7 +263,7 @@ int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_
     DRQ_REQUIRE(counter && shift_obs && shift_next && eps_critic && eps_actor, "rng: null pointer");
     DRQ_REQUIRE(B > 0 && A > 0 && pad >= 0, "rng: bad dims");
     const int n = B * A > B ? B * A : B;
-    rng_update_draws_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+    launch_k(rng_update_draws_kernel, (n + 127) / 128, 128, 0, as_stream(stream), 
         (unsigned long long)seed, (const unsigned long long*)counter, pad, shift_obs, shift_next,
         eps_critic, eps_actor, B, A);
     return check_launch("rng_update_draws_kernel");
@@ -255,20 +272,20 @@ int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_
 int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols,
                    void* stream) {
     DRQ_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad args");
-    copy2d_kernel<<<(rows * cols + 255) / 256, 256, 0, as_stream(stream)>>>(src, ld_src, dst, ld_dst, rows, cols);
+    launch_k(copy2d_kernel, (rows * cols + 255) / 256, 256, 0, as_stream(stream), src, ld_src, dst, ld_dst, rows, cols);
     return check_launch("copy2d_kernel");
 }
 
 int drq_rng_normal_f32(uint64_t seed, const uint64_t* counter, float* out, int n, void* stream) {
     DRQ_REQUIRE(counter && out && n > 0, "rng_normal: bad args");
-    rng_normal_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+    launch_k(rng_normal_kernel, (n + 127) / 128, 128, 0, as_stream(stream), 
         (unsigned long long)seed, (const unsigned long long*)counter, out, n);
     return check_launch("rng_normal_kernel");
 }
 
 int drq_counter_advance(uint64_t* counter, void* stream) {
     DRQ_REQUIRE(counter, "counter_advance: null pointer");
-    counter_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long*)counter);
+    launch_k(counter_advance_kernel, 1, 1, 0, as_stream(stream), (unsigned long long*)counter);
     return check_launch("counter_advance_kernel");
 }
 
@@ -281,7 +298,7 @@ int drq_random_shift_f32(const float* in, const int32_t* shift, float* out, int 
     const long long per = (long long)C * H * W;
     int gx = (int)((per + 255) / 256);
     if (gx > 64) gx = 64;
-    random_shift_f32_kernel<<<dim3(gx, N), 256, 0, as_stream(stream)>>>(in, shift, out, C, H, W, pad);
+    launch_k(random_shift_f32_kernel, dim3(gx, N), 256, 0, as_stream(stream), in, shift, out, C, H, W, pad);
     return check_launch("random_shift_f32_kernel");
 }
 

@@ -69,6 +69,10 @@ int drq_abi_version(void);
 const char* drq_last_error(void);
 /* number of SMs of the current device (0 if none) — used to size persistent grids */
 int drq_device_sm_count(void);
+/* programmatic dependent launch for every kernel of the library (default off): the next kernel's launch
+ * latency and CTA-local set-up overlap the running kernel's tail; each kernel waits for its predecessors
+ * (griddepcontrol.wait) before touching global memory. */
+int drq_set_pdl(int on);
 
 /* ------------------------------------------------------------------ replay */
 
@@ -174,7 +178,7 @@ int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, voi
 /* conv2..4 (drqv2.py:56-59) + bias + ReLU on tcgen05 tensor cores, bf16 in / fp32 accumulate
  * (TMEM) / bf16 out.  in, out: WB buffers of N images.  nhwc_out == 1: out is the compact NHWC
  * feature matrix [N][hout*hout][32]; nhwc_out == 2: out is the TB feature matrix the tensor-core
- * trunk consumes (feature (y*hout+x)*32+c, feat_rpad = units per row = hout*hout*4); image n is row n
+ * trunk consumes (feature (c/8)*hout*hout*8 + (y*hout+x)*8 + c%8, feat_rpad = units per row = hout*hout*4); image n is row n
  * for n < feat_half and row n - feat_half + feat_half_row after it (the next_obs half of an update starts
  * on its own 128-row block); feat_half <= 0: row = image. */
 int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float* bias, uint16_t* out,
@@ -228,7 +232,7 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void);
 #define DRQ_TEPI_F32 0          /* C(fp32 row-major, stride ldc) = acc (+bias) (+C if accumulate)   */
 #define DRQ_TEPI_RELU_BF16 1    /* C(TB bf16 activation, units = ldc) = relu(acc + bias)             */
 #define DRQ_TEPI_MASK_BF16 2    /* C(TB bf16) = acc * (mask > 0), mask TB activation with units_mask  */
-#define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: NHWC feature column -> reference order   */
+#define DRQ_TEPI_TRUNK_WGRAD 3  /* C(fp32)[m][ref(n)] = acc: encoder-output feature column -> reference order */
 #define DRQ_TEPI_TRUNK_DGRAD 4  /* C(WB bf16 of conv4's gradient) = acc * (feature > 0), scattered; ldc = WB block stride in rows; mask = TB features */
 
 /* C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, bf16 TB operands, fp32 accumulate (TMEM).
@@ -255,8 +259,8 @@ int drq_debug_conv1_stamps(int64_t* buf);
 
 /* fp32 nn.Linear weight [rows][cols] -> TB(DRQ_TB_W) bf16 [ceil(rows/64)][ceil16(cols)/8][64][8]. */
 int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* stream);
-/* trunk Linear(39200->rows) weight -> TB(DRQ_TB_W) bf16 in the NHWC feature order (y*35+x)*32+c of the
- * bf16 feature layout (reference column c*1225+y*35+x, drqv2.py:66). */
+/* trunk Linear(39200->rows) weight -> TB(DRQ_TB_W) bf16 in the feature order (c/8)*9800 + (y*35+x)*8 + c%8
+ * of the bf16 encoder output (reference column c*1225+y*35+x, drqv2.py:66). */
 int drq_pack_trunk_tb(const float* w, uint16_t* out, int rows, void* stream);
 
 /* all bf16 operand re-packs of one optimiser phase in one launch.  kind LINEAR: drq_pack_linear_tb(w, out,

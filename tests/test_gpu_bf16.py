@@ -56,7 +56,7 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
     torch.cuda.synchronize()
     got2 = feat.float().view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
     assert torch.equal(got2, got)
-    # TB feature matrix (rows = images, features in NHWC order); the second "half" starts on its own row block
+    # TB feature matrix (rows = images, channel-group-major feature order); the second "half" starts on its own row block
     from drqv2_b200._bf16 import TB
     half = N // 2
     fb = TB(128 + N, hout * hout * 32, dev)
@@ -64,7 +64,8 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
               half, 128, _stream())
     torch.cuda.synchronize()
     rows = torch.cat([fb.view()[:half], fb.view()[128:128 + N - half]]).float()
-    got3 = rows[:, :hout * hout * 32].view(N, hout, hout, 32).permute(0, 3, 1, 2).double()
+    # feature order of the bf16 encoder output: (c/8)*hw*8 + yx*8 + c%8
+    got3 = rows[:, :hout * hout * 32].view(N, 4, hout * hout, 8).permute(0, 1, 3, 2).reshape(N, 32, hout, hout).double()
     assert torch.equal(got3, got)
 
 
@@ -223,7 +224,7 @@ def test_gemm_bf16_dgrad_wgrad_layouts(dev):
 
 
 def test_trunk_weight_pack_and_epilogues(dev):
-    """NHWC-permuted trunk weight pack; wgrad epilogue writes the reference [F][39200] order;
+    """Encoder-order trunk weight pack; wgrad epilogue writes the reference [F][39200] order;
     dgrad epilogue masks by the feature and scatters into conv4's WB gradient plane."""
     from drqv2_b200 import _lib
     from drqv2_b200._bf16 import TB
@@ -233,8 +234,8 @@ def test_trunk_weight_pack_and_epilogues(dev):
     w = ((torch.rand(Fd, K, generator=g) - 0.5) * 0.02).to(dev)
     wp = TB(Fd, K, dev, rblk=64)
     _lib.call("drq_pack_trunk_tb", w.data_ptr(), wp.ptr(), Fd, _stream())
-    # reference order -> NHWC: column (y*35+x)*32+c holds w[:, c*1225 + y*35 + x]
-    w_nhwc = w.view(Fd, 32, 1225).permute(0, 2, 1).reshape(Fd, K)
+    # reference order -> encoder-output order: column (c/8)*9800 + (y*35+x)*8 + c%8 holds w[:, c*1225 + y*35 + x]
+    w_nhwc = w.view(Fd, 4, 8, 1225).permute(0, 1, 3, 2).reshape(Fd, K)
     assert torch.equal(wp.dense(), _bf(w_nhwc))
     # plain Linear weight pack (more than one 64-row block)
     w2 = ((torch.rand(70, 50, generator=g) - 0.5)).to(dev)
@@ -242,7 +243,7 @@ def test_trunk_weight_pack_and_epilogues(dev):
     _lib.call("drq_pack_linear_tb", w2.data_ptr(), w2p.ptr(), 70, 50, _stream())
     assert torch.equal(w2p.dense(), _bf(w2))
     feat_nchw = (torch.rand(Bt, 32, 35, 35, generator=g) - 0.4).clamp_min(0).to(dev)
-    feat = _tb(feat_nchw.permute(0, 2, 3, 1).reshape(Bt, K))           # NHWC feature order
+    feat = _tb(feat_nchw.view(Bt, 4, 8, 1225).permute(0, 1, 3, 2).reshape(Bt, K))     # encoder-output feature order
     dz = ((torch.rand(Bt, Fd, generator=g) - 0.5) * 1e-2).to(dev)
     dzb = _tb(dz)
     # wgrad: dW[f][ref(n)] = sum_b dz[b][f] feat[b][n]

@@ -32,6 +32,11 @@ run("wgrad 2x(1024x1024x256) bn64", lambda: gemm(x.ptr(), x.units, y.ptr(), y.un
 x56 = TB(Bt, 56, dev); w56 = TB(H, 56, dev, rblk=64)
 run("fwd K=56", lambda: gemm(x56.ptr(), x56.units, w56.ptr(), w56.units, GEMM_KK, y.ptr(), y.units, Bt, H, 56, TEPI_RELU_BF16, bias=bias.data_ptr()))
 feat = TB(512, 39200, dev); wt = TB(192, 39200, dev, rblk=64)
-S = 37
+S = 35
 part = torch.zeros(S * 2 * 256 * 128, device=dev)
-run("trunk fwd merged (2 x 256 x 128, splitk 37, bn 128)", lambda: gemm(feat.ptr(), feat.units, wt.ptr(row=64), wt.units, GEMM_KK, part.data_ptr(), 128, 256, 128, 39200, TEPI_F32, batch=2, batch_inner=1, bn=128, splitk=S, strides=_strides(outer=(feat.off(row=256), -wt.off(row=64), 256 * 128, 0, 0), split=2 * 256 * 128)))
+run("trunk fwd merged (2 x 256 x 128, splitk 35, bn 128)", lambda: gemm(feat.ptr(), feat.units, wt.ptr(row=64), wt.units, GEMM_KK, part.data_ptr(), 128, 256, 128, 39200, TEPI_F32, batch=2, batch_inner=1, bn=128, splitk=S, strides=_strides(outer=(feat.off(row=256), -wt.off(row=64), 256 * 128, 0, 0), split=2 * 256 * 128)))
+dz = TB(256, 50, dev)
+dwt = torch.zeros(50, 39200, device=dev)
+run("trunk wgrad (50 x 39200 x 256)", lambda: gemm(dz.ptr(), dz.units, feat.ptr(), feat.units, GEMM_MNMN, dwt.data_ptr(), 39200, 50, 39200, 256, 3, bn=128))
+d4 = torch.zeros(_lib.lib().drq_wb_elems(256), dtype=torch.bfloat16, device=dev)
+run("trunk dgrad (256 x 39200 x 50)", lambda: gemm(dz.ptr(), dz.units, wt.ptr(), wt.units, GEMM_KMN, d4.data_ptr(), 256 * 1776 + 128, 256, 39200, 50, 4, mask=feat.ptr(), units_mask=feat.units, bn=128))
