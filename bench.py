@@ -125,11 +125,15 @@ def run_ours(args, rank, world):
     from drqv2_b200 import DrQV2Agent, _lib, make_replay_loader
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
-    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
-    torch.manual_seed(rank)                       # ensemble member = independent seed
+    dp = args.parallel == "dp" and world > 1
+    A, Fd, H = args.action_dim, args.feature_dim, args.hidden_dim
+    B = args.batch // world if dp else args.batch  # dp: --batch is the global batch, sharded over the ranks
+    if dp and args.batch % world:
+        raise SystemExit(f"--batch {args.batch} does not split over {world} ranks")
+    torch.manual_seed(0 if dp else rank)          # ensemble member = independent seed; dp = one agent
     np.random.seed(7 + rank)
     agent = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
-                       use_cuda_graph=True, seed=rank, mode=args.mode)
+                       use_cuda_graph=True, seed=0 if dp else rank, mode=args.mode, data_parallel=dp)
     key = f"/bench/ring{rank}"
     fill_ring(key, A, args.episodes, 501, dev, seed=1 + rank)
     loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
@@ -174,7 +178,7 @@ def run_ours(args, rank, world):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = t.item()
     ms_per_step = ms / args.steps
-    value = world * 1e3 / ms_per_step
+    value = (1 if dp else world) * 1e3 / ms_per_step      # dp: global-batch updates/s; ensemble: sum over agents
 
     # ---- e2e: public API fed from host batches (pinned), metrics read back
     agent.use_tb = True
@@ -209,7 +213,7 @@ def run_ours(args, rank, world):
         t = torch.tensor([e2e_ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = t.item()
-    e2e_value = world * 1e3 / (e2e_ms / args.steps)
+    e2e_value = (1 if dp else world) * 1e3 / (e2e_ms / args.steps)
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0]) + 64
     d2h = 8 * 4
     assert np.isfinite(m["critic_loss"])
@@ -218,7 +222,7 @@ def run_ours(args, rank, world):
     out = None
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()
-        flops = update_flops(B, A, Fd, H)
+        flops = update_flops(B, A, Fd, H) * (world if dp else 1)     # per counted update
         # ---- dominant kernel, timed alone with CUDA events on its launch stream
         ws = agent.workspace(B)
         s = torch.cuda.current_stream().cuda_stream
@@ -255,17 +259,17 @@ def run_ours(args, rank, world):
                 "unit": "TFLOP/s", "frac": fl / dt / 1e12 / tf_burst, "traffic": None, "peak_source": src,
                 "kernel_ms": dt * 1e3,
                 "all_kernels_ms": {k: v[0] * 1e3 for k, v in kt.items()},
-                "whole_update": {"flop": flops, "achieved": flops * value / world / 1e12,
+                "whole_update": {"flop": flops, "achieved_per_gpu": flops * value / world / 1e12,
                                  "frac_of_sustained": flops * value / world / 1e12 / tf_sust}}
         cpu = cpu_baseline(args, steps=2)
         out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "higher_is_better": True, "scaling": "strong" if dp else "weak", "vs_baseline": None,
                "dtype": "bf16" if args.mode == "bf16" else "f32",
                "data": "synthetic",
                "config": {"workload": f"configs[1]: walker_walk-shape agent.update, B={B}, 9x84x84 u8 stacks, A={A}, "
                                       f"F={Fd}, H={H}, n-step 3, GPU-resident replay ring ({args.episodes} episodes x 501 "
-                                      f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; {world} independent agents (ensemble), one per GPU" if world > 1 else ""),
+                                      f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; global batch {args.batch} data-parallel over {world} GPUs (NCCL gradient all-reduce in the graph)" if dp else (f"; {world} independent agents (ensemble), one per GPU, no collective" if world > 1 else "")),
                           "l2": "inputs larger than L2: each step gathers a fresh 32.5 MB batch from a "
                                 f"{args.episodes * 501 * 21168 / 1e6:.0f} MB ring and streams ~700 MB of activations",
                           "mode": args.mode},
@@ -380,6 +384,9 @@ def main():
     ap.add_argument("--hidden-dim", type=int, default=1024)
     ap.add_argument("--episodes", type=int, default=64)
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--parallel", default="ensemble", choices=["ensemble", "dp"],
+                    help="N > 1: independent agents per GPU (weak scaling, no collective) or one agent with the "
+                         "global --batch sharded over the GPUs and NCCL gradient all-reduce (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -395,8 +402,15 @@ def main():
     if out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
+        # graphs holding captured NCCL kernels were dropped with the agent (run_ours returned); a teardown
+        # that still blocks must not hold the job: force-exit after a grace period
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

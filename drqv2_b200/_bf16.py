@@ -363,6 +363,7 @@ def critic_pass(agent, ws, bw):
     call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], wsp, ge("convnet.0.weight"),
          ge("convnet.0.bias"), B, agent.obs_shape[0], agent.aug.pad, s)
     # critic_opt.step(); encoder_opt.step(); refresh their bf16 operand copies
+    agent._sync_grads("encoder", "critic")          # data-parallel: mean over ranks (no-op otherwise)
     a = agent._arena
     off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
     call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
@@ -426,6 +427,7 @@ def actor_pass(agent, ws, bw):
     colsum_multi([ColsumJob(ws.dmu_pre.data_ptr(), A, ga("policy.4.bias"), B, A, 0, 0),
                   ColsumJob(dp2.ptr(), U, ga("policy.2.bias"), B, H, 1, 0), ColsumJob(dp1.ptr(), U, ga("policy.0.bias"), B, H, 1, 0),
                   ColsumJob(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 0, 0)])
+    agent._sync_grads("actor")
     a = agent._arena
     off, n = a.seg["actor"][0], a.seg["actor"][2]
     coff, cn = a.seg["critic"][0], a.seg["critic"][2]

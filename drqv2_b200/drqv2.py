@@ -18,7 +18,7 @@ import torch.nn as nn
 
 import os
 
-from . import _bf16, _lib, utils
+from . import _bf16, _lib, dist as _dist, utils
 from ._lib import EPI_MASK, EPI_MASK_WIDE, EPI_NONE, EPI_RELU, PLANE, REPR_DIM, call
 
 F32 = 4
@@ -357,11 +357,14 @@ METRIC_KEYS = ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "cri
 class DrQV2Agent:
     def __init__(self, obs_shape, action_shape, device, lr, feature_dim, hidden_dim, critic_target_tau,
                  num_expl_steps, update_every_steps, stddev_schedule, stddev_clip, use_tb,
-                 use_cuda_graph=True, seed=None, mode=None):
+                 use_cuda_graph=True, seed=None, mode=None, data_parallel=False):
         """Reference signature (drqv2.py:125-127) plus three keyword-only extras: use_cuda_graph,
         seed (device RNG key) and mode — "fp32" (parity mode, CUDA-core kernels, <= 1e-4 vs the
         reference on pre-optimiser quantities) or "bf16" (tcgen05 tensor-core kernels, bf16
-        operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "fp32"."""
+        operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "fp32".
+        data_parallel=True (torch.distributed initialised, one process per GPU): the batch given to
+        update() is this rank's shard; gradients are averaged over ranks before each optimiser step and
+        parameters are broadcast from rank 0 at construction (drqv2_b200/dist.py)."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError(f"DrQV2Agent(device={device!r}): drqv2_b200 has no CPU path; use a CUDA device")
@@ -398,6 +401,12 @@ class DrQV2Agent:
         self.aug = RandomShiftsAug(pad=4)
         self._opt_step = 0
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        self.data_parallel = bool(data_parallel) and _dist.world() > 1
+        if self.data_parallel:
+            a = self._arena
+            _dist.broadcast_([a.params, a.target, a.exp_avg, a.exp_avg_sq])
+            self._seed = _dist.rank_seed(self._seed, torch.distributed.get_rank())
+            self._bf16_dirty = True
         self.train()
         self.critic_target.train()
 
@@ -480,6 +489,16 @@ class DrQV2Agent:
         in order (drqv2.py:241-242, utils.py:119 twice)."""
         self._injected = (shift_obs, shift_next, eps_critic, eps_actor)
 
+    def _sync_grads(self, first, last=None):
+        """Data-parallel: average the gradient range of nets first..last over the ranks (in stream order,
+        inside the graph).  No-op for a single process."""
+        if not self.data_parallel:
+            return
+        a = self._arena
+        off = a.seg[first][0]
+        end = a.seg[last or first][0] + a.seg[last or first][2]
+        _dist.average_(a.grads[off:end])
+
     def _p(self, net, pname):
         return self._arena.ptr("params", net, pname)
 
@@ -532,7 +551,7 @@ class DrQV2Agent:
             if self.use_cuda_graph:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._act_body(w, n, sample)
                 w["graph"][key] = g
                 g.replay()
@@ -607,7 +626,7 @@ class DrQV2Agent:
             if state == "warm":
                 torch.cuda.synchronize()
                 state = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(state):
+                with torch.cuda.graph(state, capture_error_mode="thread_local"):   # NCCL's watchdog thread may touch CUDA during capture
                     self._update_body(ws, fetch, draw=inj is None)
                 self._graphs[key] = state
             state.replay()
@@ -737,8 +756,10 @@ class DrQV2Agent:
         a = self._arena
         if encoder_grad:
             off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
+            self._sync_grads("encoder", "critic")
         else:
             off, n = a.seg["critic"][0], a.seg["critic"][2]
+            self._sync_grads("critic")
         call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
              a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n,
              self._scal_dev.data_ptr(), s)
@@ -812,6 +833,7 @@ class DrQV2Agent:
              ga("trunk.1.bias"), None, 0, B, Fd, 1, 0, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, ga("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd)
+        self._sync_grads("actor")
         # actor_opt.step() fused with the soft target update of the (already stepped) critic
         a = self._arena
         off, n = a.seg["actor"][0], a.seg["actor"][2]
