@@ -139,24 +139,28 @@ def run_ours(args, rank, world):
     loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
     it = iter(loader)
 
-    # count kernel launches of one update (eager pass == what the graph replays)
+    # count kernel launches of one update (eager pass == what the graph replays): every C-ABI call of the
+    # update goes through _lib.call; entry points that launch two kernels are listed below
     n_calls = [0]
     orig_call = _lib.call
+    two_kernel_calls = ("drq_conv3x3_wgrad_bf16", "drq_conv1_wgrad_bf16", "drq_ln_tanh_bwd", "drq_conv3x3_wgrad_f32",
+                        "drq_conv1_wgrad_f32")
 
     def counting_call(name, *a):
-        n_calls[0] += 1
+        n_calls[0] += 2 if name in two_kernel_calls else 1
         return orig_call(name, *a)
 
+    import drqv2_b200._bf16 as BF
     import drqv2_b200.drqv2 as D
     import drqv2_b200.replay_buffer as R
-    D.call = R.call = counting_call
     step = 0
-    agent.update(it, step); step += 2             # eager warm-up (counts launches)
-    launches_per_update = n_calls[0] + 1          # + the H2D scalar copy node is not a kernel; +1 = none
+    agent.update(it, step); step += 2             # eager warm-up
+    D.call = R.call = BF.call = counting_call
+    agent.use_cuda_graph = False
+    agent.update(it, step); step += 2             # eager, counted
+    agent.use_cuda_graph = True
     launches_per_update = n_calls[0]
-    D.call = R.call = orig_call
-    # conv wgrad entry points launch 2 kernels each (partial + reduce)
-    launches_per_update += 4
+    D.call = R.call = BF.call = orig_call
     for _ in range(max(args.warmup, 3)):
         agent.update(it, step); step += 2
     torch.cuda.synchronize()
@@ -252,11 +256,15 @@ def run_ours(args, rank, world):
                                               2 * CONV_MACS[39] * B),
         }
         kt = {k: (time_kernel(fn), fl) for k, (fn, fl) in cand.items()}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
+        # launches (profiles/r1_ncu_full_conv_kernels.txt, B = 256)
+        traffic = {"conv3x3_tc_kernel<fwd>(layer2,N=2B)": 69.2e6, "conv3x3_tc_kernel<dgrad>(layer2,N=B)": 59.9e6,
+                   "conv3x3_wgrad_tc_kernel(layer2,N=B)": 56.3e6} if (args.mode == "bf16" and B == 256) else {}
         # share of the step: fwd x3 layers x(2B), dgrad x3, wgrad x3 are of the same class
         dom = max(kt, key=lambda k: kt[k][0])
         dt, fl = kt[dom]
         roof = {"bound": "tensor", "kernel": dom, "achieved": fl / dt / 1e12, "peak": tf_burst,
-                "unit": "TFLOP/s", "frac": fl / dt / 1e12 / tf_burst, "traffic": None, "peak_source": src,
+                "unit": "TFLOP/s", "frac": fl / dt / 1e12 / tf_burst, "traffic": traffic.get(dom), "peak_source": src,
                 "kernel_ms": dt * 1e3,
                 "all_kernels_ms": {k: v[0] * 1e3 for k, v in kt.items()},
                 "whole_update": {"flop": flops, "achieved_per_gpu": flops * value / world / 1e12,
@@ -375,8 +383,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--action-dim", type=int, default=6)
