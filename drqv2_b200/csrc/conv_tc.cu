@@ -53,7 +53,7 @@ static long long* g_conv_stamps = nullptr;
 #endif
 
 template <bool DGRAD>
-__global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_tc_kernel(ConvTcArgs a) {
+__global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_tc_kernel(ConvTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* a_s = smem + kWBytes;
@@ -259,7 +259,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // ignored).  A tenth "tap" multiplies d by an all-ones A operand: its row 0 is the bias
 // gradient.  Every CTA keeps its 10 accumulators (320 TMEM columns) across all of its tiles
 // and writes one fp32 partial at the end; partials are reduced in fixed order.
-constexpr int kWgStages = 4;
+constexpr int kWgStages = 3;
 constexpr int kWgDRows = kTM;                              // d tile rows per block
 constexpr int kWgStageBytes = kStageBytes + 4 * kWgDRows * 16;   // in-window + d tile
 constexpr int kWgOnesBytes = 8 * 16 * 16;                  // 8 MN units x 16 K x 16 B of bf16 ones
@@ -273,7 +273,10 @@ struct WgradTcArgs {
     int n_images, ntiles;
 };
 
-__global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
+// Two CTAs share an SM: CTA pair (2i, 2i+1) walks the same tiles, the even one accumulates taps 0..4, the odd
+// one taps 5..8 and the bias tap (5 x 32 TMEM columns each).  A lone CTA issues M64 N32 UMMAs at one per
+// ~45 cycles whatever the pipe could take; two interleaved streams nearly double that (tools/ub/ub_mma.cu).
+__global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ones_s = smem;
     uint8_t* st_s = smem + kWgOnesBytes;
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = a.n_images * a.ntiles;
+    const int half = blockIdx.x & 1, cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;     // tap half, tile walker
     pdl_trigger();
     for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kThreadsTC)
         reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;    // bf16 1.0 x2
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
     fence_proxy_async();
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     if (warp == 0) {
         // lanes 0..3: input-window channel blocks, lanes 4..7: gradient tile channel blocks
         int stage = 0; uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = cta; t < total_tiles; t += ncta) {
             const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
             mbar_wait(empty + stage, phase ^ 1);
             if (lane == 0) mbar_arrive_expect_tx(full + stage, 4 * (kWinRows + kWgDRows) * 16);
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         const uint64_t da0 = make_smem_desc(smem_u32(st_s), 128, kStageRows * 16);
         const uint64_t db0 = make_smem_desc(smem_u32(st_s) + kStageBytes, 128, kWgDRows * 16);
         const uint64_t d1 = make_smem_desc(smem_u32(ones_s), 128, 256);
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = cta; t < total_tiles; t += ncta) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
@@ -338,10 +342,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
                     const uint64_t db = db0 + so + (uint64_t)(ks * 16);
                     const uint64_t da = da0 + so + (uint64_t)(ks * 16);
                     const uint32_t accum = (first && ks == 0) ? 0u : 1u;
+                    if (half == 0) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap)
-                        umma_bf16(tmem_base + tap * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
-                    umma_bf16(tmem_base + 9 * 32, d1, db, idesc, accum);
+                        for (int tap = 0; tap < 5; ++tap)
+                            umma_bf16(tmem_base + tap * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
+                    } else {
+#pragma unroll
+                        for (int tap = 5; tap < 9; ++tap)
+                            umma_bf16(tmem_base + (tap - 5) * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
+                        umma_bf16(tmem_base + 4 * 32, d1, db, idesc, accum);
+                    }
                 }
                 umma_commit(empty + stage);
             }
@@ -355,12 +365,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         const int q = warp & 3;
         mbar_wait(done, 0);
         tc_fence_after();
-        float* out = a.partial + (long long)blockIdx.x * kWgPartial;
+        float* out = a.partial + (long long)cta * kWgPartial;
         if (q < 2) {
             // M = 64 accumulator: rows 0..15 -> lanes 0..15, rows 16..31 -> lanes 32..47
-            for (int tap = 0; tap < kWgAcc; ++tap) {
+            for (int tl = 0; tl < 5; ++tl) {
+                const int tap = half * 5 + tl;
                 float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + tap * 32, v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + tl * 32, v);
                 if (lane < 16) {
                     float4* dst = reinterpret_cast<float4*>(out + (tap * 32 + q * 16 + lane) * 32);
 #pragma unroll
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co].  Block = 32 outputs x 8
@@ -409,9 +420,11 @@ constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * 
 
 constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16 + 128;
 
-static int conv_tc_grid(int total_tiles) {
-    const int sms = 148;
-    return total_tiles < sms ? total_tiles : sms;
+// ctas_per_sm = 2 for forward / dgrad (74 KB smem, 128 TMEM columns each): independent pipelines per SM
+// keep the tensor pipe fed while one CTA's issuing thread waits for data or a free accumulator
+static int conv_tc_grid(int total_tiles, int ctas_per_sm = 1) {
+    const int slots = 148 * ctas_per_sm;
+    return total_tiles < slots ? total_tiles : slots;
 }
 
 }  // namespace drq
@@ -453,7 +466,7 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
-    launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream), a);
+    launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<fwd>");
 }
 
@@ -477,7 +490,7 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.w_valid = hin;
     a.nhwc_out = 0;
     a.stamps = g_conv_stamps;
-    launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles), kThreadsTC, kConvTcSmem, as_stream(stream), a);
+    launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
 }
 
@@ -496,8 +509,8 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     a.partial = partial;
     a.n_images = N;
     a.ntiles = (hout * kPW + kTM - 1) / kTM;
-    const int G = conv_tc_grid(N * a.ntiles);
-    launch_k(conv3x3_wgrad_tc_kernel, G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
+    const int G = conv_tc_grid(N * a.ntiles);                 // tile walkers; each is a pair of CTAs
+    launch_k(conv3x3_wgrad_tc_kernel, 2 * G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
     launch_k(wgrad_tc_reduce_kernel, (9248 + 31) / 32, 256, 0, as_stream(stream), partial, G, dw, db);
     return check_launch("wgrad_tc_reduce_kernel");

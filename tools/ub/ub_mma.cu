@@ -13,13 +13,13 @@ __device__ __forceinline__ uint64_t desc_sw(uint32_t addr, uint32_t lbo, uint32_
 
 // mode 0: K-major no swizzle ([unit][rows][16B]); 1: K-major 128B swizzle ([rows][128B], K=64 per row);
 // 2: MN-major no swizzle for both
-__global__ void __launch_bounds__(128, 1) mma_kernel(int M, int N, int mode, int iters, int distinct, long long* out) {
+__global__ void __launch_bounds__(128, 2) mma_kernel(int M, int N, int mode, int iters, int distinct, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
     for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u + (i & 7);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    if (threadIdx.x < 32) { tmem_alloc(&slot, 256); tmem_relinquish(); }
+    if (threadIdx.x < 32) { tmem_alloc(&slot, 256); tmem_relinquish(); }   // 2 CTAs per SM: 2 x 256 columns
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -55,14 +55,16 @@ int main() {
     long long* out; cudaMalloc(&out, 148 * 8);
     cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     printf("M N mode | cycles/MMA (grid 148)  -> MAC/clk/SM\n");
-    for (int mode = 0; mode < 3; ++mode)
+    for (int ctas : {1, 2}) {
+    printf("---- %d CTA(s) per SM\n", ctas);
+    for (int mode = 0; mode < 1; ++mode)
         for (int M : {64, 128})
             for (int N : {32, 64, 128, 256}) {
                 if (mode == 2 && N == 256) continue;
                 const int iters = 4000;
               for (int distinct : {9, 8}) {
                 if (distinct == 8 && mode == 1) continue;
-                mma_kernel<<<148, 128, 100 * 1024>>>(M, N, mode, iters, distinct, out);
+                mma_kernel<<<148 * ctas, 128, 100 * 1024>>>(M, N, mode, iters, distinct, out);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("M=%d N=%d mode=%d: %s\n", M, N, mode, cudaGetErrorString(e)); return 1; }
                 long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
@@ -70,5 +72,6 @@ int main() {
                 printf("%3d %3d %d %s | %7.1f  -> %.0f\n", M, N, mode, distinct == 9 ? "tap-offsets" : "aligned    ", c, (double)M * N * 16 / c);
               }
             }
+    }
     return 0;
 }
