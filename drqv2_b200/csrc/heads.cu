@@ -22,32 +22,42 @@ struct LnJobs { drq_ln_job j[DRQ_LN_MAX_JOBS]; };
 template <int NF>   // features per lane: F <= 32 * NF
 __global__ void __launch_bounds__(128)
 ln_tanh_fwd_kernel(const LnJobs jobs, int B, int F, float eps) {
+    // One block per (row, job): the four warps sum interleaved quarters of the split-K planes (all loads of a
+    // warp in flight at once), the partial rows are combined in fixed order, warp 0 normalises.
+    __shared__ float part[4][32 * NF];
     pdl_trigger();
     pdl_wait();
     const drq_ln_job& jb = jobs.j[blockIdx.y];
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= B) return;
-    float z[NF];
-    float sum = 0.f;
+    const int row = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int MAXP = 16;                           // planes per warp held in flight (S <= 64); more fall back to a loop
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
         const int f = lane + 32 * i;
         float v = 0.f;
         if (f < F) {
             const float* pp = jb.partial + (long long)row * jb.ld_partial + f;
-            int s = 0;
-#pragma unroll 1
-            for (; s + 8 <= jb.S; s += 8) {
-                float t[8];
+            float t[MAXP];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) t[k] = pp[(s + k) * jb.split_stride];
-                v += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            for (int k = 0; k < MAXP; ++k) {
+                const int s = w + 4 * k;
+                t[k] = s < jb.S ? pp[s * jb.split_stride] : 0.f;
             }
-#pragma unroll 1
-            for (; s < jb.S; ++s) v += pp[s * jb.split_stride];
-            v += jb.bias[f];
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k) v += t[k];
+            for (int s = w + 4 * MAXP; s < jb.S; s += 4) v += pp[s * jb.split_stride];
         }
+        part[w][f] = v;
+    }
+    __syncthreads();
+    if (w != 0) return;
+    float z[NF];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        const int f = lane + 32 * i;
+        float v = 0.f;
+        if (f < F) v = ((part[0][f] + part[1][f]) + (part[2][f] + part[3][f])) + jb.bias[f];
         z[i] = v;
         sum += v;
     }
@@ -421,7 +431,7 @@ int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float
                     "ln_tanh_fwd: null pointer in job %d", i);
     }
     if (B == 0) return DRQ_OK;
-    const dim3 grid((B + 3) / 4, njobs);
+    const dim3 grid(B, njobs);
     cudaStream_t s = as_stream(stream);
     if (F <= 64) launch_k(ln_tanh_fwd_kernel<2>, grid, 128, 0, s, js, B, F, eps);
     else if (F <= 128) launch_k(ln_tanh_fwd_kernel<4>, grid, 128, 0, s, js, B, F, eps);

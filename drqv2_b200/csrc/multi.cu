@@ -32,26 +32,48 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJobs jobs) {
 
 struct ColsumJobs { drq_colsum_job j[DRQ_COLSUM_MAX_JOBS]; };
 
-// out[n] = sum_m X[m][n]; block = 32 columns x 8 row lanes, fixed-order tree.  blockIdx.y = job.
+// out[n] = sum_m X[m][n] for 32 columns per block, blockIdx.y = job; fixed-order reductions.
+//   fp32 rows : 32 columns x 8 row lanes.
+//   TB bf16   : 4 units x 64 row lanes, one 16-byte load (8 columns of one row) per thread and step.
 __global__ void __launch_bounds__(256) colsum_multi_kernel(const ColsumJobs jobs) {
+    __shared__ float red[64][33];
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[8][33];
     const drq_colsum_job& jb = jobs.j[blockIdx.y];
+    if (blockIdx.x * 32 >= jb.N) return;
+    if (jb.tb) {
+        const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(jb.X);
+        const int u = threadIdx.x & 3, ry = threadIdx.x >> 2;
+        const long long unit = (long long)blockIdx.x * 4 + u;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (unit * 8 < jb.N) {
+            for (int m = ry; m < jb.M; m += 64) {
+                const uint4 v = *reinterpret_cast<const uint4*>(X + (((long long)(m >> 7) * jb.ld + unit) * DRQ_TB_ACT + (m & 127)) * 8);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[2 * j] += __uint_as_float(w[j] << 16);
+                    acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[ry][u * 8 + j] = acc[j];
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int n = blockIdx.x * 32 + threadIdx.x;
+            float t = 0.f;
+            for (int r = 0; r < 64; ++r) t += red[r][threadIdx.x];
+            if (n < jb.N) jb.out[n] = t;
+        }
+        return;
+    }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx;
-    if (blockIdx.x * 32 >= jb.N) return;
     float s = 0.f;
     if (n < jb.N) {
-        if (jb.tb) {
-            const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(jb.X);
-            const long long units = jb.ld;
-            for (int m = ty; m < jb.M; m += 8)
-                s += __bfloat162float(X[(((long long)(m >> 7) * units + (n >> 3)) * DRQ_TB_ACT + (m & 127)) * 8 + (n & 7)]);
-        } else {
-            const float* X = reinterpret_cast<const float*>(jb.X);
-            for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n];
-        }
+        const float* X = reinterpret_cast<const float*>(jb.X);
+        for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n];
     }
     red[ty][tx] = s;
     __syncthreads();
