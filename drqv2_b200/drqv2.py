@@ -427,12 +427,15 @@ class DrQV2Agent:
         self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None
         self._bf16_ws = {}
         self._bf16_dirty = True
+        self._prefetch, self._stage = None, {}
+        self.prefetch = True        # overlap the next host batch's H2D copy with the current update
 
     def __getstate__(self):
         st = dict(self.__dict__)
-        for k in ("_ws", "_graphs", "_act_ws", "_bf16_ws"):
+        for k in ("_ws", "_graphs", "_act_ws", "_bf16_ws", "_stage"):
             st[k] = {}
         st["_bf16"] = None
+        st["_prefetch"] = None
         return st
 
     def __setstate__(self, st):
@@ -597,12 +600,23 @@ class DrQV2Agent:
             ws = self.workspace(B)
             fetch = lambda: replay_iter.next_into(ws.obs[:B], ws.action, ws.reward, ws.discount, ws.obs[B:])
         else:
-            batch = next(replay_iter)
-            obs, action, reward, discount, next_obs = batch
-            B = obs.shape[0]
-            ws = self.workspace(B)
             fetch = None
-            self._load_batch(ws, obs, action, reward, discount, next_obs)
+            pf, self._prefetch = self._prefetch, None
+            if pf is not None and pf["it"] is replay_iter:
+                # the batch was pulled and its host->device copy started while the previous update ran
+                B = pf["B"]
+                ws = self.workspace(B)
+                torch.cuda.current_stream().wait_event(pf["ready"])
+                st = pf["stage"]
+                for dst, src in ((ws.obs, st["obs"]), (ws.action, st["action"]), (ws.reward, st["reward"]),
+                                 (ws.discount, st["discount"])):
+                    dst.copy_(src, non_blocking=True)
+                st["free"].record()
+            else:
+                obs, action, reward, discount, next_obs = next(replay_iter)
+                B = obs.shape[0]
+                ws = self.workspace(B)
+                self._load_batch(ws, obs, action, reward, discount, next_obs)
         self._host_scalars(step)
         if self._bf16_dirty:
             self.refresh()
@@ -631,12 +645,43 @@ class DrQV2Agent:
                 self._graphs[key] = state
             state.replay()
         self._opt_step += 1
+        if fetch is None and self.prefetch:
+            self._start_prefetch(replay_iter, ws)
         if self.use_tb:
             self._metrics_host.copy_(ws.metrics, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             vals = self._metrics_host.tolist()
             metrics = dict(zip(METRIC_KEYS, vals))
         return metrics
+
+    def _start_prefetch(self, replay_iter, ws):
+        """Pull the next host batch now and copy it to device staging buffers on a side stream, so the
+        PCIe transfer (32.5 MB at B=256) overlaps this update's kernels.  The reference's DataLoader
+        workers run ahead of the consumer in the same way (replay_buffer.py:181-186)."""
+        try:
+            batch = next(replay_iter)
+        except StopIteration:
+            return
+        obs, action, reward, discount, next_obs = (torch.as_tensor(t) for t in batch)
+        B = obs.shape[0]
+        st = self._stage.get(B)
+        if st is None:
+            w = self.workspace(B)
+            st = dict(obs=torch.empty_like(w.obs), action=torch.empty_like(w.action), reward=torch.empty_like(w.reward),
+                      discount=torch.empty_like(w.discount), free=torch.cuda.Event(), stream=torch.cuda.Stream())
+            st["free"].record()
+            self._stage[B] = st
+        side = st["stream"]
+        side.wait_event(st["free"])                  # the previous consumer of the staging buffers is done
+        with torch.cuda.stream(side):
+            st["obs"][:B].copy_(obs.view(st["obs"][:B].shape), non_blocking=True)
+            st["obs"][B:].copy_(next_obs.view(st["obs"][B:].shape), non_blocking=True)
+            st["action"].copy_(action.view(st["action"].shape), non_blocking=True)
+            st["reward"].copy_(reward.view(st["reward"].shape), non_blocking=True)
+            st["discount"].copy_(discount.view(st["discount"].shape), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        self._prefetch = dict(it=replay_iter, B=B, stage=st, ready=ready, hold=batch)
 
     def _load_batch(self, ws, obs, action, reward, discount, next_obs):
         B = ws.B
