@@ -184,8 +184,10 @@ def run_ours(args, rank, world):
     ms_per_step = ms / args.steps
     value = (1 if dp else world) * 1e3 / ms_per_step      # dp: global-batch updates/s; ensemble: sum over agents
 
-    # ---- e2e: public API fed from host batches (pinned), metrics read back
+    # ---- e2e: public API fed from host batches (pinned), metrics read back.  prefetch: the agent pulls the next
+    # host batch one update ahead and overlaps its H2D copy with the running update (a DrQV2Agent option)
     agent.use_tb = True
+    agent.prefetch = True
     g = torch.Generator().manual_seed(100 + rank)
     nhost = 4
     host_batches = []
@@ -222,6 +224,7 @@ def run_ours(args, rank, world):
     d2h = 8 * 4
     assert np.isfinite(m["critic_loss"])
     agent.use_tb = False
+    agent.prefetch = False
 
     out = None
     if rank == 0:

@@ -357,14 +357,17 @@ METRIC_KEYS = ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "cri
 class DrQV2Agent:
     def __init__(self, obs_shape, action_shape, device, lr, feature_dim, hidden_dim, critic_target_tau,
                  num_expl_steps, update_every_steps, stddev_schedule, stddev_clip, use_tb,
-                 use_cuda_graph=True, seed=None, mode=None, data_parallel=False):
+                 use_cuda_graph=True, seed=None, mode=None, data_parallel=False, prefetch=False):
         """Reference signature (drqv2.py:125-127) plus three keyword-only extras: use_cuda_graph,
         seed (device RNG key) and mode — "fp32" (parity mode, CUDA-core kernels, <= 1e-4 vs the
         reference on pre-optimiser quantities) or "bf16" (tcgen05 tensor-core kernels, bf16
         operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "fp32".
         data_parallel=True (torch.distributed initialised, one process per GPU): the batch given to
         update() is this rank's shard; gradients are averaged over ranks before each optimiser step and
-        parameters are broadcast from rank 0 at construction (drqv2_b200/dist.py)."""
+        parameters are broadcast from rank 0 at construction (drqv2_b200/dist.py).
+        prefetch=True: with a host-side replay iterator, pull the next batch at the end of every update and
+        copy it to the device on a side stream while that update still runs (the reference's DataLoader
+        workers run ahead in the same way); the default keeps drqv2.py:236's one next() per update."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError(f"DrQV2Agent(device={device!r}): drqv2_b200 has no CPU path; use a CUDA device")
@@ -380,6 +383,7 @@ class DrQV2Agent:
         self.stddev_clip = stddev_clip
         self.lr = lr
         self.use_cuda_graph = use_cuda_graph
+        self.prefetch = bool(prefetch)
         self.mode = mode or os.environ.get("DRQV2_B200_MODE", "fp32")
         if self.mode not in ("fp32", "bf16"):
             raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
@@ -428,7 +432,6 @@ class DrQV2Agent:
         self._bf16_ws = {}
         self._bf16_dirty = True
         self._prefetch, self._stage = None, {}
-        self.prefetch = True        # overlap the next host batch's H2D copy with the current update
 
     def __getstate__(self):
         st = dict(self.__dict__)

@@ -404,6 +404,35 @@ def test_update_skip_rule_and_metrics_contract(dev):
     assert agent.training
 
 
+def test_prefetch_is_transparent(dev):
+    """prefetch=True pulls host batches one update ahead (H2D overlapped with the running update) and
+    changes nothing else: same parameters bit for bit after the same batches and draws."""
+    A, Fd, H, B = 6, 50, 64, 4
+    params = O.synthetic_params(9, A, Fd, H, seed=7)
+    batches = [O.synthetic_batch(B, A, seed=20 + i) for i in range(4)]
+    agents = []
+    for pf in (False, True):
+        agent = make_agent(A, Fd, H, 1e-4, params, use_tb=True)
+        agent.prefetch = pf
+        pulled = []
+
+        def it():
+            for b in batches:
+                pulled.append(1)
+                yield (b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])
+
+        ri = it()
+        for i, b in enumerate(batches[:3]):
+            agent.inject_draws(b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+            agent.update(ri, 2 * i)
+        assert len(pulled) == (4 if pf else 3)
+        agents.append(agent)
+    torch.cuda.synchronize()
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        for (n1, p1), (_, p2) in zip(getattr(agents[0], net).named_parameters(), getattr(agents[1], net).named_parameters()):
+            assert torch.equal(p1, p2), (net, n1)
+
+
 def test_act_modes(dev):
     A, Fd, H = 12, 50, 128
     params = O.synthetic_params(9, A, Fd, H, seed=8)
