@@ -36,6 +36,7 @@ struct GemmTcArgs {
     int M, N, K;
     int batch_inner; long long bs[11];               // inner / outer batch strides: a, b, c, bias, mask; [10] split-K plane stride
     int splitk, k_chunk, nz;                         // nz = batch entries x split-K chunks
+    int grid3d;                                      // 1: grid = (n tiles, m tiles, nz), one tile per CTA; 0: persistent 1-D grid
     int accumulate;
     float* Cf; __nv_bfloat16* Cb; long long ldc;     // ldc: fp32 row stride, units of a TB output, WB block stride
     int n_store;                                     // TB outputs: feature columns to write (>= N, zero filled)
@@ -76,10 +77,16 @@ struct TileInfo {
 template <int BN>
 __device__ __forceinline__ TileInfo tile_info(const GemmTcArgs& g, int t, int nt, int mt) {
     TileInfo ti;
-    // (integer divisions are ~20 cold instructions each on the way to the first copy: skip the trivial ones)
-    int in = t, im = 0, z = 0;
-    if (nt > 1) { const int rest = t / nt; in = t - rest * nt; t = rest; } else { in = 0; }
-    if (mt > 1) { z = t / mt; im = t - z * mt; } else { z = t; }
+    // Integer divisions are ~20 cold instructions each on the way to the first copy.  When the launch has no more
+    // tiles than SMs the grid is 3-D and the tile is the block index; only the persistent 1-D grid decodes.
+    int in, im, z;
+    if (g.grid3d) {
+        in = blockIdx.x; im = blockIdx.y; z = blockIdx.z;
+    } else {
+        in = t; im = 0; z = 0;
+        if (nt > 1) { const int rest = t / nt; in = t - rest * nt; t = rest; } else { in = 0; }
+        if (mt > 1) { z = t / mt; im = t - z * mt; } else { z = t; }
+    }
     ti.m0 = im * GT_BM; ti.n0 = in * BN;
     int zs = 0, zb = z;                                  // split-K chunk, batch entry
     ti.k_begin = 0; ti.k_end = g.K;
@@ -119,21 +126,30 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     pdl_trigger();
     if (tid == 0) GT_STAMP(0);
     const int nt = (g.N + BN - 1) / BN, mt = (g.M + GT_BM - 1) / GT_BM;
-    const int total_tiles = nt * mt * g.nz;
-    if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1 + Cfg::B_COPIES); mbar_init(empty + i, 1); }
-        for (int i = 0; i < ACC; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
-        fence_barrier_init();
+    const int total_tiles = g.grid3d ? 1 : nt * mt * g.nz;
+    const int t_first = g.grid3d ? 0 : blockIdx.x, t_step = g.grid3d ? 1 : gridDim.x;
+    // Warp 0 (the copy producer) initialises the barriers and starts copying at once; the other warps meet it
+    // on named barrier 2 (warp 0 only arrives), so the TMEM allocation and the block-wide rendezvous are off
+    // the path to the first operand bytes.
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1 + Cfg::B_COPIES); mbar_init(empty + i, 1); }
+            for (int i = 0; i < ACC; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, 192;" ::: "memory");
+    } else {
+        if (warp == 1) {
+            tmem_alloc(tmem_slot, ACC * BN);
+            tmem_relinquish();
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 2, 192;" ::: "memory");
+        tc_fence_after();
     }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, ACC * BN);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
     pdl_wait();                 // everything above is CTA-local; global memory is first touched below
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = warp == 0 ? 0u : *tmem_slot;
     if (tid == 0) GT_STAMP(1);
 
     if (warp == 0) {
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         if (lane < 1 + Cfg::B_COPIES) {
             int stage = 0; uint32_t phase = 0;
 #pragma unroll 1
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = t_first; t < total_tiles; t += t_step) {
                 const TileInfo ti = tile_info<BN>(g, t, nt, mt);
                 const int m0 = ti.m0, n0 = ti.n0, k_begin = ti.k_begin, k_end = ti.k_end;
                 const int nk = (k_end - k_begin + BK - 1) / BK;
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         constexpr uint32_t idesc = make_idesc_bf16(GT_BM, BN / Cfg::B_COPIES, MODE == MODE_MNMN, MODE != MODE_KK);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = t_first; t < total_tiles; t += t_step) {
             const TileInfo ti = tile_info<BN>(g, t, nt, mt);
             const int nk = (ti.k_end - ti.k_begin + BK - 1) / BK;
             mbar_wait(tempty + acc, acc_phase ^ 1);
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         float* xp = xpose_s + q * Cfg::XP_FLOATS;
         int acc = 0; uint32_t acc_phase = 0; int it = 0;
 #pragma unroll 1
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (int t = t_first; t < total_tiles; t += t_step, ++it) {
             const TileInfo ti = tile_info<BN>(g, t, nt, mt);
             const int m0 = ti.m0, n0 = ti.n0;
             const long long off_c = ti.off_c;
@@ -393,9 +409,11 @@ static int launch_gemm_tc(GemmTcArgs& g, int batch, cudaStream_t s) {
     using Cfg = GemmCfg<MODE, BN, EPI>;
     if (int rc = ensure_smem((const void*)gemm_tc_kernel<MODE, BN, EPI>, Cfg::SMEM, "gemm_bf16")) return rc;
     g.nz = g.splitk * batch;
-    const int tiles = ((g.N + BN - 1) / BN) * ((g.M + GT_BM - 1) / GT_BM) * g.nz;
+    const int nt = (g.N + BN - 1) / BN, mt = (g.M + GT_BM - 1) / GT_BM;
+    const int tiles = nt * mt * g.nz;
     const int sms = drq_device_sm_count();
-    launch_k(gemm_tc_kernel<MODE, BN, EPI>, dim3(tiles < sms ? tiles : sms), GT_THREADS, Cfg::SMEM, s, g);
+    g.grid3d = tiles <= sms ? 1 : 0;
+    launch_k(gemm_tc_kernel<MODE, BN, EPI>, g.grid3d ? dim3(nt, mt, g.nz) : dim3(sms), GT_THREADS, Cfg::SMEM, s, g);
     return check_launch("gemm_tc_kernel");
 }
 
