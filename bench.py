@@ -272,6 +272,36 @@ def run_ours(args, rank, world):
                 "all_kernels_ms": {k: v[0] * 1e3 for k, v in kt.items()},
                 "whole_update": {"flop": flops, "achieved_per_gpu": flops * value / world / 1e12,
                                  "frac_of_sustained": flops * value / world / 1e12 / tf_sust}}
+        # ---- HBM-bound kernels of the update, timed alone the same way (algorithmic bytes per launch)
+        ar = agent._arena
+        F32 = 4
+        off, n = ar.seg["actor"][0], ar.seg["actor"][2]
+        coff, cn = ar.seg["critic"][0], ar.seg["critic"][2]
+        eoff, en = ar.seg["encoder"][0], ar.seg["encoder"][2] + ar.seg["critic"][2]
+        sc = agent._scal_dev.data_ptr()
+
+        def adam_actor_ema():
+            _lib.call("drq_adam_ema_step", ar.params.data_ptr() + F32 * off, ar.grads.data_ptr() + F32 * off,
+                      ar.exp_avg.data_ptr() + F32 * off, ar.exp_avg_sq.data_ptr() + F32 * off, n, sc,
+                      ar.params.data_ptr() + F32 * coff, ar.target.data_ptr(), cn, 0.01, 0.99, s)
+
+        def adam_enc_critic():
+            _lib.call("drq_adam_step", ar.params.data_ptr() + F32 * eoff, ar.grads.data_ptr() + F32 * eoff,
+                      ar.exp_avg.data_ptr() + F32 * eoff, ar.exp_avg_sq.data_ptr() + F32 * eoff, en, sc, s)
+
+        saved = [t.clone() for t in (ar.params, ar.exp_avg, ar.exp_avg_sq, ar.target)]
+        t_adam = time_kernel(adam_actor_ema) + time_kernel(adam_enc_critic)
+        for t, sv in zip((ar.params, ar.exp_avg, ar.exp_avg_sq, ar.target), saved):
+            t.copy_(sv)                            # the timing launches stepped the optimiser: restore
+        adam_bytes = 28 * (n + en) + 12 * cn       # p,g,m,v read + p,m,v written; EMA: p, tp read + tp written
+        t_gather = time_kernel(lambda: it.next_into(ws.obs[:B], ws.action, ws.reward, ws.discount, ws.obs[B:]))
+        gather_bytes = 2 * 2 * B * 9 * 84 * 84     # u8 stacks read from the ring + written to the batch
+        # (timed back to back, so the 126 MB L2 holds part of the working set: fractions above 1 are L2 hits)
+        roof["hbm_kernels"] = {
+            "adam_ema_kernel(both optimiser phases)": {"bytes": adam_bytes, "ms": t_adam * 1e3, "achieved_gbs": adam_bytes / t_adam / 1e9,
+                                                       "peak_gbs": hbm, "frac": adam_bytes / t_adam / 1e9 / hbm},
+            "ring_sample+ring_gather_kernel": {"bytes": gather_bytes, "ms": t_gather * 1e3, "achieved_gbs": gather_bytes / t_gather / 1e9,
+                                               "peak_gbs": hbm, "frac": gather_bytes / t_gather / 1e9 / hbm}}
         cpu = cpu_baseline(args, steps=2)
         out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
