@@ -167,7 +167,8 @@ def run_ours(args, rank, world):
     if world > 1:
         torch.distributed.barrier()
     sampler = ClockSampler(dev.index)
-    sampler.start()
+    if rank == 0:                     # one nvidia-smi poller per job: NVML queries perturb the GPUs they touch, and in
+        sampler.start()               # data-parallel mode a stall on any rank stalls every rank twice per update
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
