@@ -468,6 +468,55 @@ class DrQV2Agent:
             self._bf16.repack_all()
         self._bf16_dirty = False
 
+    # ------------------------------------------------------------------ snapshot interop (train.py:192-204)
+    _NETS = ("encoder", "actor", "critic")
+
+    def load_reference_agent(self, ref):
+        """Take over the state of a reference ``drqv2.DrQV2Agent`` (e.g. ``torch.load(snapshot)['agent']``,
+        train.py:199-204): the four networks' parameters and the three Adam optimisers' moments and step."""
+        with torch.no_grad():
+            for net in self._NETS + ("critic_target",):
+                getattr(self, net).load_state_dict(getattr(ref, net).state_dict())
+            a, step = self._arena, 0
+            for net in self._NETS:
+                opt = getattr(ref, f"{net}_opt")
+                for (pname, _), rp in zip(getattr(self, net).named_parameters(), getattr(ref, net).parameters()):
+                    st = opt.state.get(rp, {})
+                    off = a.offsets[net][pname]
+                    n = rp.numel()
+                    if "exp_avg" in st:
+                        a.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                        a.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                        step = max(step, int(st["step"]))
+                    else:
+                        a.exp_avg[off:off + n].zero_()
+                        a.exp_avg_sq[off:off + n].zero_()
+            self._opt_step = step
+        self._bf16_dirty = True
+        return self
+
+    def export_reference_state(self):
+        """State for a reference agent: ``{net: state_dict}`` for the four networks and ``{net}_opt``
+        entries in ``torch.optim.Adam.state_dict()`` form (parameter ids in ``parameters()`` order), so that
+        ``ref.encoder.load_state_dict(s['encoder']); ref.encoder_opt.load_state_dict(s['encoder_opt'])``
+        continues training in the reference."""
+        out = {net: {k: v.detach().clone() for k, v in getattr(self, net).state_dict().items()}
+               for net in self._NETS + ("critic_target",)}
+        a = self._arena
+        for net in self._NETS:
+            state = {}
+            for i, (pname, p) in enumerate(getattr(self, net).named_parameters()):
+                off, n = a.offsets[net][pname], p.numel()
+                if self._opt_step > 0:
+                    state[i] = dict(step=torch.tensor(float(self._opt_step)),
+                                    exp_avg=a.exp_avg[off:off + n].view(p.shape).clone(),
+                                    exp_avg_sq=a.exp_avg_sq[off:off + n].view(p.shape).clone())
+            group = dict(lr=self.lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False,
+                         foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
+                         params=list(range(len(state) if state else len(list(getattr(self, net).parameters())))))
+            out[f"{net}_opt"] = dict(state=state, param_groups=[group])
+        return out
+
     def train(self, training=True):
         self.training = training
         self.encoder.train(training)

@@ -18,6 +18,8 @@ quarter), new episodes are visible immediately, eviction is FIFO by whole episod
 """
 from __future__ import annotations
 
+import datetime
+import io
 import pathlib
 from collections import defaultdict
 
@@ -38,6 +40,57 @@ def _stream():
 def episode_len(episode):
     # rows minus the dummy first transition (replay_buffer.py:17-19)
     return next(iter(episode.values())).shape[0] - 1
+
+
+# ----------------------------------------------------------------------------- on-disk episode format
+# The reference keeps every episode as `{timestamp}_{index}_{length}.npz` (np.savez_compressed of the spec
+# arrays, observations as full frame stacks; replay_buffer.py:22-34,71-78).  The ring stores single frames;
+# these helpers convert both ways so that an existing reference buffer directory can be loaded and a
+# `save_snapshot` run leaves the same files behind.
+def save_episode(episode, fn):
+    """np.savez_compressed of the episode dict, byte-compatible with replay_buffer.py:22-27."""
+    with io.BytesIO() as bs:
+        np.savez_compressed(bs, **episode)
+        bs.seek(0)
+        with pathlib.Path(fn).open("wb") as f:
+            f.write(bs.read())
+
+
+def load_episode(fn):
+    """replay_buffer.py:30-34."""
+    with pathlib.Path(fn).open("rb") as f:
+        episode = np.load(f)
+        return {k: episode[k] for k in episode.keys()}
+
+
+def frames_from_stacks(obs, stack):
+    """Stacked observations u8 [rows, stack*C, H, W] (dmc.py:86-109: row t = frames max(t-stack+1..t, 0)) ->
+    the frame rendered at each row, u8 [rows, C, H, W].  Raises if obs is not such a stack."""
+    rows, SC = obs.shape[0], obs.shape[1]
+    if SC % stack:
+        raise ValueError("observation channels must be a multiple of frame_stack")
+    C = SC // stack
+    newest = obs[:, (stack - 1) * C:]
+    for j in range(stack - 1):
+        lag = stack - 1 - j
+        want = newest[np.maximum(np.arange(rows) - lag, 0)]
+        if not np.array_equal(obs[:, j * C:(j + 1) * C], want):
+            raise ValueError("observations are not a frame stack of consecutive frames; "
+                             "construct ReplayBufferStorage(..., frame_stack=1) to store them whole")
+    return np.ascontiguousarray(newest)
+
+
+def stacks_from_frames(frames, stack):
+    """Inverse of frames_from_stacks: u8 [rows, C, H, W] -> u8 [rows, stack*C, H, W]."""
+    rows = frames.shape[0]
+    t = np.arange(rows)
+    return np.concatenate([frames[np.maximum(t - (stack - 1 - j), 0)] for j in range(stack)], axis=1)
+
+
+def episode_files(replay_dir):
+    """Episode files of a reference buffer directory in the order the reference's loader keeps them
+    (sorted by name = by timestamp, replay_buffer.py:112)."""
+    return sorted(pathlib.Path(replay_dir).glob("*.npz"))
 
 
 class GpuRing:
@@ -114,8 +167,34 @@ class ReplayBufferStorage:
         self._num_episodes = 0
         self._num_transitions = 0
         self._key = str(self._replay_dir)
-        _RINGS.setdefault(self._key, dict(ring=None, capacity=None, storage=self))
-        _RINGS[self._key]["storage"] = self
+        entry = _RINGS.setdefault(self._key, dict(ring=None, capacity=None, storage=self))
+        entry["storage"] = self
+        entry.setdefault("save_snapshot", False)
+        self._pending = []
+        self._preload()
+
+    def _preload(self):
+        """Episodes a previous (reference or drqv2_b200, save_snapshot) run left in replay_dir
+        (replay_buffer.py:63-69): counted now, pushed into the ring as soon as it exists."""
+        if not self._replay_dir.is_dir():
+            return
+        for fn in episode_files(self._replay_dir):
+            try:
+                _, _, eps_len = fn.stem.split("_")
+                self._num_transitions += int(eps_len)
+            except ValueError:
+                continue
+            self._num_episodes += 1
+            self._pending.append(fn)
+
+    def _ingest_pending(self, ring):
+        names = [s.name for s in self._data_specs]
+        pending, self._pending = self._pending, []
+        for fn in pending:
+            ep = load_episode(fn)
+            ring.add_episode(frames_from_stacks(ep[names[0]], ring.stack) if ring.stack > 1 else ep[names[0]],
+                             ep[names[1]].astype(np.float32), ep[names[2]].astype(np.float32),
+                             ep[names[3]].astype(np.float32))
 
     def __len__(self):
         return self._num_transitions
@@ -140,27 +219,38 @@ class ReplayBufferStorage:
             stack = self._frame_stack
             assert obs_c % stack == 0, "observation channels must be a multiple of frame_stack"
             entry["ring"] = GpuRing(cap, obs_c // stack, stack, action_dim, self._device)
+            self._ingest_pending(entry["ring"])
         return entry["ring"]
+
+    def load_existing(self):
+        """Create the ring from the episodes found in replay_dir (resume without waiting for a new episode).
+        Returns the number of episodes loaded."""
+        if not self._pending:
+            return 0
+        n = len(self._pending)
+        ep = load_episode(self._pending[0])
+        names = [s.name for s in self._data_specs]
+        self._ring(ep[names[0]].shape[1], ep[names[1]].shape[1])
+        return n
 
     def _store_episode(self, episode):
         names = [s.name for s in self._data_specs]
         obs_key, act_key, rew_key, disc_key = names[0], names[1], names[2], names[3]
         obs = episode[obs_key]
         ring = self._ring(obs.shape[1], episode[act_key].shape[1])
-        S, C = ring.stack, ring.frame_c
-        newest = obs[:, (S - 1) * C:]                     # the frame rendered at each row
         # the stack must be the de-duplicated history the ring assumes (dmc.py:86-109)
-        for j in range(S - 1):
-            lag = S - 1 - j
-            want = newest[np.maximum(np.arange(obs.shape[0]) - lag, 0)]
-            if not np.array_equal(obs[:, j * C:(j + 1) * C], want):
-                raise ValueError("observations are not a frame stack of consecutive frames; "
-                                 "construct ReplayBufferStorage(..., frame_stack=1) to store them whole")
+        newest = frames_from_stacks(obs, ring.stack) if ring.stack > 1 else np.ascontiguousarray(obs)
+        eps_idx = self._num_episodes
         eps_len = episode_len(episode)
         self._num_episodes += 1
         self._num_transitions += eps_len
-        ring.add_episode(np.ascontiguousarray(newest), episode[act_key].astype(np.float32),
+        ring.add_episode(newest, episode[act_key].astype(np.float32),
                          episode[rew_key].astype(np.float32), episode[disc_key].astype(np.float32))
+        if _RINGS[self._key].get("save_snapshot"):
+            # keep the reference's files (replay_buffer.py:71-78; its loader deletes them unless save_snapshot)
+            self._replay_dir.mkdir(parents=True, exist_ok=True)
+            ts = datetime.datetime.now().strftime("%Y%m%dT%H%M%S")
+            save_episode(episode, self._replay_dir / f"{ts}_{eps_idx}_{eps_len}.npz")
 
 
 class RingIterator:
@@ -240,7 +330,10 @@ class RingLoader:
 
 def make_replay_loader(replay_dir, max_size, batch_size, num_workers, save_snapshot, nstep, discount):
     """Same positional signature as the reference (replay_buffer.py:173-190; train.py:68-71).
-    ``num_workers`` and ``save_snapshot`` have no meaning for a device-resident ring and are
-    accepted for compatibility."""
-    del num_workers, save_snapshot
-    return RingLoader(replay_dir, max_size, batch_size, nstep, discount)
+    ``num_workers`` has no meaning for a device-resident ring.  ``save_snapshot``: every stored episode is
+    also written to ``replay_dir`` in the reference's npz format (the reference's loader deletes episode
+    files once loaded unless this is set, replay_buffer.py:116-117)."""
+    del num_workers
+    loader = RingLoader(replay_dir, max_size, batch_size, nstep, discount)
+    _RINGS[loader.key]["save_snapshot"] = bool(save_snapshot)
+    return loader

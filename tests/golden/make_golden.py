@@ -149,6 +149,10 @@ def make_replay_golden(replay_buffer, dmc, dm_env):
         assert len(storage) == sum(lens)
         files = sorted((d / "buffer").glob("*.npz"), key=lambda f: int(f.stem.split("_")[1]))
         episodes = [replay_buffer.load_episode(f) for f in files]
+        # one episode file exactly as the reference's save_episode wrote it (replay_buffer.py:22-27): the fixture of
+        # the npz interoperability tests ({ts}_{idx}_{len}.npz; the timestamp is dropped from the fixture's name)
+        import shutil
+        shutil.copyfile(files[1], HERE / "ref_episode_1_5.npz")
         for nstep in (1, 3):
             rb = replay_buffer.ReplayBuffer(d / "buffer", 10 ** 6, 0, nstep, 0.99, fetch_every=10 ** 9,
                                             save_snapshot=True)

@@ -516,6 +516,99 @@ def test_ring_storage_loader_update_end_to_end(dev, tmp_path):
             bad.add(TS(observation=obs, action=a[t], reward=r[t], discount=d[t], _last=(t == 2)))
 
 
+def test_replay_snapshot_files_and_resume(dev, tmp_path):
+    """save_snapshot leaves the reference's episode files behind, and a new storage over the same directory
+    (or over a directory the reference itself wrote) rebuilds the same ring (replay_buffer.py:63-78)."""
+    import collections
+    import pathlib
+    from drqv2_b200 import replay_buffer as R
+    Spec = collections.namedtuple("Spec", "shape dtype name")
+    A = 6
+    specs = (Spec((9, 84, 84), np.uint8, "observation"), Spec((A,), np.float32, "action"),
+             Spec((1,), np.float32, "reward"), Spec((1,), np.float32, "discount"))
+
+    class TS(dict):
+        def last(self):
+            return self["_last"]
+
+    ref_ep = R.load_episode(pathlib.Path(__file__).parent / "golden" / "ref_episode_1_5.npz")
+    d1 = tmp_path / "buffer"
+    st = R.ReplayBufferStorage(specs, d1)
+    loader = R.make_replay_loader(d1, 1000, 4, 0, True, 3, 0.99)           # save_snapshot=True
+    for rep in range(2):
+        rows = ref_ep["observation"].shape[0]
+        for t in range(rows):
+            st.add(TS(observation=ref_ep["observation"][t], action=ref_ep["action"][t], reward=ref_ep["reward"][t],
+                      discount=ref_ep["discount"][t], _last=t == rows - 1))
+    files = R.episode_files(d1)
+    assert len(files) == 2 and all(f.stem.split("_")[1:] == [str(i), "5"] for i, f in enumerate(files))
+    back = R.load_episode(files[0])
+    assert all(np.array_equal(back[k], ref_ep[k]) for k in ref_ep)
+    ring1 = loader.ring()
+    # resume: a fresh registry entry over the same files
+    R._RINGS.pop(str(d1))
+    st2 = R.ReplayBufferStorage(specs, d1)
+    assert len(st2) == 10
+    R.make_replay_loader(d1, 1000, 4, 0, False, 3, 0.99)
+    assert st2.load_existing() == 2
+    ring2 = R._RINGS[str(d1)]["ring"]
+    torch.cuda.synchronize()
+    assert ring2.episodes == ring1.episodes
+    n = 2 * 6
+    assert torch.equal(ring2.frames[:n], ring1.frames[:n]) and torch.equal(ring2.action[:n], ring1.action[:n])
+    assert torch.equal(ring2.reward[:n], ring1.reward[:n]) and torch.equal(ring2.discount[:n], ring1.discount[:n])
+
+
+def test_reference_snapshot_interop(dev):
+    """a reference agent's state (what train.py:192-204 pickles) moves into this agent and back."""
+    import bench
+    from drqv2_b200 import DrQV2Agent
+    ref = bench._load_reference()
+    if ref is None:
+        pytest.skip("baseline/_ref (unmodified reference sources) not present")
+    A, Fd, H = 6, 50, 64
+    torch.manual_seed(3)
+    ragent = ref.DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False)
+    b = O.synthetic_batch(4, A, seed=2)
+    batch = tuple(b[k].cuda() for k in ("obs", "action", "reward", "discount", "next_obs"))
+    for i in range(2):                                         # two reference updates: Adam state, step = 2
+        ragent.update(iter([batch]), 2 * i)
+    mine = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False, seed=1)
+    mine.load_reference_agent(ragent)
+    assert mine._opt_step == 2
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        for (n1, p1), p2 in zip(getattr(mine, net).named_parameters(), getattr(ragent, net).parameters()):
+            assert torch.equal(p1, p2), (net, n1)
+    for net in ("encoder", "actor", "critic"):
+        opt = getattr(ragent, f"{net}_opt")
+        sd = getattr(mine, f"{net}_opt").state_dict()
+        ref_m = torch.cat([opt.state[p]["exp_avg"].reshape(-1) for p in getattr(ragent, net).parameters()])
+        assert torch.equal(sd["exp_avg"][:ref_m.numel()], ref_m)
+    # same deterministic action from both
+    obs = b["obs"][0].numpy()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False            # the reference's convs default to TF32 on GPU (SURVEY §8a R4)
+    try:
+        with torch.no_grad():
+            want = ragent.act(obs, 5000, True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    got = mine.act(obs, 5000, True)
+    assert np.abs(got - want).max() < 2e-5
+    # and back: a fresh reference agent continues from the exported state
+    r2 = ref.DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False)
+    st = mine.export_reference_state()
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        getattr(r2, net).load_state_dict(st[net])
+    for net in ("encoder", "actor", "critic"):
+        getattr(r2, f"{net}_opt").load_state_dict(st[f"{net}_opt"])
+        o1, o2 = getattr(ragent, f"{net}_opt"), getattr(r2, f"{net}_opt")
+        for p1, p2 in zip(getattr(ragent, net).parameters(), getattr(r2, net).parameters()):
+            assert torch.equal(o1.state[p1]["exp_avg_sq"], o2.state[p2]["exp_avg_sq"])
+            assert float(o2.state[p2]["step"]) == 2.0
+    r2.update(iter([batch]), 4)                                # and the reference trains on from it
+
+
 def test_agent_pickle_roundtrip(dev):
     """train.py:192-204 snapshots the whole agent with torch.save / torch.load."""
     A, Fd, H, B = 6, 50, 64, 4
