@@ -108,8 +108,16 @@ ln_tanh_bwd_row_kernel(const float* __restrict__ dh, long long ld_dh, const floa
         dxh[i] = 0.f; xh[i] = 0.f;
         if (f < F) {
             const float hv = h[(long long)row * ld_h + f];
-            float dhv = 0.f;                                   // dh = sum of the split-K / per-head partial planes
-            for (int pl = 0; pl < n_planes; ++pl) dhv += dh[pl * plane_stride + (long long)row * ld_dh + f];
+            // dh = sum of the split-K / per-head partial planes (loads of 8 planes in flight, fixed order)
+            float dhv = 0.f;
+            const float* dp = dh + (long long)row * ld_dh + f;
+            for (int p0 = 0; p0 < n_planes; p0 += 8) {
+                float t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = p0 + k < n_planes ? dp[(p0 + k) * plane_stride] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dhv += t[k];
+            }
             const float dy = dhv * (1.0f - hv * hv);
             dy_out[(long long)row * F + f] = dy;
             xh[i] = xhat[(long long)row * F + f];
@@ -220,7 +228,14 @@ __global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long 
     const int b = i / A, j = i - b * A;
     const float m = mu[i];
     float dav = 0.f;
-    for (int pl = 0; pl < n_planes; ++pl) dav += da[pl * plane_stride + (long long)b * ld_da + j];
+    const float* dp = da + (long long)b * ld_da + j;
+    for (int p0 = 0; p0 < n_planes; p0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = p0 + k < n_planes ? dp[(p0 + k) * plane_stride] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dav += t[k];
+    }
     const float g = dav * (1.0f - m * m);
     dmu_pre[i] = g;
     if (dmu_bf) dmu_bf[fb_index(j, b, rpad_mb)] = __float2bfloat16_rn(g);
