@@ -317,16 +317,14 @@ def critic_pass(agent, ws, bw):
     call("drq_scatter_fb", ws.action.data_ptr(), A, bw.x.ptr(0), bw.x.units, Fd, B, A, s)
     # ---- target Q on (next, next action) and online Q on (obs, action): 4 heads per launch
     twin_q_fwd(agent, bw, bw.x, 2, B)
+    # ---- TD target + critic loss (drqv2.py:185-189) and the backward through the scalar Q heads, one launch
     q = bw.q4.data_ptr()
-    call("drq_critic_loss", q, q + F32 * B, q + F32 * 2 * B, q + F32 * 3 * B, ws.reward.data_ptr(),
-         ws.discount.data_ptr(), ws.dq.data_ptr(), ws.dq.data_ptr() + F32 * B, ws.target_q.data_ptr(),
-         ws.metrics.data_ptr(), B, s)
-    # ---- backward through the online Q heads
     c1, c2, dc1, dc2 = bw.c1, bw.c2, bw.dc1, bw.dc2
     w0, w2, xC = st.q0, st.q2, bw.x
     U, HS = c1.units, c1.stride
-    call("drq_q_head_bwd_bf16", ws.dq.data_ptr(), c2.ptr(), U, HS, pc("Q1.4.weight"), dc2.ptr(),
-         gc("Q1.4.weight"), gc("Q1.4.bias"), B, H, 2, qs_f, s)
+    call("drq_q_head_bwd_loss_bf16", 1, q, q + F32 * 2 * B, ws.reward.data_ptr(), ws.discount.data_ptr(),
+         ws.target_q.data_ptr(), ws.metrics.data_ptr(), c2.ptr(), U, HS, pc("Q1.4.weight"), dc2.ptr(),
+         gc("Q1.4.weight"), gc("Q1.4.bias"), B, H, qs_f, s)
     gemm(dc2.ptr(), U, c1.ptr(), U, GEMM_MNMN, gc("Q1.2.weight"), H, H, H, B, TEPI_F32, batch=2,
          strides=_strides((HS, HS, qs_f, 0, 0)), bn=128)
     gemm(dc2.ptr(), U, w2.ptr(), w2.units, GEMM_KMN, dc1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=c1.ptr(), units_mask=U,
@@ -394,14 +392,13 @@ def actor_pass(agent, ws, bw):
                          ws.xA.data_ptr(), Fd + A, None, None, xA.ptr(), xA.units, 0)], B, Fd)
     twin_q_fwd(agent, bw, xA, 1, B)
     q = bw.q4.data_ptr()
-    call("drq_actor_loss", q, q + F32 * B, ws.dq.data_ptr(), ws.dq.data_ptr() + F32 * B,
-         ws.metrics.data_ptr() + F32 * 5, B, s)
     c1, c2, dc1, dc2 = bw.c1, bw.c2, bw.dc1, bw.dc2
     w0, w2 = st.q0, st.q2
     U, HS = c1.units, c1.stride
     qs_f = agent._q_strides()
-    call("drq_q_head_bwd_bf16", ws.dq.data_ptr(), c2.ptr(), U, HS, pc("Q1.4.weight"), dc2.ptr(), None, None,
-         B, H, 2, qs_f, s)
+    # actor loss -mean(min(Q1,Q2)) (drqv2.py:213-216) and the backward through the scalar Q heads, one launch
+    call("drq_q_head_bwd_loss_bf16", 2, q, None, None, None, None, ws.metrics.data_ptr() + F32 * 5, c2.ptr(), U, HS,
+         pc("Q1.4.weight"), dc2.ptr(), None, None, B, H, qs_f, s)
     gemm(dc2.ptr(), U, w2.ptr(), w2.units, GEMM_KMN, dc1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=c1.ptr(), units_mask=U,
          batch=2, strides=_strides((HS, w2.stride, HS, 0, HS)))
     PS = B * (Fd + A)

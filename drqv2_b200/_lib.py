@@ -60,6 +60,7 @@ SIGNATURES = {
     "drq_colsum_fb": [P, L, P, I, I, I, L, L, P],
     "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, I, L, P],
     "drq_q_head_bwd_bf16": [P, P, L, L, P, P, P, P, I, I, I, L, P],
+    "drq_q_head_bwd_loss_bf16": [I, P, P, P, P, P, P, P, L, L, P, P, P, P, I, I, L, P],
     "drq_critic_loss": [P, P, P, P, P, P, P, P, P, P, I, P],
     "drq_actor_loss": [P, P, P, P, P, I, P],
     "drq_copy2d_f32": [P, L, P, L, I, I, P],

@@ -378,27 +378,55 @@ q_head_fwd_kernel(const __nv_bfloat16* __restrict__ c2, long long rpad, long lon
     }
 }
 
-// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0) (FB bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
+// dc2[z][b][k] = dq[z][b] * w3[z][k] * (c2 > 0) (TB bf16); optionally dw3[z][k] = sum_b dq[z][b] c2[z][b][k]
 // and db3[z] = sum_b dq[z][b].  One block per 8-feature unit; fixed-order tree.
+// LOSS selects where dq comes from: 0 = given; 1 = the critic loss of drqv2.py:185-189 computed here from
+// (q, target q, reward, discount) - block (0,0) also writes the five metrics; 2 = the actor loss of
+// drqv2.py:213-216 (-mean(min(Q1,Q2))), block (0,0) writes actor_loss.  Heads = 2 for LOSS != 0.
+struct QLossArgs {
+    const float* q;            // [2][B] online Q1, Q2
+    const float* tq;           // [2][B] target Q1, Q2 (critic loss)
+    const float* reward; const float* discount;
+    float* target_q_out;       // nullable [B]
+    float* metrics;            // nullable
+};
+
+template <int LOSS>
+__device__ __forceinline__ float loss_dq(const QLossArgs& L, const float* dqz, int z, int b, int B) {
+    if (LOSS == 0) return dqz[b];
+    const float q1 = L.q[b], q2 = L.q[B + b];
+    if (LOSS == 1) {
+        const float tv = fminf(L.tq[b], L.tq[B + b]);                               // drqv2.py:185
+        const float tq = __fadd_rn(L.reward[b], __fmul_rn(L.discount[b], tv));      // drqv2.py:186
+        return (2.0f / (float)B) * ((z ? q2 : q1) - tq);                            // d/dq mean((q - tq)^2)
+    }
+    const float g = -1.0f / (float)B;                                               // d/dq -mean(min(q1, q2))
+    const float mine = z ? q2 : q1, other = z ? q1 : q2;
+    return mine < other ? g : (mine == other ? 0.5f * g : 0.f);
+}
+
+template <int LOSS>
 __global__ void __launch_bounds__(256)
-q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict__ c2, long long rpad,
+q_head_bwd_kernel(const float* __restrict__ dq, const QLossArgs L, const __nv_bfloat16* __restrict__ c2, long long rpad,
                   long long bs_c2, const float* __restrict__ w3, __nv_bfloat16* __restrict__ dc2,
                   float* __restrict__ dw3, float* __restrict__ db3, int B, long long w_stride) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[256][9];
     const int u = blockIdx.x, z = blockIdx.y;
-    const float* dqz = dq + (long long)z * B;
+    const float* dqz = LOSS == 0 ? dq + (long long)z * B : nullptr;
     const long long base = z * bs_c2;
     float w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = w3[z * w_stride + u * 8 + j];
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float dq_sum = 0.f;
     for (int b = threadIdx.x; b < B; b += 256) {
         const long long at = base + fb_index(u * 8, b, rpad);
         const uint4 v = *reinterpret_cast<const uint4*>(c2 + at);
         const uint32_t cw[4] = {v.x, v.y, v.z, v.w};
-        const float g = dqz[b];
+        const float g = loss_dq<LOSS>(L, dqz, z, b, B);
+        dq_sum += g;
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -422,11 +450,42 @@ q_head_bwd_kernel(const float* __restrict__ dq, const __nv_bfloat16* __restrict_
             __syncthreads();
         }
         if (threadIdx.x < 8) dw3[z * w_stride + u * 8 + threadIdx.x] = red[0][threadIdx.x];
+        __syncthreads();
     }
-    if (db3 && u == 0 && threadIdx.x == 0) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += dqz[b];
-        db3[z * w_stride] = s;
+    if (u != 0) return;
+    float* sh = &red[0][0];
+    if (db3) {
+        const float t = block_sum_256(dq_sum, sh);
+        if (threadIdx.x == 0) db3[z * w_stride] = t;
+    }
+    if (LOSS != 0 && z == 0 && (L.metrics || L.target_q_out)) {
+        // the scalars of drqv2.py:189-195,216 (one block, fixed-order sums)
+        float s_r = 0.f, s_t = 0.f, s_1 = 0.f, s_2 = 0.f, s_l1 = 0.f, s_l2 = 0.f, s_min = 0.f;
+        for (int b = threadIdx.x; b < B; b += 256) {
+            const float q1 = L.q[b], q2 = L.q[B + b];
+            if (LOSS == 1) {
+                const float tv = fminf(L.tq[b], L.tq[B + b]);
+                const float tq = __fadd_rn(L.reward[b], __fmul_rn(L.discount[b], tv));
+                const float e1 = q1 - tq, e2 = q2 - tq;
+                if (L.target_q_out) L.target_q_out[b] = tq;
+                s_r += L.reward[b]; s_t += tq; s_1 += q1; s_2 += q2; s_l1 += e1 * e1; s_l2 += e2 * e2;
+            } else {
+                s_min += fminf(q1, q2);
+            }
+        }
+        const float inv = 1.0f / (float)B;
+        if (LOSS == 1) {
+            const float r = block_sum_256(s_r, sh), t = block_sum_256(s_t, sh);
+            const float a = block_sum_256(s_1, sh), c = block_sum_256(s_2, sh);
+            const float l1 = block_sum_256(s_l1, sh), l2 = block_sum_256(s_l2, sh);
+            if (L.metrics && threadIdx.x == 0) {
+                L.metrics[0] = r * inv; L.metrics[1] = t * inv; L.metrics[2] = a * inv; L.metrics[3] = c * inv;
+                L.metrics[4] = l1 * inv + l2 * inv;
+            }
+        } else {
+            const float t = block_sum_256(s_min, sh);
+            if (L.metrics && threadIdx.x == 0) L.metrics[0] = -(t * inv);
+        }
     }
 }
 
@@ -543,9 +602,28 @@ int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64
                         uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
                         void* stream) {
     DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_bwd: bad args");
-    launch_k(q_head_bwd_kernel, dim3(H / 8, heads), 256, 0, as_stream(stream), 
-        dq, reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3,
-        db3, B, w_stride);
+    launch_k(q_head_bwd_kernel<0>, dim3(H / 8, heads), 256, 0, as_stream(stream), dq, QLossArgs{},
+             reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3, db3, B,
+             w_stride);
+    return check_launch("q_head_bwd_kernel");
+}
+
+int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const float* reward, const float* discount,
+                             float* target_q_out, float* metrics, const uint16_t* c2, int64_t rpad, int64_t bs_c2,
+                             const float* w3, uint16_t* dc2, float* dw3, float* db3, int B, int H, int64_t w_stride,
+                             void* stream) {
+    DRQ_REQUIRE(loss == 1 || loss == 2, "q_head_bwd_loss: loss must be 1 (critic) or 2 (actor)");
+    DRQ_REQUIRE(q && c2 && w3 && dc2 && B > 0 && H > 0 && H % 8 == 0, "q_head_bwd_loss: bad args");
+    DRQ_REQUIRE(loss == 2 || (tq && reward && discount), "q_head_bwd_loss: critic loss needs tq, reward, discount");
+    const QLossArgs L{q, tq, reward, discount, target_q_out, metrics};
+    const auto c2p = reinterpret_cast<const __nv_bfloat16*>(c2);
+    const auto dp = reinterpret_cast<__nv_bfloat16*>(dc2);
+    if (loss == 1)
+        launch_k(q_head_bwd_kernel<1>, dim3(H / 8, 2), 256, 0, as_stream(stream), nullptr, L, c2p, rpad, bs_c2, w3, dp, dw3, db3,
+                 B, w_stride);
+    else
+        launch_k(q_head_bwd_kernel<2>, dim3(H / 8, 2), 256, 0, as_stream(stream), nullptr, L, c2p, rpad, bs_c2, w3, dp, dw3, db3,
+                 B, w_stride);
     return check_launch("q_head_bwd_kernel");
 }
 

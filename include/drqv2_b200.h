@@ -387,6 +387,13 @@ int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const f
 int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
                         uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
                         void* stream);
+/* the same with the loss gradient computed in place (one launch less per pass): loss = 1: critic loss of
+ * drqv2.py:185-189 from q[2][B], tq[2][B], reward, discount (metrics[0..4] and target_q_out as drq_critic_loss);
+ * loss = 2: actor loss of drqv2.py:213-216 from q[2][B] (metrics[0] = actor_loss).  Two heads. */
+int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const float* reward, const float* discount,
+                             float* target_q_out, float* metrics, const uint16_t* c2, int64_t rpad, int64_t bs_c2,
+                             const float* w3, uint16_t* dc2, float* dw3, float* db3, int B, int H, int64_t w_stride,
+                             void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 
