@@ -92,7 +92,8 @@ class LnJob(C.Structure):
     _fields_ = [("partial", C.c_void_p), ("ld_partial", C.c_int64), ("split_stride", C.c_int64), ("S", C.c_int32),
                 ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("h_out", C.c_void_p), ("ld_h", C.c_int64), ("xhat", C.c_void_p), ("rstd", C.c_void_p),
-                ("h_bf16", C.c_void_p), ("units_bf16", C.c_int64), ("row0_bf16", C.c_int64)]
+                ("h_bf16", C.c_void_p), ("units_bf16", C.c_int64), ("row0_bf16", C.c_int64),
+                ("tail", C.c_void_p), ("ld_tail", C.c_int64), ("n_tail", C.c_int32)]
 
 
 class PackJob(C.Structure):
@@ -110,7 +111,7 @@ def pack_multi(jobs):
 
 class ColsumJob(C.Structure):
     _fields_ = [("X", C.c_void_p), ("ld", C.c_int64), ("out", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
-                ("tb", C.c_int32), ("reserved", C.c_int32)]
+                ("tb", C.c_int32), ("reserved", C.c_int32), ("Y", C.c_void_p)]
 
 
 def colsum_multi(jobs):
@@ -299,13 +300,14 @@ def critic_pass(agent, ws, bw):
          TEPI_F32, batch=2, batch_inner=1, splitk=S, bn=128,
          strides=_strides(outer=(feat.off(row=RB), -st.trunk.off(row=FP), B * NT, 0, 0), split=2 * B * NT))
     pz = lambda z, col: part.data_ptr() + F32 * (z * B * NT + col)
-    job = lambda p, net_p, names, h_out, ld_h, xhat, rstd, tb, row0: LnJob(
+    job = lambda p, net_p, names, h_out, ld_h, xhat, rstd, tb, row0, tail=None: LnJob(
         p, NT, 2 * B * NT, S, net_p(names[0]), net_p(names[1]), net_p(names[2]), h_out, ld_h, xhat, rstd,
-        tb.buf.data_ptr(), tb.units, row0)
+        tb.buf.data_ptr(), tb.units, row0, tail, A, A if tail else 0)
     tn = ("trunk.0.bias", "trunk.1.weight", "trunk.1.bias")
     ln_tanh_multi([
         job(pz(0, 0), pa, tn, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(), bw.hA, 0),       # actor(obs)
-        job(pz(0, FP), pc, tn, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(), ws.rstdC.data_ptr(), bw.x, 0),  # critic(obs)
+        job(pz(0, FP), pc, tn, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(), ws.rstdC.data_ptr(), bw.x, 0,
+            ws.action.data_ptr()),                                                                         # critic(obs) ++ action
         job(pz(1, 0), tp, tn, ws.xT.data_ptr(), Fd + A, None, None, bw.x, bw.x.rpad),                          # target(next) -> x[1]
         job(pz(1, FP), pa, tn, bw.hA_next_f32.data_ptr(), Fd, None, None, bw.hA, RB),                          # actor(next)
     ], B, Fd)
@@ -314,7 +316,6 @@ def critic_pass(agent, ws, bw):
     # next action: clipped sample (drqv2.py:183) -> xT's action columns
     call("drq_actor_sample", bw.mu_pre.data_ptr() + F32 * RB * A, ws.eps_c.data_ptr(), std_ptr, float(agent.stddev_clip),
          ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, bw.x.ptr(1), bw.x.units, Fd, B, A, s)
-    call("drq_scatter_fb", ws.action.data_ptr(), A, bw.x.ptr(0), bw.x.units, Fd, B, A, s)
     # ---- target Q on (next, next action) and online Q on (obs, action): 4 heads per launch
     twin_q_fwd(agent, bw, bw.x, 2, B)
     # ---- TD target + critic loss (drqv2.py:185-189) and the backward through the scalar Q heads, one launch
@@ -337,14 +338,17 @@ def critic_pass(agent, ws, bw):
          splitk=bw.SX, strides=_strides((HS, w0.stride, PS, 0, 0), split=2 * PS))
     # ---- trunk backward
     call("drq_ln_tanh_bwd", bw.dxf.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
-         ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), gc("trunk.1.weight"), gc("trunk.1.bias"),
+         ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), None, None,
          bw.dz.ptr(), bw.dz.units, B, Fd, 2 * bw.SX, PS, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, gc("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
     # all bias gradients of the critic backward in one launch
     colsum_multi([ColsumJob(dc2.ptr(0), U, gc("Q1.2.bias"), B, H, 1, 0), ColsumJob(dc2.ptr(1), U, gc("Q2.2.bias"), B, H, 1, 0),
                   ColsumJob(dc1.ptr(0), U, gc("Q1.0.bias"), B, H, 1, 0), ColsumJob(dc1.ptr(1), U, gc("Q2.0.bias"), B, H, 1, 0),
-                  ColsumJob(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 0, 0)])
+                  ColsumJob(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 0, 0),
+                  # LayerNorm affine: dgamma = sum_b dy * xhat, dbeta = sum_b dy (dy staged behind dz by drq_ln_tanh_bwd)
+                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.weight"), B, Fd, 0, 0, ws.xhatC.data_ptr()),
+                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.bias"), B, Fd, 0, 0)])
     # ---- encoder backward
     d = [t.data_ptr() for t in bw.dpre]
     acts = [t.data_ptr() for t in bw.acts]
@@ -417,13 +421,15 @@ def actor_pass(agent, ws, bw):
     gemm(dp1.ptr(), U, hA.ptr(), hA.units, GEMM_MNMN, ga("policy.0.weight"), Fd, H, Fd, B, TEPI_F32)
     gemm(dp1.ptr(), U, a0.ptr(), a0.units, GEMM_KMN, ws.dhA.data_ptr(), Fd, B, Fd, H, TEPI_F32)
     call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
-         pa("trunk.1.weight"), ws.dz.data_ptr(), ga("trunk.1.weight"), ga("trunk.1.bias"), bw.dz.ptr(), bw.dz.units,
+         pa("trunk.1.weight"), ws.dz.data_ptr(), None, None, bw.dz.ptr(), bw.dz.units,
          B, Fd, 1, 0, s)
     gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, ga("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
          TEPI_TRUNK_WGRAD, bn=128)
     colsum_multi([ColsumJob(ws.dmu_pre.data_ptr(), A, ga("policy.4.bias"), B, A, 0, 0),
                   ColsumJob(dp2.ptr(), U, ga("policy.2.bias"), B, H, 1, 0), ColsumJob(dp1.ptr(), U, ga("policy.0.bias"), B, H, 1, 0),
-                  ColsumJob(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 0, 0)])
+                  ColsumJob(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 0, 0),
+                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.weight"), B, Fd, 0, 0, ws.xhatA.data_ptr()),
+                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.bias"), B, Fd, 0, 0)])
     agent._sync_grads("actor")
     a = agent._arena
     off, n = a.seg["actor"][0], a.seg["actor"][2]

@@ -85,6 +85,8 @@ ln_tanh_fwd_kernel(const LnJobs jobs, int B, int F, float eps) {
         }
     }
     if (jb.rstd && lane == 0) jb.rstd[row] = rstd;
+    if (jb.tail && h_bf && lane < jb.n_tail)
+        h_bf[fb_index(F + lane, jb.row0_bf16 + row, jb.units_bf16)] = __float2bfloat16_rn(jb.tail[(long long)row * jb.ld_tail + lane]);
 }
 
 // per row: dy = dh*(1-h^2); dxhat = dy*gamma; dz = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)).
@@ -503,6 +505,7 @@ int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float
         js.j[i] = jobs[i];
         DRQ_REQUIRE(jobs[i].partial && jobs[i].bias && jobs[i].gamma && jobs[i].beta && jobs[i].h_out && jobs[i].S >= 1,
                     "ln_tanh_fwd: null pointer in job %d", i);
+        DRQ_REQUIRE(jobs[i].n_tail >= 0 && jobs[i].n_tail <= 32, "ln_tanh_fwd: tail of job %d wider than 32", i);
     }
     if (B == 0) return DRQ_OK;
     const dim3 grid(B, njobs);
@@ -519,7 +522,7 @@ int drq_ln_tanh_fwd(const float* partial, int S, int64_t split_stride, const flo
     drq_ln_job j{};
     j.partial = partial; j.ld_partial = F; j.split_stride = split_stride; j.S = S;
     j.bias = bias; j.gamma = gamma; j.beta = beta; j.h_out = h_out; j.ld_h = ld_h; j.xhat = xhat; j.rstd = rstd;
-    j.h_bf16 = h_bf16; j.units_bf16 = rpad_hb; j.row0_bf16 = 0;
+    j.h_bf16 = h_bf16; j.units_bf16 = rpad_hb; j.row0_bf16 = 0; j.tail = nullptr; j.ld_tail = 0; j.n_tail = 0;
     return drq_ln_tanh_fwd_multi(&j, 1, B, F, eps, stream);
 }
 
@@ -527,7 +530,7 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
                     const float* rstd, const float* gamma, float* dz, float* dgamma, float* dbeta,
                     uint16_t* dz_bf16, int64_t rpad_zb, int B, int F, int n_planes, int64_t plane_stride,
                     void* stream) {
-    DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && dgamma && dbeta && n_planes >= 1, "ln_tanh_bwd: null pointer");
+    DRQ_REQUIRE(dh && h && xhat && rstd && gamma && dz && n_planes >= 1 && (!dgamma == !dbeta), "ln_tanh_bwd: null pointer");
     DRQ_REQUIRE(B > 0 && F > 0 && F <= 32 * kMaxFPerLane, "ln_tanh_bwd: bad dims (F<=256)");
     // dy = dh * tanh' is staged in the second half of the caller's 2*B*F buffer
     float* dy = dz + (long long)B * F;
@@ -536,6 +539,7 @@ int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h
                                                                       reinterpret_cast<__nv_bfloat16*>(dz_bf16), rpad_zb, B, F,
                                                                       n_planes, plane_stride);
     if (int rc = check_launch("ln_tanh_bwd_row_kernel")) return rc;
+    if (!dgamma) return DRQ_OK;
     launch_k(ln_param_grad_kernel, F, 256, 0, as_stream(stream), dy, xhat, dgamma, dbeta, B, F);
     return check_launch("ln_param_grad_kernel");
 }

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) colsum_multi_kernel(const ColsumJobs jobs
     float s = 0.f;
     if (n < jb.N) {
         const float* X = reinterpret_cast<const float*>(jb.X);
-        for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n];
+        if (jb.Y) { for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n] * jb.Y[m * jb.ld + n]; }
+        else { for (int m = ty; m < jb.M; m += 8) s += X[m * jb.ld + n]; }
     }
     red[ty][tx] = s;
     __syncthreads();

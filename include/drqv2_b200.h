@@ -276,9 +276,10 @@ int drq_pack_multi(const drq_pack_job* jobs, int njobs, void* stream);
 
 /* all bias gradients (column sums over the batch rows) of one backward pass in one launch: out[n] =
  * sum_m X[m][n], X fp32 row-major with row stride ld (tb == 0) or a TB bf16 activation with ld units per
- * row (tb != 0). */
+ * row (tb != 0).  With Y (fp32 jobs) the sum runs over the elementwise product - LayerNorm's dgamma. */
 #define DRQ_COLSUM_MAX_JOBS 8
-typedef struct { const void* X; int64_t ld; float* out; int32_t M; int32_t N; int32_t tb; int32_t reserved; } drq_colsum_job;
+typedef struct { const void* X; int64_t ld; float* out; int32_t M; int32_t N; int32_t tb; int32_t reserved;
+                 const float* Y; /* fp32 jobs: nullable, same shape/ld as X: out[n] = sum_m X[m][n] * Y[m][n] */ } drq_colsum_job;
 int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------ dense, fp32 */
@@ -323,6 +324,8 @@ typedef struct {
     const float* bias; const float* gamma; const float* beta;
     float* h_out; int64_t ld_h; float* xhat; float* rstd;
     uint16_t* h_bf16; int64_t units_bf16; int64_t row0_bf16;
+    const float* tail; int64_t ld_tail; int32_t n_tail;   /* nullable: tail[b][0..n_tail) is appended at feature F of the bf16 row
+                                                             (the action of torch.cat([h, action]), drqv2.py:117) */
 } drq_ln_job;
 int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float eps, void* stream);
 
@@ -330,7 +333,9 @@ int drq_ln_tanh_fwd_multi(const drq_ln_job* jobs, int njobs, int B, int F, float
  * per-head / split-K partial products of the Q heads' first-layer data gradient.
  * backward of tanh∘LayerNorm: dh (ld_dh) -> dz (gradient w.r.t. the Linear
  * output), dgamma[F], dbeta[F].  h is the saved tanh output (ld_h).
- * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) is scratch. */
+ * dz must hold 2*B*F floats: [0,B*F) receives dz, [B*F,2*B*F) receives dy = dh * tanh'.
+ * dgamma == NULL: only the row kernel runs; dgamma = colsum(dy * xhat) and dbeta = colsum(dy) are then left to
+ * drq_colsum_multi. */
 int drq_ln_tanh_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h,
                     const float* xhat, const float* rstd, const float* gamma, float* dz,
                     float* dgamma, float* dbeta, uint16_t* dz_bf16, int64_t rpad_zb, int B, int F,
