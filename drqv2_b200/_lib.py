@@ -64,6 +64,7 @@ SIGNATURES = {
     "drq_critic_loss": [P, P, P, P, P, P, P, P, P, P, I, P],
     "drq_actor_loss": [P, P, P, P, P, I, P],
     "drq_copy2d_f32": [P, L, P, L, I, I, P],
+    "drq_set_l2_persist": [P, L],
     "drq_adam_step": [P, P, P, P, L, P, P],
     "drq_soft_update": [P, P, L, F, F, P],
     "drq_adam_ema_step": [P, P, P, P, L, P, P, P, L, F, F, P],

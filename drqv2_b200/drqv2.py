@@ -257,8 +257,8 @@ class _Arena:
         self.total = off
         self.params = torch.zeros(off, device=device)
         self.grads = torch.zeros(off, device=device)
-        self.exp_avg = torch.zeros(off, device=device)
-        self.exp_avg_sq = torch.zeros(off, device=device)
+        self.moments = torch.zeros(2, off, device=device)        # [exp_avg | exp_avg_sq], one range (L2 persistence)
+        self.exp_avg, self.exp_avg_sq = self.moments[0], self.moments[1]
         n_t = self.seg["critic"][2]
         self.target = torch.zeros(n_t, device=device)
         self.offsets = {}
@@ -432,6 +432,9 @@ class DrQV2Agent:
         self._bf16_ws = {}
         self._bf16_dirty = True
         self._prefetch, self._stage = None, {}
+        if os.environ.get("DRQV2_B200_L2_PERSIST", "0") == "1":
+            m = self._arena.moments
+            _lib.call("drq_set_l2_persist", m.data_ptr(), m.numel() * F32)
 
     def __getstate__(self):
         st = dict(self.__dict__)

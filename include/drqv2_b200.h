@@ -407,6 +407,11 @@ int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const fl
  * float64 exactly as torch/optim/adam.py:531-547 and cast to fp32.
  * One launch updates the contiguous range p[0..n): torch.optim.Adam x3 of
  * drqv2.py:148-150,201-202,221 over the flat parameter arena. */
+/* Optional: keep [base, base+bytes) (the Adam moment arenas) in the persisting L2 set-aside - the optimiser
+ * kernels are then launched with a persisting access-policy window over it (clamped to the device limits).
+ * base == NULL switches it off. */
+int drq_set_l2_persist(const void* base, int64_t bytes);
+
 int drq_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* scalars,
                   void* stream);
 
