@@ -109,6 +109,14 @@ def pack_multi(jobs):
     call("drq_pack_multi", arr, len(jobs), _stream())
 
 
+class OptSeg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ema", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("off", C.c_int64), ("n", C.c_int64), ("out", C.c_void_p), ("out2", C.c_void_p)]
+
+
+OPT_PLAIN, OPT_LINEAR, OPT_TRUNK, OPT_CONV, OPT_CONV1 = 0, 1, 2, 3, 4
+
+
 class ColsumJob(C.Structure):
     _fields_ = [("X", C.c_void_p), ("ld", C.c_int64), ("out", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
                 ("tb", C.c_int32), ("reserved", C.c_int32), ("Y", C.c_void_p)]
@@ -152,6 +160,7 @@ class Bf16State:
         self.conv1_w = torch.zeros(_lib.lib().drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)   # fp16 weights + fused bias
         self.conv_wf = [torch.zeros(36 * 32 * 8, dtype=torch.bfloat16, device=dev) for _ in range(3)]
         self.conv_wd = [torch.zeros(36 * 32 * 8, dtype=torch.bfloat16, device=dev) for _ in range(3)]
+        self.build_opt_plans()
 
     def trunk_ptr(self, slot):
         return self.trunk.ptr(row=slot * self.FP)
@@ -186,6 +195,72 @@ class Bf16State:
                 PackJob(PACK_LINEAR, H, Fd, 0, pa("policy.0.weight"), None, self.p0.ptr(), None),
                 PackJob(PACK_LINEAR, H, H, 0, pa("policy.2.weight"), None, self.p2.ptr(), None),
                 PackJob(PACK_LINEAR, A, H, 0, pa("policy.4.weight"), None, self.p4.ptr(), None)]
+
+    # ---- optimiser step + operand refresh in one launch (drq_adam_pack_step)
+    def _segments(self, mod, offs, base, ema, packed):
+        """One segment per tensor of `mod` in arena order; tensors without a bf16 copy merge into PLAIN runs.
+        packed: pname -> (kind, rows, cols, out, out2)."""
+        segs = []
+        skip = None
+        for pname, prm in mod.named_parameters():
+            if pname == skip:
+                continue
+            off, n = offs[pname] - base, prm.numel()
+            if pname in packed:
+                kind, rows, cols, out, out2 = packed[pname]
+                if kind == OPT_CONV1:                      # weight and bias are one segment
+                    skip = pname.replace("weight", "bias")
+                    assert offs[skip] - base == off + n
+                    n += 32
+                segs.append(OptSeg(kind, ema, rows, cols, off, n, out, out2))
+            elif segs and segs[-1].kind == OPT_PLAIN and segs[-1].ema == ema and segs[-1].off + segs[-1].n == off:
+                segs[-1].n += _ceil(n, 4)                  # arena tensors start on 16-byte boundaries
+            else:
+                segs.append(OptSeg(OPT_PLAIN, ema, 0, 0, off, _ceil(n, 4), None, None))
+        return segs
+
+    def _critic_like_packed(self, slot, z0):
+        ag = self.agent
+        A, Fd, H = ag.action_dim, ag.feature_dim, ag.hidden_dim
+        pk = {"trunk.0.weight": (OPT_TRUNK, Fd, REPR_DIM, self.trunk_ptr(slot), None)}
+        for z in range(2):
+            pk[f"Q{z + 1}.0.weight"] = (OPT_LINEAR, H, Fd + A, self.q0.ptr(z0 + z), None)
+            pk[f"Q{z + 1}.2.weight"] = (OPT_LINEAR, H, H, self.q2.ptr(z0 + z), None)
+        return pk
+
+    def build_opt_plans(self):
+        ag = self.agent
+        a = ag._arena
+        A, Fd, H = ag.action_dim, ag.feature_dim, ag.hidden_dim
+        enc = {"convnet.0.weight": (OPT_CONV1, ag.obs_shape[0], 0, self.conv1_w.data_ptr(), None)}
+        for i, k in enumerate((2, 4, 6)):
+            enc[f"convnet.{k}.weight"] = (OPT_CONV, 0, 0, self.conv_wf[i].data_ptr(), self.conv_wd[i].data_ptr())
+        segs = self._segments(ag.encoder, a.offsets["encoder"], 0, 0, enc)
+        segs += self._segments(ag.critic, a.offsets["critic"], 0, 0, self._critic_like_packed(self.CRITIC, 0))
+        self.plan_critic = (OptSeg * len(segs))(*segs)
+        act = {"trunk.0.weight": (OPT_TRUNK, Fd, REPR_DIM, self.trunk_ptr(self.ACTOR), None),
+               "policy.0.weight": (OPT_LINEAR, H, Fd, self.p0.ptr(), None),
+               "policy.2.weight": (OPT_LINEAR, H, H, self.p2.ptr(), None),
+               "policy.4.weight": (OPT_LINEAR, A, H, self.p4.ptr(), None)}
+        segs = self._segments(ag.actor, a.offsets["actor"], 0, 0, act)
+        segs += self._segments(ag.critic, a.offsets["critic"], a.seg["critic"][0], 1, self._critic_like_packed(self.TARGET, 2))
+        self.plan_actor = (OptSeg * len(segs))(*segs)
+
+    def step_critic_encoder(self):
+        """critic_opt.step(); encoder_opt.step() (drqv2.py:201-202) and their bf16 operand copies."""
+        ag = self.agent
+        a = ag._arena
+        call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
+             ag._scal_dev.data_ptr(), None, None, 0.0, 0.0, self.plan_critic, len(self.plan_critic), _stream())
+
+    def step_actor_target(self):
+        """actor_opt.step() and the soft target update (drqv2.py:221,259-260) and their bf16 operand copies."""
+        ag = self.agent
+        a = ag._arena
+        tau = float(ag.critic_target_tau)
+        call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
+             ag._scal_dev.data_ptr(), a.ptr("params", "critic"), a.target.data_ptr(), tau, float(1 - tau),
+             self.plan_actor, len(self.plan_actor), _stream())
 
     def repack_critic_encoder(self):
         """after critic_opt.step() / encoder_opt.step() (drqv2.py:201-202)"""
@@ -366,11 +441,7 @@ def critic_pass(agent, ws, bw):
          ge("convnet.0.bias"), B, agent.obs_shape[0], agent.aug.pad, s)
     # critic_opt.step(); encoder_opt.step(); refresh their bf16 operand copies
     agent._sync_grads("encoder", "critic")          # data-parallel: mean over ranks (no-op otherwise)
-    a = agent._arena
-    off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
-    call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
-         a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(), s)
-    st.repack_critic_encoder()
+    st.step_critic_encoder()
 
 
 def actor_pass(agent, ws, bw):
@@ -431,14 +502,7 @@ def actor_pass(agent, ws, bw):
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.weight"), B, Fd, 0, 0, ws.xhatA.data_ptr()),
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.bias"), B, Fd, 0, 0)])
     agent._sync_grads("actor")
-    a = agent._arena
-    off, n = a.seg["actor"][0], a.seg["actor"][2]
-    coff, cn = a.seg["critic"][0], a.seg["critic"][2]
-    tau = float(agent.critic_target_tau)
-    call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
-         a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(),
-         a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, tau, float(1 - tau), s)
-    st.repack_actor_target()
+    st.step_actor_target()
 
 
 def act_workspace(agent, n, dev):

@@ -68,6 +68,7 @@ SIGNATURES = {
     "drq_adam_step": [P, P, P, P, L, P, P],
     "drq_soft_update": [P, P, L, F, F, P],
     "drq_adam_ema_step": [P, P, P, P, L, P, P, P, L, F, F, P],
+    "drq_adam_pack_step": [P, P, P, P, P, P, P, F, F, P, I, P],
 }
 # entry points with a non-status return
 SPECIAL = {

@@ -10,6 +10,8 @@ built extension or without a CUDA device these classes raise.
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 import math
 
 import numpy as np
@@ -240,20 +242,40 @@ class Critic(nn.Module):
 
 
 # ----------------------------------------------------------------------------- flat arenas
+@contextlib.contextmanager
+def _capture(graph):
+    """``torch.cuda.graph`` with the cyclic garbage collector held off.  A collection in the middle of a
+    capture may run the destructors of dead CUDA objects (other agents' graphs, pinned buffers, events);
+    cudaFree / cudaEventDestroy from the capturing thread are illegal then and abort the process."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        # thread_local: NCCL's watchdog thread may touch CUDA while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            yield
+    finally:
+        if was:
+            gc.enable()
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
 class _Arena:
     """Flat fp32 storage for parameters / gradients / Adam moments of
-    [encoder | critic | actor] (each segment padded to 4 floats) and for the target
-    critic.  Module parameters become views, so state_dict()/pickle see ordinary tensors
+    [encoder | critic | actor] (every tensor starts on a 16-byte boundary; the padding
+    carries zero gradients) and for the target critic.  Module parameters become views, so state_dict()/pickle see ordinary tensors
     in the reference's layouts while one kernel can update a whole optimiser's range."""
 
     def __init__(self, encoder, critic, actor, critic_target, device):
         self.seg = {}
         off = 0
         for name, mod in (("encoder", encoder), ("critic", critic), ("actor", actor)):
-            n = sum(p.numel() for p in mod.parameters())
-            n_pad = (n + 3) // 4 * 4
-            self.seg[name] = (off, n, n_pad)
-            off += n_pad
+            n = sum(_pad4(p.numel()) for p in mod.parameters())
+            self.seg[name] = (off, n, n)
+            off += n
         self.total = off
         self.params = torch.zeros(off, device=device)
         self.grads = torch.zeros(off, device=device)
@@ -280,7 +302,7 @@ class _Arena:
                 if flat_grad is not None:
                     p.grad = flat_grad[off:off + n].view(p.shape)
                 offs[pname] = off
-                off += n
+                off += _pad4(n)
         return offs
 
     def ptr(self, which, net, pname=None):
@@ -340,10 +362,15 @@ class _Opt:
         self._agent, self.net = agent, net
         self.defaults = dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False)
 
+    def _flat(self, arena):
+        """the net's tensors in parameters() order, without the arena's alignment padding"""
+        offs = self._agent._arena.offsets[self.net]
+        return torch.cat([arena[offs[k]:offs[k] + p.numel()] for k, p in getattr(self._agent, self.net).named_parameters()])
+
     def state_dict(self):
-        a, (off, n, _) = self._agent._arena, self._agent._arena.seg[self.net]
-        return dict(step=self._agent._opt_step, exp_avg=a.exp_avg[off:off + n].clone(),
-                    exp_avg_sq=a.exp_avg_sq[off:off + n].clone(), **self.defaults)
+        a = self._agent._arena
+        return dict(step=self._agent._opt_step, exp_avg=self._flat(a.exp_avg), exp_avg_sq=self._flat(a.exp_avg_sq),
+                    **self.defaults)
 
     def zero_grad(self, set_to_none=True):
         off, n, _ = self._agent._arena.seg[self.net]
@@ -457,10 +484,9 @@ class DrQV2Agent:
                 off = a.offsets[name][pname]
                 p.data = a.params[off:off + p.numel()].view(p.shape)
                 p.grad = a.grads[off:off + p.numel()].view(p.shape)
-        off = 0
         for pname, p in self.critic_target.named_parameters():
+            off = a.offsets["critic"][pname] - a.seg["critic"][0]
             p.data = a.target[off:off + p.numel()].view(p.shape)
-            off += p.numel()
         self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None
         self._bf16_dirty = True
 
@@ -609,7 +635,7 @@ class DrQV2Agent:
             if self.use_cuda_graph:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                with _capture(g):
                     self._act_body(w, n, sample)
                 w["graph"][key] = g
                 g.replay()
@@ -695,7 +721,7 @@ class DrQV2Agent:
             if state == "warm":
                 torch.cuda.synchronize()
                 state = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(state, capture_error_mode="thread_local"):   # NCCL's watchdog thread may touch CUDA during capture
+                with _capture(state):
                     self._update_body(ws, fetch, draw=inj is None)
                 self._graphs[key] = state
             state.replay()
@@ -784,8 +810,8 @@ class DrQV2Agent:
                      ws.feat.data_ptr(), 2 * B, self.obs_shape[0], self.aug.pad)
 
     def _q_strides(self):
-        Fd, A, H = self.feature_dim, self.action_dim, self.hidden_dim
-        return H * (Fd + A) + H + H * H + H + H + 1   # floats between Q1.* and Q2.* tensors
+        co = self._arena.offsets["critic"]
+        return co["Q2.0.weight"] - co["Q1.0.weight"]   # floats between Q1.* and Q2.* tensors
 
     def _twin_q_fwd(self, pfn, x, c1, c2, q, B):
         """Both Q heads in one batched launch per layer (drqv2.py:103-111,118-119)."""

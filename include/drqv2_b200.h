@@ -426,6 +426,29 @@ int drq_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n_ad
                       const float* scalars, const float* ema_src, float* ema_dst, int64_t n_ema,
                       float tau, float one_minus_tau, void* stream);
 
+/* Optimiser step and bf16 operand refresh in one launch (bf16 mode): every tensor of an optimiser phase is a
+ * segment; the kernel applies Adam (ema == 0: p/g/m/v[off .. off+n)) or the soft target update (ema == 1:
+ * ema_dst[off ..] = tau*ema_src[off ..] + (1-tau)*ema_dst[off ..]) and writes the bf16 copy the tensor-core
+ * kernels read straight from the updated value - what drq_adam_ema_step followed by drq_pack_multi produce,
+ * bit for bit, without reading the fp32 parameters a second time.
+ *   DRQ_OPT_PLAIN : no bf16 copy (biases, LayerNorm, the scalar Q heads)
+ *   DRQ_OPT_LINEAR: nn.Linear weight [rows][cols]            -> out as drq_pack_linear_tb
+ *   DRQ_OPT_TRUNK : trunk weight [rows][32*35*35]            -> out as drq_pack_trunk_tb
+ *   DRQ_OPT_CONV  : conv weight [32][32][3][3] (n = 9216)    -> out (fwd), out2 (dgrad) as drq_pack_conv_w_bf16
+ *   DRQ_OPT_CONV1 : conv1 weight [32][rows=cin][3][3] and its bias, adjacent (n = 288*cin + 32)
+ *                                                            -> out as drq_pack_conv1_w_bf16 */
+#define DRQ_OPT_PLAIN 0
+#define DRQ_OPT_LINEAR 1
+#define DRQ_OPT_TRUNK 2
+#define DRQ_OPT_CONV 3
+#define DRQ_OPT_CONV1 4
+#define DRQ_OPT_MAX_SEGS 32
+typedef struct { int32_t kind; int32_t ema; int32_t rows; int32_t cols; int64_t off; int64_t n;
+                 uint16_t* out; uint16_t* out2; } drq_opt_seg;
+int drq_adam_pack_step(float* p, const float* g, float* m, float* v, const float* scalars,
+                       const float* ema_src, float* ema_dst, float tau, float one_minus_tau,
+                       const drq_opt_seg* segs, int nsegs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

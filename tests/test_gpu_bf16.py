@@ -411,3 +411,69 @@ def test_bf16_graph_equals_eager_and_act(dev):
         a = fresh.act(obs[i].numpy(), 5000, True)
         want = o64.act(obs[i], 5000, True)[0].numpy()
         assert np.abs(a - want).max() < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("A,Fd,H", [(6, 50, 1024), (1, 20, 256), (21, 50, 320)])
+def test_fused_optimiser_step_equals_adam_then_pack(dev, A, Fd, H):
+    """drq_adam_pack_step (Adam / soft update + bf16 operand refresh in one launch) against
+    drq_adam_step / drq_adam_ema_step followed by drq_pack_multi: every fp32 arena and every packed
+    operand bit for bit (torch.optim.Adam drqv2.py:148-150, utils.soft_update_params utils.py:42-45)."""
+    import math
+    from oracle import drq_oracle as O
+    from drqv2_b200._lib import call
+    F32 = 4
+    params = O.synthetic_params(9, A, Fd, H, seed=3)
+    agent = _make_agent(A, Fd, H, 1e-3, params, "bf16")
+    st, a = agent._bf16, agent._arena
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a.grads.copy_(torch.randn(a.total, device="cuda", generator=g) * 1e-2)
+    a.exp_avg.copy_(torch.randn(a.total, device="cuda", generator=g) * 1e-2)
+    a.exp_avg_sq.copy_(torch.rand(a.total, device="cuda", generator=g) * 1e-4)
+    a.target.copy_(torch.randn(a.target.numel(), device="cuda", generator=g) * 0.1)
+    live = torch.zeros(a.total, device="cuda")  # the arena's alignment padding carries no gradient / state
+    for net in ("encoder", "critic", "actor"):
+        for pname, prm in getattr(agent, net).named_parameters():
+            live[a.offsets[net][pname]:a.offsets[net][pname] + prm.numel()] = 1
+    for x in (a.grads, a.exp_avg, a.exp_avg_sq):
+        x.mul_(live)
+    c0, cn = a.seg["critic"][0], a.seg["critic"][2]
+    a.target.mul_(live[c0:c0 + cn])
+    t = 7
+    agent._scal_dev[:6] = torch.tensor([0.1, 0.999, 0.001, math.sqrt(1 - 0.999 ** t), 1e-8, -1e-3 / (1 - 0.9 ** t)])
+    arenas = (a.params, a.exp_avg, a.exp_avg_sq, a.target)
+    packed = [st.trunk.buf, st.q0.buf, st.q2.buf, st.p0.buf, st.p2.buf, st.p4.buf, st.conv1_w] + st.conv_wf + st.conv_wd
+    snap = [x.clone() for x in arenas]
+
+    def run(fused):
+        for x, y in zip(arenas, snap):
+            x.copy_(y)
+        for x in packed:
+            x.fill_(-7.0)                       # stale operands: every live element must be rewritten
+        st.repack_all()
+        if fused:
+            st.step_critic_encoder()
+            st.step_actor_target()
+        else:
+            off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
+            call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+                 a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(), s)
+            st.repack_critic_encoder()
+            off, n = a.seg["actor"][0], a.seg["actor"][2]
+            coff, cn = a.seg["critic"][0], a.seg["critic"][2]
+            call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+                 a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, agent._scal_dev.data_ptr(),
+                 a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, 0.01, 0.99, s)
+            st.repack_actor_target()
+        torch.cuda.synchronize()
+        return [x.clone() for x in arenas], [x.clone() for x in packed]
+
+    agent.critic_target_tau = 0.01
+    ref_a, ref_p = run(False)
+    new_a, new_p = run(True)
+    assert not torch.equal(ref_a[0], snap[0]) and not torch.equal(ref_a[3], snap[3])
+    for name, x, y in zip(("params", "exp_avg", "exp_avg_sq", "target"), ref_a, new_a):
+        assert torch.equal(x, y), (name, int((x != y).sum()))
+    for i, (x, y) in enumerate(zip(ref_p, new_p)):
+        assert torch.equal(x.view(torch.int16), y.view(torch.int16)), (i, int((x.view(torch.int16) != y.view(torch.int16)).sum()))
