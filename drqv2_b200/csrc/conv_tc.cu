@@ -252,19 +252,23 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 
 
 // ---------------------------------------------------------------- conv 32->32 weight gradient
-// dW[tap][ci][co] = sum_{n,p} in[n][p + off(tap)][ci] * d[n][p][co]: per tap a GEMM with
-// M = ci, N = co and K = positions.  Both operands are read straight from WB-layout windows
-// as MN-major UMMA operands (8 channels = one 16-byte unit, consecutive positions 16 bytes
-// apart = consecutive K).  M is padded to 64 (rows 32..63 read neighbouring smem and are
-// ignored).  A tenth "tap" multiplies d by an all-ones A operand: its row 0 is the bias
-// gradient.  Every CTA keeps its 10 accumulators (320 TMEM columns) across all of its tiles
-// and writes one fp32 partial at the end; partials are reduced in fixed order.
+// dW[tap][ci][co] = sum_{n,p} in[n][p + off(tap)][ci] * d[n][p][co]: GEMMs with K = positions whose operands
+// are read straight from WB-layout windows as MN-major UMMA operands (8 channels = one 16-byte unit,
+// consecutive positions 16 bytes apart = consecutive K).
+// A UMMA of this shape is bound by the shared-memory bytes of its operands ((A + B) / 128 B per cycle,
+// tools/ub/ub_mma.cu), so the three horizontal taps share one instruction: the input window is staged three
+// times, shifted by 0 / 1 / 2 positions, as 12 consecutive MN units, a 13th unit holds bf16 ones (its rows
+// give the bias gradient) and one M = 128 UMMA per vertical tap and K step multiplies all of them by the
+// gradient tile: 3 UMMAs of 5 KB per K step instead of 10 of 3 KB.  Units 13..15 read whatever follows
+// in shared memory; their accumulator rows are ignored.  Every CTA keeps its 3 accumulators (96 TMEM columns)
+// across all of its tiles and writes one fp32 partial at the end; partials are reduced in fixed order.
 constexpr int kWgStages = 3;
 constexpr int kWgDRows = kTM;                              // d tile rows per block
-constexpr int kWgStageBytes = kStageBytes + 4 * kWgDRows * 16;   // in-window + d tile
-constexpr int kWgOnesBytes = 8 * 16 * 16;                  // 8 MN units x 16 K x 16 B of bf16 ones
+constexpr int kWgPlane = kStageRows * 16;                  // one MN unit: 216 positions x 8 channels
+constexpr int kWgABytes = 13 * kWgPlane;                   // 3 shifted windows x 4 channel blocks + ones
+constexpr int kWgStageBytes = kWgABytes + 4 * kWgDRows * 16;
 constexpr int kWgAcc = 10;
-constexpr int kWgPartial = kWgAcc * 32 * 32;               // floats per CTA
+constexpr int kWgPartial = kWgAcc * 32 * 32;               // floats per CTA: [9 taps + bias][ci][co]
 
 struct WgradTcArgs {
     const __nv_bfloat16* in; long long cs_in;
@@ -273,14 +277,10 @@ struct WgradTcArgs {
     int n_images, ntiles;
 };
 
-// Two CTAs share an SM: CTA pair (2i, 2i+1) walks the same tiles, the even one accumulates taps 0..4, the odd
-// one taps 5..8 and the bias tap (5 x 32 TMEM columns each).  A lone CTA issues M64 N32 UMMAs at one per
-// ~45 cycles whatever the pipe could take; two interleaved streams nearly double that (tools/ub/ub_mma.cu).
-__global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
+__global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ones_s = smem;
-    uint8_t* st_s = smem + kWgOnesBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kWgStages * kWgStageBytes);
+    uint8_t* st_s = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kWgStages * kWgStageBytes + 3 * kWgPlane);
     uint64_t* full = bars;
     uint64_t* empty = bars + kWgStages;
     uint64_t* done = bars + 2 * kWgStages;
@@ -288,17 +288,19 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = a.n_images * a.ntiles;
-    const int half = blockIdx.x & 1, cta = blockIdx.x >> 1, ncta = gridDim.x >> 1;     // tap half, tile walker
+    const int cta = blockIdx.x, ncta = gridDim.x;
     pdl_trigger();
-    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kThreadsTC)
-        reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;    // bf16 1.0 x2
+    for (int i = threadIdx.x; i < kWgStages * (kWgPlane / 4); i += kThreadsTC) {
+        const int st = i / (kWgPlane / 4), w = i - st * (kWgPlane / 4);
+        reinterpret_cast<uint32_t*>(st_s + st * kWgStageBytes + 12 * kWgPlane)[w] = 0x3F803F80u;    // bf16 1.0 x2
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWgStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 128);
         tmem_relinquish();
     }
     fence_proxy_async();
@@ -309,29 +311,28 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTc
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // lanes 0..3: input-window channel blocks, lanes 4..7: gradient tile channel blocks
+        // lanes 0..11: input window, shift lane / 4, channel block lane % 4; lanes 12..15: gradient tile channel blocks
         int stage = 0; uint32_t phase = 0;
         for (int t = cta; t < total_tiles; t += ncta) {
             const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
             mbar_wait(empty + stage, phase ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(full + stage, 4 * (kWinRows + kWgDRows) * 16);
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, (12 * kWinRows + 4 * kWgDRows) * 16);
             __syncwarp();
             const long long row0 = (long long)n * kPLB + kGuard + p0;
             uint8_t* dst = st_s + stage * kWgStageBytes;
-            if (lane < 4)
-                bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
-            else if (lane < 8)
-                bulk_g2s(dst + kStageBytes + (lane - 4) * kWgDRows * 16, a.d + ((lane - 4) * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
+            if (lane < 12)
+                bulk_g2s(dst + lane * kWgPlane, a.in + ((lane & 3) * a.cs_in + row0 + (lane >> 2)) * 8, kWinRows * 16, full + stage);
+            else if (lane < 16)
+                bulk_g2s(dst + kWgABytes + (lane - 12) * kWgDRows * 16, a.d + ((lane - 12) * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(64, 32, true, true);
+        constexpr uint32_t idesc = make_idesc_bf16(128, 32, true, true);
         int stage = 0; uint32_t phase = 0;
         bool first = true;
         // descriptors = per-stage base + compile-time (address >> 4) offsets (cheap issue loop)
-        const uint64_t da0 = make_smem_desc(smem_u32(st_s), 128, kStageRows * 16);
-        const uint64_t db0 = make_smem_desc(smem_u32(st_s) + kStageBytes, 128, kWgDRows * 16);
-        const uint64_t d1 = make_smem_desc(smem_u32(ones_s), 128, 256);
+        const uint64_t da0 = make_smem_desc(smem_u32(st_s), 128, kWgPlane);
+        const uint64_t db0 = make_smem_desc(smem_u32(st_s) + kWgABytes, 128, kWgDRows * 16);
         for (int t = cta; t < total_tiles; t += ncta) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
@@ -342,16 +343,9 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTc
                     const uint64_t db = db0 + so + (uint64_t)(ks * 16);
                     const uint64_t da = da0 + so + (uint64_t)(ks * 16);
                     const uint32_t accum = (first && ks == 0) ? 0u : 1u;
-                    if (half == 0) {
 #pragma unroll
-                        for (int tap = 0; tap < 5; ++tap)
-                            umma_bf16(tmem_base + tap * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
-                    } else {
-#pragma unroll
-                        for (int tap = 5; tap < 9; ++tap)
-                            umma_bf16(tmem_base + (tap - 5) * 32, da + (uint64_t)((tap / 3) * kPW + (tap % 3)), db, idesc, accum);
-                        umma_bf16(tmem_base + 4 * 32, d1, db, idesc, accum);
-                    }
+                    for (int dy = 0; dy < 3; ++dy)
+                        umma_bf16(tmem_base + dy * 32, da + (uint64_t)(dy * kPW), db, idesc, accum);
                 }
                 umma_commit(empty + stage);
             }
@@ -362,27 +356,27 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_wgrad_tc_kernel(WgradTc
         if (elect_one()) umma_commit(done);
         __syncwarp();
     } else {
+        // accumulator row = MN unit * 8 + channel: lane quarter q < 3 holds the horizontal tap q (row = ci), quarter 3
+        // the ones unit (row 96 = bias gradient)
         const int q = warp & 3;
         mbar_wait(done, 0);
         tc_fence_after();
         float* out = a.partial + (long long)cta * kWgPartial;
-        if (q < 2) {
-            // M = 64 accumulator: rows 0..15 -> lanes 0..15, rows 16..31 -> lanes 32..47
-            for (int tl = 0; tl < 5; ++tl) {
-                const int tap = half * 5 + tl;
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + tl * 32, v);
-                if (lane < 16) {
-                    float4* dst = reinterpret_cast<float4*>(out + (tap * 32 + q * 16 + lane) * 32);
+        for (int dy = 0; dy < 3; ++dy) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + dy * 32, v);
+            float4* dst = nullptr;
+            if (q < 3) dst = reinterpret_cast<float4*>(out + ((dy * 3 + q) * 32 + lane) * 32);
+            else if (dy == 0 && lane == 0) dst = reinterpret_cast<float4*>(out + 9 * 32 * 32);
+            if (dst) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
 // dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co].  Block = 32 outputs x 8
@@ -414,9 +408,9 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     }
 }
 
-// + kStageBytes of tail padding: rows 32..63 of the M=64 A operand address 4 more channel blocks
-// past the staged window (results ignored) and must stay inside the allocation
-constexpr size_t kWgradTcSmem = kWgOnesBytes + kWgStages * kWgStageBytes + (2 * kWgStages + 1) * 8 + 16 + kStageBytes;
+// + 3 planes of tail padding: MN units 13..15 of the last stage's A operand (results ignored) must stay inside
+// the allocation
+constexpr size_t kWgradTcSmem = kWgStages * kWgStageBytes + 3 * kWgPlane + (2 * kWgStages + 1) * 8 + 16;
 
 constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesTC + 2 * kAccStages) * 8 + 16 + 128;
 
@@ -509,8 +503,8 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     a.partial = partial;
     a.n_images = N;
     a.ntiles = (hout * kPW + kTM - 1) / kTM;
-    const int G = conv_tc_grid(N * a.ntiles);                 // tile walkers; each is a pair of CTAs
-    launch_k(conv3x3_wgrad_tc_kernel, 2 * G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
+    const int G = conv_tc_grid(N * a.ntiles);                 // tile walkers, one per SM
+    launch_k(conv3x3_wgrad_tc_kernel, G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
     launch_k(wgrad_tc_reduce_kernel, (9248 + 31) / 32, 256, 0, as_stream(stream), partial, G, dw, db);
     return check_launch("wgrad_tc_reduce_kernel");
