@@ -138,6 +138,35 @@ def run_ours(args, rank, world):
     fill_ring(key, A, args.episodes, 501, dev, seed=1 + rank)
     loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
     it = iter(loader)
+    K = 1 if dp else max(1, args.agents_per_gpu)
+    # further ensemble members of this GPU: own parameters, optimiser state, ring, RNG stream, graph and CUDA stream
+    members, member_its = [agent], [it]
+    for k in range(1, K):
+        torch.manual_seed(1000 * k + rank)
+        members.append(DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
+                                  use_cuda_graph=True, seed=1000 * k + rank, mode=args.mode))
+        fill_ring(f"{key}_m{k}", A, args.episodes, 501, dev, seed=1 + rank + 1000 * k)
+        member_its.append(iter(make_replay_loader(f"{key}_m{k}", args.episodes * 501, B, 0, False, 3, 0.99)))
+    member_streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+
+    def update_all(iters, step):
+        """one update of every member of this GPU; returns member 0's metrics"""
+        if K == 1:
+            return agent.update(iters[0], step)
+        cur = torch.cuda.current_stream()
+        pending = []
+        for ag, mit, st in zip(members, iters, member_streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                pending.append(ag.update_async(mit, step))
+        m = dict()
+        for ag, ws_, st in zip(members, pending, member_streams):
+            if ag.use_tb:
+                with torch.cuda.stream(st):
+                    mk = ag.read_metrics(ws_)
+                m = m or mk
+            cur.wait_stream(st)
+        return m
 
     # count kernel launches of one update (eager pass == what the graph replays): every C-ABI call of the
     # update goes through _lib.call; entry points that launch two kernels are listed below
@@ -162,7 +191,7 @@ def run_ours(args, rank, world):
     launches_per_update = n_calls[0]
     D.call = R.call = BF.call = orig_call
     for _ in range(max(args.warmup, 3)):
-        agent.update(it, step); step += 2
+        update_all(member_its, step); step += 2
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -173,7 +202,7 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        agent.update(it, step); step += 2
+        update_all(member_its, step); step += 2
     e1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -183,12 +212,13 @@ def run_ours(args, rank, world):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = t.item()
     ms_per_step = ms / args.steps
-    value = (1 if dp else world) * 1e3 / ms_per_step      # dp: global-batch updates/s; ensemble: sum over agents
+    value = (1 if dp else world * K) * 1e3 / ms_per_step  # dp: global-batch updates/s; ensemble: sum over agents
 
     # ---- e2e: public API fed from host batches (pinned), metrics read back.  prefetch: the agent pulls the next
     # host batch one update ahead and overlaps its H2D copy with the running update (a DrQV2Agent option)
-    agent.use_tb = True
-    agent.prefetch = True
+    for ag in members:
+        ag.use_tb = True
+        ag.prefetch = True
     g = torch.Generator().manual_seed(100 + rank)
     nhost = 4
     host_batches = []
@@ -204,15 +234,15 @@ def run_ours(args, rank, world):
             yield host_batches[i % nhost]
             i += 1
 
-    hit = host_iter()
+    hits = [host_iter() for _ in range(K)]
     for _ in range(4):
-        agent.update(hit, step); step += 2
+        update_all(hits, step); step += 2
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     e0.record()
     for _ in range(args.steps):
-        m = agent.update(hit, step); step += 2
+        m = update_all(hits, step); step += 2
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1)
@@ -220,12 +250,13 @@ def run_ours(args, rank, world):
         t = torch.tensor([e2e_ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = t.item()
-    e2e_value = (1 if dp else world) * 1e3 / (e2e_ms / args.steps)
-    h2d = sum(t.numel() * t.element_size() for t in host_batches[0]) + 64
-    d2h = 8 * 4
+    e2e_value = (1 if dp else world * K) * 1e3 / (e2e_ms / args.steps)
+    h2d = K * (sum(t.numel() * t.element_size() for t in host_batches[0]) + 64)
+    d2h = K * 8 * 4
     assert np.isfinite(m["critic_loss"])
-    agent.use_tb = False
-    agent.prefetch = False
+    for ag in members:
+        ag.use_tb = False
+        ag.prefetch = False
 
     out = None
     if rank == 0:
@@ -317,12 +348,12 @@ def run_ours(args, rank, world):
                "data": "synthetic",
                "config": {"workload": f"configs[1]: walker_walk-shape agent.update, B={B}, 9x84x84 u8 stacks, A={A}, "
                                       f"F={Fd}, H={H}, n-step 3, GPU-resident replay ring ({args.episodes} episodes x 501 "
-                                      f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; global batch {args.batch} data-parallel over {world} GPUs (NCCL gradient all-reduce in the graph)" if dp else (f"; {world} independent agents (ensemble), one per GPU, no collective" if world > 1 else "")),
+                                      f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; global batch {args.batch} data-parallel over {world} GPUs (NCCL gradient all-reduce in the graph)" if dp else (f"; {world * K} independent agents (ensemble), {K} per GPU on their own streams, no collective" if world * K > 1 else "")),
                           "l2": "inputs larger than L2: each step gathers a fresh 32.5 MB batch from a "
                                 f"{args.episodes * 501 * 21168 / 1e6:.0f} MB ring and streams ~700 MB of activations",
-                          "mode": args.mode},
+                          "mode": args.mode, "agents_per_gpu": K},
                "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": launches_per_update * args.steps, "launches_per_update": launches_per_update,
+               "gpu_launches": launches_per_update * args.steps * K, "launches_per_update": launches_per_update,
                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     return out
 
@@ -432,6 +463,9 @@ def main():
     ap.add_argument("--hidden-dim", type=int, default=1024)
     ap.add_argument("--episodes", type=int, default=64)
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--agents-per-gpu", type=int, default=1,
+                    help="ensemble members per GPU (BASELINE configs[3] uses 8): independent agents replayed on their own "
+                         "streams; value = updates/s summed over all members of all GPUs")
     ap.add_argument("--parallel", default="ensemble", choices=["ensemble", "dp"],
                     help="N > 1: independent agents per GPU (weak scaling, no collective) or one agent with the "
                          "global --batch sharded over the GPUs and NCCL gradient all-reduce (strong scaling)")

@@ -26,6 +26,7 @@ SIGNATURES = {
     "drq_rng_update_draws": [U, P, I, P, P, P, P, I, I, P],
     "drq_rng_normal_f32": [U, P, P, I, P],
     "drq_counter_advance": [P, P],
+    "drq_scalars_fetch": [P, I, P, P, P],
     "drq_random_shift_f32": [P, P, P, I, I, I, I, I, P],
     "drq_conv1_fwd_f32": [P, P, P, P, P, I, I, I, P],
     "drq_conv1_wgrad_f32": [P, P, P, P, P, P, I, I, I, P],

@@ -19,16 +19,20 @@ int ensure_smem(const void* kernel, size_t bytes, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Programmatic dependent launch (drq_set_pdl): every kernel triggers its dependents at entry and waits
-// for its predecessors (griddepcontrol.wait = all prior grids complete and flushed) before it touches
-// global memory, so the next kernel's launch latency, barrier / TMEM set-up and first instruction
-// fetches overlap the tail of the running one.  Without the launch attribute both instructions are no-ops.
+// Programmatic dependent launch (drq_set_pdl): every kernel waits for its predecessors (griddepcontrol.wait =
+// all prior grids complete and flushed) before it touches global memory, so its launch latency, barrier / TMEM
+// set-up and first instruction fetches may overlap the tail of the running kernel.  The long tensor-core
+// kernels release their dependents (pdl_release) once their producer warp has issued its last load - the
+// remaining tail is MMA drain and epilogue; everything else releases implicitly at exit.  Releasing at kernel
+// entry (pdl_trigger, -DDRQ_PDL_ENTRY_TRIGGER) parks the next kernel's CTAs on the SMs for the whole run of a
+// multi-wave kernel and was measured 25 % slower.  Without the launch attribute the instructions are no-ops.
 extern int g_pdl;
 __device__ __forceinline__ void pdl_trigger() {
-#ifndef DRQ_NO_PDL_TRIGGER
+#ifdef DRQ_PDL_ENTRY_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... P, typename... A>

@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
                 if (++rs == kC1RawStages) { rs = 0; rphase ^= 1; }
             }
         }
+        pdl_release();                          // last rows are on their way: the next kernel may set itself up
     } else {
         // ------------------------------------------------ epilogue warps 17..20 -> lane quarters 1,2,3,0
         const int q = warp & 3;

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_tc_kernel(ConvTcArgs a)
                     bulk_g2s(dst + lane * kStageRows * 16, a.in + (lane * a.cs_in + row0) * 8, kWinRows * 16, full + stage);
                 if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             }
+            pdl_release();                      // last window is on its way: the next kernel may set itself up
             CV_STAMPS(if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[0] = w_empty; a.stamps[1] = CV_T() - t_begin; })
         }
     } else if (warp == 1) {
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
                 bulk_g2s(dst + kWgABytes + (lane - 12) * kWgDRows * 16, a.d + ((lane - 12) * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
+        pdl_release();
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(128, 32, true, true);
         int stage = 0; uint32_t phase = 0;

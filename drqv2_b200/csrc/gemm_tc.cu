@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
                 }
             }
         }
+        pdl_release();                          // last tiles are on their way: the next kernel may set itself up
         if (lane == 0) GT_STAMP(3);
     } else if (warp == 1) {
         // ------------------------------------------------ UMMA issuer

@@ -176,6 +176,19 @@ __global__ void counter_advance_kernel(unsigned long long* counter) {
     pdl_trigger();
     pdl_wait(); *counter += 1ull; }
 
+// out[0..16) = ring[cursor % slots][0..16); cursor += 1.  The ring is pinned host memory the host fills one
+// update ahead of the device: a CUDA graph cannot take new scalars per replay, and a fixed staging buffer
+// would be overwritten by a host that enqueues updates faster than the device runs them.
+__global__ void scalars_fetch_kernel(const float* ring, int slots, unsigned long long* cursor, float* out) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned long long c = *cursor;
+    const float v = *reinterpret_cast<const volatile float*>(ring + (c % (unsigned long long)slots) * 16 + threadIdx.x);
+    out[threadIdx.x] = v;
+    __syncwarp();
+    if (threadIdx.x == 0) *cursor = c + 1ull;
+}
+
 // out[n,c,r,col] = in[n,c,clamp(r+sy-pad),clamp(col+sx-pad)]
 __global__ void random_shift_f32_kernel(const float* __restrict__ in, const int* __restrict__ shift,
                                         float* __restrict__ out, int C, int H, int W, int pad) {
@@ -287,6 +300,12 @@ int drq_counter_advance(uint64_t* counter, void* stream) {
     DRQ_REQUIRE(counter, "counter_advance: null pointer");
     launch_k(counter_advance_kernel, 1, 1, 0, as_stream(stream), (unsigned long long*)counter);
     return check_launch("counter_advance_kernel");
+}
+
+int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream) {
+    DRQ_REQUIRE(ring && cursor && out && slots > 0, "scalars_fetch: bad arguments");
+    launch_k(scalars_fetch_kernel, 1, 16, 0, as_stream(stream), ring, slots, (unsigned long long*)cursor, out);
+    return check_launch("scalars_fetch_kernel");
 }
 
 int drq_random_shift_f32(const float* in, const int32_t* shift, float* out, int N, int C, int H,

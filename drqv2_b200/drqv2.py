@@ -452,6 +452,7 @@ class DrQV2Agent:
         self._act_ws = {}
         self._scal_host = torch.zeros(16, dtype=torch.float32).pin_memory()
         self._scal_dev = torch.zeros(16, device=dev)        # [0..7] adam scalars, [8] stddev
+        self._init_scalar_ring()
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._injected = None
@@ -469,6 +470,7 @@ class DrQV2Agent:
             st[k] = {}
         st["_bf16"] = None
         st["_prefetch"] = None
+        st["_scal_events"] = [None, None]
         return st
 
     def __setstate__(self, st):
@@ -476,6 +478,7 @@ class DrQV2Agent:
         # re-pin host staging buffers (pinning does not survive pickling)
         self._scal_host = self._scal_host.clone().pin_memory()
         self._metrics_host = self._metrics_host.clone().pin_memory()
+        self._init_scalar_ring()
         # parameters were pickled as views of the arenas (torch keeps shared storage); make
         # sure .grad views exist again
         a = self._arena
@@ -672,9 +675,24 @@ class DrQV2Agent:
     def update(self, replay_iter, step):
         """drqv2.py:230-262.  Returns {} (and does not advance the iterator) when
         step % update_every_steps != 0."""
-        metrics = dict()
+        ws = self.update_async(replay_iter, step)
+        if ws is None or not self.use_tb:
+            return dict()
+        return self.read_metrics(ws)
+
+    def read_metrics(self, ws):
+        """The metrics of the update last enqueued on the current stream (one 32-byte D2H copy and a
+        stream synchronise; drqv2.py:191-196,223-226)."""
+        self._metrics_host.copy_(ws.metrics, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return dict(zip(METRIC_KEYS, self._metrics_host.tolist()))
+
+    def update_async(self, replay_iter, step):
+        """update() without the metrics read-back: enqueues the whole update on the current stream and
+        returns its workspace (None when step % update_every_steps != 0) - no host synchronisation, so
+        several agents can be driven from one thread (ensemble.AgentEnsemble)."""
         if step % self.update_every_steps != 0:
-            return metrics
+            return None
         if hasattr(replay_iter, "next_into"):
             # GPU-resident ring: sample + n-step gather straight into the static buffers
             B = replay_iter.batch_size
@@ -726,14 +744,10 @@ class DrQV2Agent:
                 self._graphs[key] = state
             state.replay()
         self._opt_step += 1
+        self._scalars_enqueued()
         if fetch is None and self.prefetch:
             self._start_prefetch(replay_iter, ws)
-        if self.use_tb:
-            self._metrics_host.copy_(ws.metrics, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            vals = self._metrics_host.tolist()
-            metrics = dict(zip(METRIC_KEYS, vals))
-        return metrics
+        return ws
 
     def _start_prefetch(self, replay_iter, ws):
         """Pull the next host batch now and copy it to device staging buffers on a side stream, so the
@@ -773,18 +787,51 @@ class DrQV2Agent:
                 continue
             dst.copy_(src.view(dst.shape), non_blocking=True)
 
+    _SCAL_SLOTS = 256
+
+    def _init_scalar_ring(self):
+        """Pinned ring of per-update scalars the device reads in stream order (drq_scalars_fetch): the host may
+        enqueue up to _SCAL_SLOTS / 2 updates ahead of the device without overwriting a slot still to be read."""
+        self._scal_ring = torch.zeros(self._SCAL_SLOTS, 16, dtype=torch.float32).pin_memory()
+        self._scal_cursor = torch.zeros(1, dtype=torch.int64, device=self._dev)
+        self._scal_enq = 0
+        self._scal_events = [None, None]
+
     def _host_scalars(self, step):
+        """Adam scalars of the coming optimiser step and stddev(step) into the ring slot the device reads next."""
+        half = self._SCAL_SLOTS // 2
+        slot = self._scal_enq % self._SCAL_SLOTS
+        if slot % half == 0:                       # entering a half of the ring: its previous readers must be done
+            ev = self._scal_events[slot // half]
+            if ev is not None:
+                ev.synchronize()
         stddev = utils.schedule(self.stddev_schedule, step)
         sc = utils.adam_scalars(self.lr, self._opt_step + 1)
         self._scal_host[:8] = torch.from_numpy(sc)
         self._scal_host[8] = stddev
+        self._scal_ring[slot].copy_(self._scal_host)
         self._stddev = stddev
+
+    def _fetch_scalars(self):
+        """device side of _host_scalars: one tiny kernel, in stream order (graph-capturable)"""
+        call("drq_scalars_fetch", self._scal_ring.data_ptr(), self._SCAL_SLOTS, self._scal_cursor.data_ptr(),
+             self._scal_dev.data_ptr(), _stream())
+
+    def _scalars_enqueued(self):
+        """host bookkeeping after an update that consumes one ring slot has been enqueued"""
+        half = self._SCAL_SLOTS // 2
+        slot = self._scal_enq % self._SCAL_SLOTS
+        if (slot + 1) % half == 0:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._scal_events[slot // half] = ev
+        self._scal_enq += 1
 
     def _update_body(self, ws, fetch=None, draw=True):
         """Everything of one update that runs on the device, in stream order; no host sync."""
         B = ws.B
         s = _stream()
-        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        self._fetch_scalars()
         if fetch is not None:
             fetch()
         if draw:
@@ -993,7 +1040,8 @@ class DrQV2Agent:
             ws.feat[B:].copy_(next_obs)
         self._stage_inputs(ws, action=action, reward=reward, discount=discount)
         self._host_scalars(step)
-        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        self._fetch_scalars()
+        self._scalars_enqueued()
         self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=own)
         metrics = dict()
         if self.use_tb:
@@ -1013,7 +1061,8 @@ class DrQV2Agent:
         if obs.data_ptr() != ws.feat.data_ptr():
             ws.feat[:B].copy_(obs)
         self._host_scalars(step)
-        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        self._fetch_scalars()
+        self._scalars_enqueued()
         self._actor_pass(ws, ws.feat[:B])
         metrics = dict()
         if self.use_tb:

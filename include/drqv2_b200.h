@@ -119,6 +119,13 @@ int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_
 int drq_rng_normal_f32(uint64_t seed, const uint64_t* counter, float* out, int n, void* stream);
 int drq_counter_advance(uint64_t* counter, void* stream);
 
+/* Per-update host scalars for graph replays: out[0..16) = ring[*cursor % slots][0..16), then *cursor += 1.
+ * `ring` is pinned (device-visible) host memory of slots x 16 floats that the host fills ahead of the device -
+ * the Adam bias corrections of torch/optim/adam.py:531-547 and the exploration stddev of utils.py:130-146 change
+ * every update, a captured graph cannot take new arguments, and a single staging buffer would be overwritten by
+ * a host that enqueues updates faster than the device runs them.  `cursor` is a device counter. */
+int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream);
+
 /* ------------------------------------------------------------------ augmentation */
 
 /* RandomShiftsAug as an exact integer shift (drqv2.py:19-45 in intent):

@@ -630,3 +630,50 @@ def test_agent_pickle_roundtrip(dev):
     # state_dict interchange with reference-shaped modules (names/layouts, drqv2.py:55-59,74-81,100-111)
     sd = agent.critic.state_dict()
     assert list(sd) == list(O.param_shapes(9, A, Fd, H)["critic"])
+
+
+def test_async_updates_read_their_own_scalars(dev):
+    """Updates enqueued back to back without a host sync (use_tb=False, the host runs ahead of the device) read
+    the Adam bias corrections / stddev of their own step: same parameters, bit for bit, as the synchronous loop."""
+    A, Fd, H, B = 6, 50, 64, 4
+    params = O.synthetic_params(9, A, Fd, H, seed=11)
+    batches = [O.synthetic_batch(B, A, seed=40 + i) for i in range(8)]
+    finals = []
+    for sync in (True, False):
+        agent = make_agent(A, Fd, H, 1e-3, params, use_tb=sync, use_graph=True)
+        for i, b in enumerate(batches):
+            agent.inject_draws(b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+            agent.update(iter([(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])]), 2 * i)
+        torch.cuda.synchronize()
+        finals.append([p.detach().clone() for net in ("encoder", "actor", "critic", "critic_target")
+                       for p in getattr(agent, net).parameters()])
+    for p1, p2 in zip(*finals):
+        assert torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ensemble_members_equal_solo_agents(dev, mode):
+    """AgentEnsemble (BASELINE configs[3]): members updated concurrently on their own streams end up with exactly
+    the parameters of the same agents updated one after the other; members differ from each other (own seed)."""
+    from drqv2_b200 import DrQV2Agent
+    from drqv2_b200.ensemble import AgentEnsemble
+    A, Fd, H, B, K = 6, 50, 64, 4, 3
+    args = ((9, 84, 84), (A,), "cuda", 1e-3, Fd, H, 0.01, 2000, 2, SCHED, 0.3, True)
+    batches = [[O.synthetic_batch(B, A, seed=60 + 10 * k + i) for i in range(4)] for k in range(K)]
+    as_iter = lambda b: iter([(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])])
+    ens = AgentEnsemble(K, *args, base_seed=3, mode=mode)
+    for i in range(4):
+        ms = ens.update([as_iter(batches[k][i]) for k in range(K)], 2 * i)
+        assert len(ms) == K and all(np.isfinite(m["critic_loss"]) for m in ms)
+    ens.synchronize()
+    for k in range(K):
+        torch.manual_seed(3 + k)
+        solo = DrQV2Agent(*args, seed=3 + k, mode=mode)
+        for i in range(4):
+            solo.update(as_iter(batches[k][i]), 2 * i)
+        torch.cuda.synchronize()
+        for net in ("encoder", "actor", "critic", "critic_target"):
+            for (n1, p1), (_, p2) in zip(getattr(ens[k], net).named_parameters(), getattr(solo, net).named_parameters()):
+                assert torch.equal(p1, p2), (k, net, n1)
+    w0 = ens[0].critic.Q1[0].weight
+    assert not torch.equal(w0, ens[1].critic.Q1[0].weight)
