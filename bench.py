@@ -176,7 +176,9 @@ def run_ours(args, rank, world):
 
     def counting_call(name, *a):
         # drq_ln_tanh_bwd launches its parameter-gradient kernel only when dgamma (argument 8) is given
-        n_calls[0] += 2 if (name in two_kernel_calls or (name == "drq_ln_tanh_bwd" and a[8])) else 1
+        # the bf16 wgrad entry points skip their reduce kernel when dw (argument 4) is NULL (reduced by one launch later)
+        two = (name in two_kernel_calls and (not name.endswith("_bf16") or a[4])) or (name == "drq_ln_tanh_bwd" and a[8])
+        n_calls[0] += 2 if two else 1
         return orig_call(name, *a)
 
     import drqv2_b200._bf16 as BF
@@ -276,7 +278,7 @@ def run_ours(args, rank, world):
                                                         2 * CONV_MACS[39] * 2 * B),
                 "conv3x3_tc_kernel<dgrad>(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_bf16", d[1], st.conv_wd[0].data_ptr(), acts[0], 2 * B, d[0], B, 39, s),
                                                          2 * CONV_MACS[39] * B),
-                "conv3x3_wgrad_tc_kernel(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_bf16", acts[0], 2 * B, d[1], bw.wg_ws.data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
+                "conv3x3_wgrad_tc_kernel(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_bf16", acts[0], 2 * B, d[1], bw.wg_ws[1].data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
                                                         2 * CONV_MACS[39] * B),
             }
         else:

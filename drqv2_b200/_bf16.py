@@ -117,6 +117,11 @@ class OptSeg(C.Structure):
 OPT_PLAIN, OPT_LINEAR, OPT_TRUNK, OPT_CONV, OPT_CONV1 = 0, 1, 2, 3, 4
 
 
+class WgReduceJob(C.Structure):
+    _fields_ = [("partial", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p), ("n_images", C.c_int32),
+                ("hout", C.c_int32), ("cin", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ColsumJob(C.Structure):
     _fields_ = [("X", C.c_void_p), ("ld", C.c_int64), ("out", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
                 ("tb", C.c_int32), ("reserved", C.c_int32), ("Y", C.c_void_p)]
@@ -291,7 +296,8 @@ class Bf16Workspace:
         self.feat = TB(2 * RB, REPR_DIM, dev)                        # feature order (c/8)*9800 + yx*8 + c%8
         self.dpre = [zb(L.drq_wb_elems(B)) for _ in range(4)]
         self.cs_d = B * PLB + WB_SLACK
-        self.wg_ws = zf(max(L.drq_conv_wgrad_bf16_ws_floats(), L.drq_conv1_wgrad_bf16_ws_floats()))
+        # per-CTA weight-gradient partials of conv1..conv4, reduced by one launch at the end of the backward
+        self.wg_ws = [zf(L.drq_conv1_wgrad_bf16_ws_floats())] + [zf(L.drq_conv_wgrad_bf16_ws_floats()) for _ in range(3)]
         FP = st.FP
         self.NT = 2 * FP                                             # columns of one trunk GEMM half
         ntiles = (RB // TB_ACT) * (self.NT // 128)
@@ -430,15 +436,18 @@ def critic_pass(agent, ws, bw):
     ge = lambda k: agent._g("encoder", k)
     gemm(bw.dz.ptr(), bw.dz.units, st.trunk_ptr(st.CRITIC), st.trunk.units, GEMM_KMN, d[3], bw.cs_d, B, REPR_DIM, Fd,
          TEPI_TRUNK_DGRAD, mask=feat.ptr(), units_mask=feat.units, bn=128)
-    wsp = bw.wg_ws.data_ptr()
+    jobs = []
     for layer, hout in ((3, 35), (2, 37), (1, 39)):
         k = 2 * layer
-        call("drq_conv3x3_wgrad_bf16", acts[layer - 1], 2 * B, d[layer], wsp, ge(f"convnet.{k}.weight"),
-             ge(f"convnet.{k}.bias"), B, hout, s)
+        call("drq_conv3x3_wgrad_bf16", acts[layer - 1], 2 * B, d[layer], bw.wg_ws[layer].data_ptr(), None, None, B, hout, s)
+        jobs.append(WgReduceJob(bw.wg_ws[layer].data_ptr(), ge(f"convnet.{k}.weight"), ge(f"convnet.{k}.bias"), B, hout, 0, 0))
         call("drq_conv3x3_dgrad_bf16", d[layer], st.conv_wd[layer - 1].data_ptr(), acts[layer - 1], 2 * B,
              d[layer - 1], B, hout, s)
-    call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], wsp, ge("convnet.0.weight"),
-         ge("convnet.0.bias"), B, agent.obs_shape[0], agent.aug.pad, s)
+    call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+         B, agent.obs_shape[0], agent.aug.pad, s)
+    jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], 0))
+    arr = (WgReduceJob * len(jobs))(*jobs)
+    call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s)        # all four layers' partials -> dW, db in one launch
     # critic_opt.step(); encoder_opt.step(); refresh their bf16 operand copies
     agent._sync_grads("encoder", "critic")          # data-parallel: mean over ranks (no-op otherwise)
     st.step_critic_encoder()

@@ -46,6 +46,7 @@ SIGNATURES = {
     "drq_debug_conv_stamps": [P],
     "drq_debug_conv1_stamps": [P],
     "drq_pack_multi": [P, I, P],
+    "drq_conv_wgrad_reduce_multi": [P, I, P],
     "drq_colsum_multi": [P, I, P],
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],

@@ -26,6 +26,7 @@
 // position), warp 16 issues UMMAs (and bulk-loads the gradient tile in wgrad), warps 17..20 run the
 // epilogue, warp 21 bulk-copies the source rows of the next tiles (4 stages ahead).
 #include "pack.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace drq {
 
@@ -411,22 +412,7 @@ conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin, flo
     pdl_trigger();
     pdl_wait();
     __shared__ float red[8][33], redb[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + tx;                 // 96 = 3 x 32: a block stays inside one co
-    const int co = i / kC1K, k = i - co * kC1K;
-    float s = 0.f, sb = 0.f;
-    for (int g = ty; g < G; g += 8) {
-        s += partial[(long long)g * (32 * kC1K) + i];
-        sb += partial[(long long)g * (32 * kC1K) + co * kC1K + cin * 9];
-    }
-    red[ty][tx] = s; redb[ty][tx] = sb;
-    __syncthreads();
-    if (ty == 0 && k <= cin * 9) {
-        float t = red[0][tx], tb = redb[0][tx];
-#pragma unroll
-        for (int r = 1; r < 8; ++r) { t += red[r][tx]; tb += redb[r][tx]; }
-        if (k < cin * 9) dw[co * cin * 9 + k] = fmaf(t, kC1Scale, kC1Shift * tb); else db[co] = t;
-    }
+    conv1_reduce_block(partial, G, cin, dw, db, blockIdx.x, red, redb);
 }
 
 constexpr size_t kConv1FwdSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * kC1ABytes +
@@ -475,7 +461,7 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void) { return 148ll * 32 * kC1K; }
 
 int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
                          float* dw, float* db, int N, int cin, int pad, void* stream) {
-    DRQ_REQUIRE(obs && dpre && partial && dw && db, "conv1_wgrad_bf16: null pointer");
+    DRQ_REQUIRE(obs && dpre && partial && (dw != nullptr) == (db != nullptr), "conv1_wgrad_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0 && pad <= 4, "conv1_wgrad_bf16: bad dims (cin <= 10, pad <= 4)");
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 9>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 0>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
@@ -485,12 +471,12 @@ int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_
     a.cs_d = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
     a.partial = partial;
     a.n_images = N;
-    const int tiles = N * 14;
-    const int G = tiles < 148 ? tiles : 148;
+    const int G = conv1_wgrad_ctas(N);
     if (cin == 9) launch_k(conv1_tc_kernel<true, 9>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
     else launch_k(conv1_tc_kernel<true, 0>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
     if (int rc = check_launch("conv1_tc_kernel<wgrad>")) return rc;
-    launch_k(conv1_wgrad_reduce_kernel, 32 * kC1K / 32, 256, 0, as_stream(stream), partial, G, cin, dw, db);
+    if (!dw) return DRQ_OK;                                   // partials only: reduced later by drq_conv_wgrad_reduce_multi
+    launch_k(conv1_wgrad_reduce_kernel, kC1ReduceBlocks, 256, 0, as_stream(stream), partial, G, cin, dw, db);
     return check_launch("conv1_wgrad_reduce_kernel");
 }
 

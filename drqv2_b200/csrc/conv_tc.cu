@@ -14,6 +14,7 @@
 // Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = UMMA issuer, warps 2..5 =
 // epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> coalesced 16-byte stores).
 #include "pack.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace drq {
 
@@ -269,7 +270,8 @@ constexpr int kWgPlane = kStageRows * 16;                  // one MN unit: 216 p
 constexpr int kWgABytes = 13 * kWgPlane;                   // 3 shifted windows x 4 channel blocks + ones
 constexpr int kWgStageBytes = kWgABytes + 4 * kWgDRows * 16;
 constexpr int kWgAcc = 10;
-constexpr int kWgPartial = kWgAcc * 32 * 32;               // floats per CTA: [9 taps + bias][ci][co]
+constexpr int kWgPartial = kWgAcc * 32 * 32;
+static_assert(kWgPartial == kWgPartialFloats, "wgrad_reduce.cuh");               // floats per CTA: [9 taps + bias][ci][co]
 
 struct WgradTcArgs {
     const __nv_bfloat16* in; long long cs_in;
@@ -381,33 +383,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
     if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
-// dw[co][ci][tap] = sum_g partial[g][tap][ci][co]; db[co] = sum_g partial[g][9][0][co].  Block = 32 outputs x 8
-// slices of the G partials (fixed association), combined in fixed order.
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int G, float* __restrict__ dw,
                                                               float* __restrict__ db) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + tx;
-    const bool live = i < 9 * 32 * 32 + 32;
-    const int src = i < 9216 ? i : 9 * 1024 + (i - 9216);
-    float s = 0.f;
-    if (live)
-        for (int g = ty; g < G; g += 8) s += partial[(long long)g * kWgPartial + src];
-    red[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0 && live) {
-        float t = red[0][tx];
-#pragma unroll
-        for (int r = 1; r < 8; ++r) t += red[r][tx];
-        if (i < 9216) {
-            const int tap = i / 1024, ci = (i / 32) % 32, co = i % 32;
-            dw[(co * 32 + ci) * 9 + tap] = t;
-        } else {
-            db[i - 9216] = t;
-        }
-    }
+    wgrad3x3_reduce_block(partial, G, dw, db, blockIdx.x, red);
 }
 
 // + 3 planes of tail padding: MN units 13..15 of the last stage's A operand (results ignored) must stay inside
@@ -494,7 +475,7 @@ int64_t drq_conv_wgrad_bf16_ws_floats(void) { return 148ll * kWgPartial; }
 
 int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, float* partial, float* dw,
                            float* db, int N, int hout, void* stream) {
-    DRQ_REQUIRE(in && dpre && partial && dw && db, "conv3x3_wgrad_bf16: null pointer");
+    DRQ_REQUIRE(in && dpre && partial && (dw != nullptr) == (db != nullptr), "conv3x3_wgrad_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && n_in >= N && hout > 0 && hout <= kPW - 2, "conv3x3_wgrad_bf16: bad dims");
     if (int rc = ensure_smem((const void*)conv3x3_wgrad_tc_kernel, kWgradTcSmem, "conv3x3_wgrad_bf16")) return rc;
     WgradTcArgs a{};
@@ -505,10 +486,11 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     a.partial = partial;
     a.n_images = N;
     a.ntiles = (hout * kPW + kTM - 1) / kTM;
-    const int G = conv_tc_grid(N * a.ntiles);                 // tile walkers, one per SM
+    const int G = conv_wgrad_ctas(N, hout);                   // tile walkers, one per SM
     launch_k(conv3x3_wgrad_tc_kernel, G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;
-    launch_k(wgrad_tc_reduce_kernel, (9248 + 31) / 32, 256, 0, as_stream(stream), partial, G, dw, db);
+    if (!dw) return DRQ_OK;                                   // partials only: reduced later by drq_conv_wgrad_reduce_multi
+    launch_k(wgrad_tc_reduce_kernel, kWgReduceBlocks, 256, 0, as_stream(stream), partial, G, dw, db);
     return check_launch("wgrad_tc_reduce_kernel");
 }
 

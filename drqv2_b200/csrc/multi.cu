@@ -3,6 +3,7 @@
 // gradients of a backward pass (drq_colsum_multi).  These kernels are microseconds of work each; as
 // separate launches their cost is launch latency and cold instruction fetch.
 #include "pack.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace drq {
 
@@ -86,6 +87,22 @@ __global__ void __launch_bounds__(256) colsum_multi_kernel(const ColsumJobs jobs
     }
 }
 
+struct WgReduceJobs { drq_wgrad_reduce_job j[DRQ_WGRAD_REDUCE_MAX_JOBS]; int G[DRQ_WGRAD_REDUCE_MAX_JOBS]; };
+
+// all weight-gradient partial reductions of the encoder backward in one launch: blockIdx.y = layer
+__global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const WgReduceJobs jobs) {
+    __shared__ float red[8][33], redb[8][33];
+    pdl_trigger();
+    pdl_wait();
+    const drq_wgrad_reduce_job& jb = jobs.j[blockIdx.y];
+    const int G = jobs.G[blockIdx.y];
+    if (jb.cin > 0) {
+        if ((int)blockIdx.x < kC1ReduceBlocks) conv1_reduce_block(jb.partial, G, jb.cin, jb.dw, jb.db, blockIdx.x, red, redb);
+    } else {
+        wgrad3x3_reduce_block(jb.partial, G, jb.dw, jb.db, blockIdx.x, red);
+    }
+}
+
 }  // namespace drq
 
 using namespace drq;
@@ -133,6 +150,20 @@ int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream) {
     }
     launch_k(colsum_multi_kernel, dim3((nmax + 31) / 32, njobs), 256, 0, as_stream(stream), cj);
     return check_launch("colsum_multi_kernel");
+}
+
+int drq_conv_wgrad_reduce_multi(const drq_wgrad_reduce_job* jobs, int njobs, void* stream) {
+    DRQ_REQUIRE(jobs && njobs >= 1 && njobs <= DRQ_WGRAD_REDUCE_MAX_JOBS, "wgrad_reduce_multi: 1..%d jobs", DRQ_WGRAD_REDUCE_MAX_JOBS);
+    WgReduceJobs wj{};
+    for (int i = 0; i < njobs; ++i) {
+        const drq_wgrad_reduce_job& jb = jobs[i];
+        DRQ_REQUIRE(jb.partial && jb.dw && jb.db && jb.n_images > 0 && jb.cin >= 0 && jb.cin * 9 + 1 <= 96 &&
+                    (jb.cin > 0 || (jb.hout > 0 && jb.hout <= DRQ_PW - 2)), "wgrad_reduce_multi: bad job %d", i);
+        wj.j[i] = jb;
+        wj.G[i] = jb.cin > 0 ? conv1_wgrad_ctas(jb.n_images) : conv_wgrad_ctas(jb.n_images, jb.hout);
+    }
+    launch_k(wgrad_reduce_multi_kernel, dim3(kWgReduceBlocks, njobs), 256, 0, as_stream(stream), wj);
+    return check_launch("wgrad_reduce_multi_kernel");
 }
 
 }  // extern "C"
