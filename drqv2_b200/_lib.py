@@ -24,6 +24,8 @@ SIGNATURES = {
     "drq_ring_gather_nstep": [P, P, P, P, L, I, I, I, P, P, I, I, F, P, P, P, P, P, P],
     "drq_ring_sample": [P, P, I, U, P, P, P, I, P],
     "drq_rng_update_draws": [U, P, I, P, P, P, P, I, I, P],
+    "drq_ring_sample_step": [P, P, I, U, P, P, P, I, P],
+    "drq_update_prologue": [P, I, P, P, U, P, I, P, P, P, P, I, I, P],
     "drq_rng_normal_f32": [U, P, P, I, P],
     "drq_counter_advance": [P, P],
     "drq_scalars_fetch": [P, I, P, P, P],

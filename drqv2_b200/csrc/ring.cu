@@ -94,16 +94,10 @@ ring_gather_kernel(const uint8_t* __restrict__ frames, const float* __restrict__
     }
 }
 
-__global__ void ring_sample_kernel(const int* __restrict__ ep_table, const int* __restrict__ n_episodes, int nstep,
-                                   unsigned long long seed, const unsigned long long* counter,
-                                   int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
-    pdl_trigger();
-    pdl_wait();
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+__device__ __forceinline__ void ring_sample_elem(const int* __restrict__ ep_table, int E, int nstep, unsigned long long seed,
+                                                 unsigned long long c, int* __restrict__ ep_start_out, int* __restrict__ idx_out, int b) {
     uint32_t r[4];
-    const int E = *n_episodes;
-    Philox::gen(seed, (*counter << 3) | 0ull, (uint64_t)b, r);
+    Philox::gen(seed, (c << 3) | 0ull, (uint64_t)b, r);
     // unbiased enough for E, len << 2^32: multiply-shift range reduction
     const int e = (int)(((uint64_t)r[0] * (uint64_t)E) >> 32);
     const int start = ep_table[2 * e], len = ep_table[2 * e + 1];
@@ -113,15 +107,42 @@ __global__ void ring_sample_kernel(const int* __restrict__ ep_table, const int* 
     idx_out[b] = i;
 }
 
-// stream ids: 1 shift_obs, 2 shift_next, 3 eps_critic, 4 eps_actor
-__global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned long long* counter,
-                                        int pad, int* __restrict__ shift_obs,
-                                        int* __restrict__ shift_next, float* __restrict__ eps_c,
-                                        float* __restrict__ eps_a, int B, int A) {
+__global__ void ring_sample_kernel(const int* __restrict__ ep_table, const int* __restrict__ n_episodes, int nstep,
+                                   unsigned long long seed, const unsigned long long* counter,
+                                   int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
     pdl_trigger();
     pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ring_sample_elem(ep_table, *n_episodes, nstep, seed, *counter, ep_start_out, idx_out, b);
+}
+
+// the same draw followed by counter += 1: one block, so that the increment can follow every read
+__global__ void __launch_bounds__(256) ring_sample_step_kernel(const int* __restrict__ ep_table, const int* __restrict__ n_episodes,
+                                                               int nstep, unsigned long long seed, unsigned long long* counter,
+                                                               int* __restrict__ ep_start_out, int* __restrict__ idx_out, int B) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned long long c = *counter;
+    const int E = *n_episodes;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) ring_sample_elem(ep_table, E, nstep, seed, c, ep_start_out, idx_out, b);
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = c + 1ull;
+}
+
+// stream ids: 1 shift_obs, 2 shift_next, 3 eps_critic, 4 eps_actor
+__device__ __forceinline__ float box_muller(uint32_t a, uint32_t b, bool odd) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, co;
+    sincospif(2.0f * u2, &s, &co);
+    return odd ? rad * s : rad * co;
+}
+
+__device__ __forceinline__ void update_draws_elem(unsigned long long seed, unsigned long long c, int pad, int* __restrict__ shift_obs,
+                                                  int* __restrict__ shift_next, float* __restrict__ eps_c,
+                                                  float* __restrict__ eps_a, int B, int A, int i) {
     const unsigned range = 2 * pad + 1;
     if (i < B) {
         uint32_t r[4];
@@ -131,27 +152,44 @@ __global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned 
         shift_next[2 * i] = (int)(((uint64_t)r[2] * range) >> 32);
         shift_next[2 * i + 1] = (int)(((uint64_t)r[3] * range) >> 32);
     }
-    const int n = B * A;
     // Box-Muller: 4 words -> 2 pairs -> 4 normals; element i uses pair (i>>1) of stream 3/4.
-    if (i < n) {
+    if (i < B * A) {
         uint32_t r[4];
         Philox::gen(seed, (c << 3) | 3ull, (uint64_t)(i >> 1), r);
-        {
-            const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float rad = sqrtf(-2.0f * logf(u1));
-            float s, co;
-            sincospif(2.0f * u2, &s, &co);
-            eps_c[i] = (i & 1) ? rad * s : rad * co;
-        }
-        {
-            const float u1 = ((float)(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float u2 = ((float)(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float rad = sqrtf(-2.0f * logf(u1));
-            float s, co;
-            sincospif(2.0f * u2, &s, &co);
-            eps_a[i] = (i & 1) ? rad * s : rad * co;
-        }
+        eps_c[i] = box_muller(r[0], r[1], i & 1);
+        eps_a[i] = box_muller(r[2], r[3], i & 1);
+    }
+}
+
+__global__ void rng_update_draws_kernel(unsigned long long seed, const unsigned long long* counter,
+                                        int pad, int* __restrict__ shift_obs,
+                                        int* __restrict__ shift_next, float* __restrict__ eps_c,
+                                        float* __restrict__ eps_a, int B, int A) {
+    pdl_trigger();
+    pdl_wait();
+    update_draws_elem(seed, *counter, pad, shift_obs, shift_next, eps_c, eps_a, B, A, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Everything an update needs before its first real kernel, in one block: the per-update host scalars
+// (scalars_fetch_kernel), the four random draws (rng_update_draws_kernel) and counter += 1.
+__global__ void __launch_bounds__(1024) update_prologue_kernel(const float* scal_ring, int slots, unsigned long long* cursor,
+                                                               float* scal_out, unsigned long long seed, unsigned long long* counter,
+                                                               int pad, int* __restrict__ shift_obs, int* __restrict__ shift_next,
+                                                               float* __restrict__ eps_c, float* __restrict__ eps_a, int B, int A) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x < 16) {
+        const unsigned long long cur = *cursor;
+        scal_out[threadIdx.x] = *reinterpret_cast<const volatile float*>(scal_ring + (cur % (unsigned long long)slots) * 16 + threadIdx.x);
+        __syncwarp(0xFFFFu);
+        if (threadIdx.x == 0) *cursor = cur + 1ull;
+    }
+    if (shift_obs) {
+        const unsigned long long c = *counter;
+        const int n = B * A > B ? B * A : B;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) update_draws_elem(seed, c, pad, shift_obs, shift_next, eps_c, eps_a, B, A, i);
+        __syncthreads();
+        if (threadIdx.x == 0) *counter = c + 1ull;
     }
 }
 
@@ -300,6 +338,26 @@ int drq_counter_advance(uint64_t* counter, void* stream) {
     DRQ_REQUIRE(counter, "counter_advance: null pointer");
     launch_k(counter_advance_kernel, 1, 1, 0, as_stream(stream), (unsigned long long*)counter);
     return check_launch("counter_advance_kernel");
+}
+
+int drq_ring_sample_step(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed, uint64_t* counter,
+                         int32_t* ep_start_out, int32_t* idx_out, int B, void* stream) {
+    DRQ_REQUIRE(ep_table && n_episodes && counter && ep_start_out && idx_out, "ring_sample_step: null pointer");
+    DRQ_REQUIRE(B > 0 && nstep > 0, "ring_sample_step: bad dims");
+    launch_k(ring_sample_step_kernel, 1, 256, 0, as_stream(stream), ep_table, n_episodes, nstep, (unsigned long long)seed,
+             (unsigned long long*)counter, ep_start_out, idx_out, B);
+    return check_launch("ring_sample_step_kernel");
+}
+
+int drq_update_prologue(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed, uint64_t* counter,
+                        int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic, float* eps_actor, int B, int A,
+                        void* stream) {
+    DRQ_REQUIRE(scal_ring && cursor && scal_out && slots > 0, "update_prologue: bad scalar ring");
+    const bool draws = shift_obs != nullptr;
+    DRQ_REQUIRE(!draws || (counter && shift_next && eps_critic && eps_actor && B > 0 && A > 0 && pad >= 0), "update_prologue: bad draw arguments");
+    launch_k(update_prologue_kernel, 1, 1024, 0, as_stream(stream), scal_ring, slots, (unsigned long long*)cursor, scal_out,
+             (unsigned long long)seed, (unsigned long long*)counter, pad, shift_obs, shift_next, eps_critic, eps_actor, B, A);
+    return check_launch("update_prologue_kernel");
 }
 
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream) {

@@ -831,14 +831,14 @@ class DrQV2Agent:
         """Everything of one update that runs on the device, in stream order; no host sync."""
         B = ws.B
         s = _stream()
-        self._fetch_scalars()
+        # one launch: this update's host scalars (Adam bias corrections, stddev) out of the pinned ring and - unless
+        # the draws were injected - the four random draws of drqv2.py:34 (x2) and utils.py:119 (x2), counter += 1
+        call("drq_update_prologue", self._scal_ring.data_ptr(), self._SCAL_SLOTS, self._scal_cursor.data_ptr(),
+             self._scal_dev.data_ptr(), self._seed, self._counter.data_ptr(), self.aug.pad,
+             ws.shift[:B].data_ptr() if draw else None, ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
+             B, self.action_dim, s)
         if fetch is not None:
             fetch()
-        if draw:
-            call("drq_rng_update_draws", self._seed, self._counter.data_ptr(), self.aug.pad,
-                 ws.shift[:B].data_ptr(), ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
-                 B, self.action_dim, s)
-            call("drq_counter_advance", self._counter.data_ptr(), s)
         if self.mode == "bf16":
             bw = self.bf16_workspace(B)
             _bf16.encode(self, ws, bw)

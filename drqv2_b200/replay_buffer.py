@@ -279,9 +279,8 @@ class RingIterator:
         if ep_start is None:
             if getattr(ring, "_n_eligible", 0) == 0:
                 raise RuntimeError("replay ring has no episode long enough to sample from")
-            call("drq_ring_sample", ring.ep_table.data_ptr(), ring.n_episodes.data_ptr(), l.nstep, l.seed,
-                 l._counter.data_ptr(), l._ep_start.data_ptr(), l._idx.data_ptr(), B, s)
-            call("drq_counter_advance", l._counter.data_ptr(), s)
+            call("drq_ring_sample_step", ring.ep_table.data_ptr(), ring.n_episodes.data_ptr(), l.nstep, l.seed,
+                 l._counter.data_ptr(), l._ep_start.data_ptr(), l._idx.data_ptr(), B, s)     # draws, then counter += 1
             ep_start, idx = l._ep_start, l._idx
         call("drq_ring_gather_nstep", ring.frames.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
              ring.discount.data_ptr(), ring.capacity, ring.frame_c, ring.stack, ring.A, ep_start.data_ptr(),

@@ -126,6 +126,16 @@ int drq_counter_advance(uint64_t* counter, void* stream);
  * a host that enqueues updates faster than the device runs them.  `cursor` is a device counter. */
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream);
 
+/* drq_ring_sample followed by *counter += 1 in one launch (one block). */
+int drq_ring_sample_step(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed, uint64_t* counter,
+                         int32_t* ep_start_out, int32_t* idx_out, int B, void* stream);
+
+/* everything an update needs before its first real kernel, in one launch (one block): drq_scalars_fetch, then -
+ * unless shift_obs == NULL (injected draws) - drq_rng_update_draws and *counter += 1. */
+int drq_update_prologue(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed, uint64_t* counter,
+                        int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic, float* eps_actor, int B, int A,
+                        void* stream);
+
 /* ------------------------------------------------------------------ augmentation */
 
 /* RandomShiftsAug as an exact integer shift (drqv2.py:19-45 in intent):
