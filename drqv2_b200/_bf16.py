@@ -240,8 +240,11 @@ class Bf16State:
         enc = {"convnet.0.weight": (OPT_CONV1, ag.obs_shape[0], 0, self.conv1_w.data_ptr(), None)}
         for i, k in enumerate((2, 4, 6)):
             enc[f"convnet.{k}.weight"] = (OPT_CONV, 0, 0, self.conv_wf[i].data_ptr(), self.conv_wd[i].data_ptr())
-        segs = self._segments(ag.encoder, a.offsets["encoder"], 0, 0, enc)
-        segs += self._segments(ag.critic, a.offsets["critic"], 0, 0, self._critic_like_packed(self.CRITIC, 0))
+        segs_e = self._segments(ag.encoder, a.offsets["encoder"], 0, 0, enc)
+        segs_c = self._segments(ag.critic, a.offsets["critic"], 0, 0, self._critic_like_packed(self.CRITIC, 0))
+        self.plan_encoder = (OptSeg * len(segs_e))(*segs_e)
+        self.plan_critic_only = (OptSeg * len(segs_c))(*segs_c)
+        segs = segs_e + segs_c
         self.plan_critic = (OptSeg * len(segs))(*segs)
         act = {"trunk.0.weight": (OPT_TRUNK, Fd, REPR_DIM, self.trunk_ptr(self.ACTOR), None),
                "policy.0.weight": (OPT_LINEAR, H, Fd, self.p0.ptr(), None),
@@ -257,6 +260,20 @@ class Bf16State:
         a = ag._arena
         call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
              ag._scal_dev.data_ptr(), None, None, 0.0, 0.0, self.plan_critic, len(self.plan_critic), _stream())
+
+    def _step(self, plan):
+        ag = self.agent
+        a = ag._arena
+        call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
+             ag._scal_dev.data_ptr(), None, None, 0.0, 0.0, plan, len(plan), _stream())
+
+    def step_critic(self):
+        """critic_opt.step() (drqv2.py:201) and the critic's bf16 operand copies."""
+        self._step(self.plan_critic_only)
+
+    def step_encoder(self):
+        """encoder_opt.step() (drqv2.py:202) and the encoder's bf16 operand copies."""
+        self._step(self.plan_encoder)
 
     def step_actor_target(self):
         """actor_opt.step() and the soft target update (drqv2.py:221,259-260) and their bf16 operand copies."""
@@ -436,21 +453,37 @@ def critic_pass(agent, ws, bw):
     ge = lambda k: agent._g("encoder", k)
     gemm(bw.dz.ptr(), bw.dz.units, st.trunk_ptr(st.CRITIC), st.trunk.units, GEMM_KMN, d[3], bw.cs_d, B, REPR_DIM, Fd,
          TEPI_TRUNK_DGRAD, mask=feat.ptr(), units_mask=feat.units, bn=128)
-    jobs = []
-    for layer, hout in ((3, 35), (2, 37), (1, 39)):
-        k = 2 * layer
-        call("drq_conv3x3_wgrad_bf16", acts[layer - 1], 2 * B, d[layer], bw.wg_ws[layer].data_ptr(), None, None, B, hout, s)
-        jobs.append(WgReduceJob(bw.wg_ws[layer].data_ptr(), ge(f"convnet.{k}.weight"), ge(f"convnet.{k}.bias"), B, hout, 0, 0))
-        call("drq_conv3x3_dgrad_bf16", d[layer], st.conv_wd[layer - 1].data_ptr(), acts[layer - 1], 2 * B,
-             d[layer - 1], B, hout, s)
-    call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
-         B, agent.obs_shape[0], agent.aug.pad, s)
-    jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], 0))
-    arr = (WgReduceJob * len(jobs))(*jobs)
-    call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s)        # all four layers' partials -> dW, db in one launch
-    # critic_opt.step(); encoder_opt.step(); refresh their bf16 operand copies
-    agent._sync_grads("encoder", "critic")          # data-parallel: mean over ranks (no-op otherwise)
-    st.step_critic_encoder()
+    def encoder_backward():
+        s2 = _stream()
+        jobs = []
+        for layer, hout in ((3, 35), (2, 37), (1, 39)):
+            k = 2 * layer
+            call("drq_conv3x3_wgrad_bf16", acts[layer - 1], 2 * B, d[layer], bw.wg_ws[layer].data_ptr(), None, None, B, hout, s2)
+            jobs.append(WgReduceJob(bw.wg_ws[layer].data_ptr(), ge(f"convnet.{k}.weight"), ge(f"convnet.{k}.bias"), B, hout, 0, 0))
+            call("drq_conv3x3_dgrad_bf16", d[layer], st.conv_wd[layer - 1].data_ptr(), acts[layer - 1], 2 * B,
+                 d[layer - 1], B, hout, s2)
+        call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+             B, agent.obs_shape[0], agent.aug.pad, s2)
+        jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], 0))
+        arr = (WgReduceJob * len(jobs))(*jobs)
+        call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s2)   # all four layers' partials -> dW, db in one launch
+
+    side = agent._encoder_side_stream()
+    if side is None:
+        encoder_backward()
+        # critic_opt.step(); encoder_opt.step(); refresh their bf16 operand copies
+        agent._sync_grads("encoder", "critic")      # data-parallel: mean over ranks (no-op otherwise)
+        st.step_critic_encoder()
+        return
+    # The actor pass needs the stepped critic but nothing of the encoder's backward (it works on this update's
+    # features, drqv2.py:256), so the encoder backward and encoder_opt.step() run on a second stream beside
+    # critic_opt.step() and the whole actor pass; DrQV2Agent._update_body joins the streams at the end.
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        encoder_backward()
+        st.step_encoder()
+    st.step_critic()
 
 
 def actor_pass(agent, ws, bw):

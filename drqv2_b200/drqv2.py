@@ -411,6 +411,9 @@ class DrQV2Agent:
         self.lr = lr
         self.use_cuda_graph = use_cuda_graph
         self.prefetch = bool(prefetch)
+        # bf16 mode: encoder backward + encoder_opt.step() on a second stream beside the actor pass (DRQV2_B200_OVERLAP=0: in line)
+        self.overlap_encoder_backward = os.environ.get("DRQV2_B200_OVERLAP", "1") != "0"
+        self._side_stream = None
         self.mode = mode or os.environ.get("DRQV2_B200_MODE", "fp32")
         if self.mode not in ("fp32", "bf16"):
             raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
@@ -471,6 +474,7 @@ class DrQV2Agent:
         st["_bf16"] = None
         st["_prefetch"] = None
         st["_scal_events"] = [None, None]
+        st["_side_stream"] = None
         return st
 
     def __setstate__(self, st):
@@ -827,6 +831,15 @@ class DrQV2Agent:
             self._scal_events[slot // half] = ev
         self._scal_enq += 1
 
+    def _encoder_side_stream(self):
+        """Second stream for the encoder backward + encoder_opt.step() of the bf16 update (None: run in line).
+        Data-parallel updates keep one stream: their gradient all-reduce covers encoder and critic together."""
+        if not self.overlap_encoder_backward or self.data_parallel or self.mode != "bf16":
+            return None
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self._dev)
+        return self._side_stream
+
     def _update_body(self, ws, fetch=None, draw=True):
         """Everything of one update that runs on the device, in stream order; no host sync."""
         B = ws.B
@@ -844,6 +857,9 @@ class DrQV2Agent:
             _bf16.encode(self, ws, bw)
             _bf16.critic_pass(self, ws, bw)
             _bf16.actor_pass(self, ws, bw)
+            side = self._encoder_side_stream()
+            if side is not None:                    # the encoder backward ran beside the actor pass
+                torch.cuda.current_stream().wait_stream(side)
             return
         self._encode(ws)
         self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=True)
