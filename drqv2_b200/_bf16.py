@@ -381,8 +381,35 @@ def actor_mlp_fwd(agent, hA, p1, p2, mu_pre, M):
     gemm(p2.ptr(), p2.units, w4.ptr(), w4.units, GEMM_KK, mu_pre, A, M, A, H, TEPI_F32, bias=pa("policy.4.bias"))
 
 
+class _Beside:
+    """Weight-gradient work beside the data-gradient chain: `with beside:` enqueues on the agent's third stream
+    after everything enqueued so far on the main stream; `beside.join()` makes the main stream wait for it.
+    Without a third stream (data-parallel mode, DRQV2_B200_OVERLAP=0) both are no-ops."""
+
+    def __init__(self, agent):
+        self.side = agent._wgrad_side_stream()
+        self.main = torch.cuda.current_stream()
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 def critic_pass(agent, ws, bw):
     st, s = agent._bf16, _stream()
+    beside = _Beside(agent)
     B, A, Fd, H = ws.B, agent.action_dim, agent.feature_dim, agent.hidden_dim
     RB, FP, NT = bw.RB, st.FP, bw.NT
     pc = lambda k: agent._p("critic", k)
@@ -424,12 +451,14 @@ def critic_pass(agent, ws, bw):
     call("drq_q_head_bwd_loss_bf16", 1, q, q + F32 * 2 * B, ws.reward.data_ptr(), ws.discount.data_ptr(),
          ws.target_q.data_ptr(), ws.metrics.data_ptr(), c2.ptr(), U, HS, pc("Q1.4.weight"), dc2.ptr(),
          gc("Q1.4.weight"), gc("Q1.4.bias"), B, H, qs_f, s)
-    gemm(dc2.ptr(), U, c1.ptr(), U, GEMM_MNMN, gc("Q1.2.weight"), H, H, H, B, TEPI_F32, batch=2,
-         strides=_strides((HS, HS, qs_f, 0, 0)), bn=128)
+    with beside:
+        gemm(dc2.ptr(), U, c1.ptr(), U, GEMM_MNMN, gc("Q1.2.weight"), H, H, H, B, TEPI_F32, batch=2,
+             strides=_strides((HS, HS, qs_f, 0, 0)), bn=128)
     gemm(dc2.ptr(), U, w2.ptr(), w2.units, GEMM_KMN, dc1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=c1.ptr(), units_mask=U,
          batch=2, strides=_strides((HS, w2.stride, HS, 0, HS)))
-    gemm(dc1.ptr(), U, xC.ptr(0), xC.units, GEMM_MNMN, gc("Q1.0.weight"), Fd + A, H, Fd + A, B, TEPI_F32, batch=2,
-         strides=_strides((HS, 0, qs_f, 0, 0)))
+    with beside:
+        gemm(dc1.ptr(), U, xC.ptr(0), xC.units, GEMM_MNMN, gc("Q1.0.weight"), Fd + A, H, Fd + A, B, TEPI_F32, batch=2,
+             strides=_strides((HS, 0, qs_f, 0, 0)))
     # d[h] = sum over heads and K chunks of dc1 @ W0[:, :F]: partial planes, summed by the consumer
     PS = B * (Fd + A)
     gemm(dc1.ptr(), U, w0.ptr(), w0.units, GEMM_KMN, bw.dxf.data_ptr(), Fd + A, B, Fd, H, TEPI_F32, batch=2,
@@ -438,15 +467,16 @@ def critic_pass(agent, ws, bw):
     call("drq_ln_tanh_bwd", bw.dxf.data_ptr(), Fd + A, ws.xC.data_ptr(), Fd + A, ws.xhatC.data_ptr(),
          ws.rstdC.data_ptr(), pc("trunk.1.weight"), ws.dz.data_ptr(), None, None,
          bw.dz.ptr(), bw.dz.units, B, Fd, 2 * bw.SX, PS, s)
-    gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, gc("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
-         TEPI_TRUNK_WGRAD, bn=128)
-    # all bias gradients of the critic backward in one launch
-    colsum_multi([ColsumJob(dc2.ptr(0), U, gc("Q1.2.bias"), B, H, 1, 0), ColsumJob(dc2.ptr(1), U, gc("Q2.2.bias"), B, H, 1, 0),
-                  ColsumJob(dc1.ptr(0), U, gc("Q1.0.bias"), B, H, 1, 0), ColsumJob(dc1.ptr(1), U, gc("Q2.0.bias"), B, H, 1, 0),
-                  ColsumJob(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 0, 0),
-                  # LayerNorm affine: dgamma = sum_b dy * xhat, dbeta = sum_b dy (dy staged behind dz by drq_ln_tanh_bwd)
-                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.weight"), B, Fd, 0, 0, ws.xhatC.data_ptr()),
-                  ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.bias"), B, Fd, 0, 0)])
+    with beside:
+        gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, gc("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
+             TEPI_TRUNK_WGRAD, bn=128)
+        # all bias gradients of the critic backward in one launch
+        colsum_multi([ColsumJob(dc2.ptr(0), U, gc("Q1.2.bias"), B, H, 1, 0), ColsumJob(dc2.ptr(1), U, gc("Q2.2.bias"), B, H, 1, 0),
+                      ColsumJob(dc1.ptr(0), U, gc("Q1.0.bias"), B, H, 1, 0), ColsumJob(dc1.ptr(1), U, gc("Q2.0.bias"), B, H, 1, 0),
+                      ColsumJob(ws.dz.data_ptr(), Fd, gc("trunk.0.bias"), B, Fd, 0, 0),
+                      # LayerNorm affine: dgamma = sum_b dy * xhat, dbeta = sum_b dy (dy staged behind dz by drq_ln_tanh_bwd)
+                      ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.weight"), B, Fd, 0, 0, ws.xhatC.data_ptr()),
+                      ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, gc("trunk.1.bias"), B, Fd, 0, 0)])
     # ---- encoder backward
     d = [t.data_ptr() for t in bw.dpre]
     acts = [t.data_ptr() for t in bw.acts]
@@ -468,6 +498,7 @@ def critic_pass(agent, ws, bw):
         arr = (WgReduceJob * len(jobs))(*jobs)
         call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s2)   # all four layers' partials -> dW, db in one launch
 
+    beside.join()                                   # the critic's weight gradients are complete
     side = agent._encoder_side_stream()
     if side is None:
         encoder_backward()
@@ -490,6 +521,7 @@ def actor_pass(agent, ws, bw):
     """update_actor (drqv2.py:206-228).  The actor's own forward on obs already ran with the critic pass
     (its parameters have not changed since); here: sample, the stepped critic's Q, and the backward."""
     st, s = agent._bf16, _stream()
+    beside = _Beside(agent)
     B, A, Fd, H = ws.B, agent.action_dim, agent.feature_dim, agent.hidden_dim
     FP = st.FP
     pc = lambda k: agent._p("critic", k)
@@ -526,23 +558,28 @@ def actor_pass(agent, ws, bw):
     # actor MLP backward (activations of the obs rows, saved by the forward in the critic pass)
     dmu, hA, p1, p2, dp1, dp2 = bw.dmu, bw.hA, bw.p1, bw.p2, bw.dp1, bw.dp2
     a0, a2, a4 = st.p0, st.p2, st.p4
-    gemm(dmu.ptr(), dmu.units, p2.ptr(), U, GEMM_MNMN, ga("policy.4.weight"), H, A, H, B, TEPI_F32, bn=128)
+    with beside:
+        gemm(dmu.ptr(), dmu.units, p2.ptr(), U, GEMM_MNMN, ga("policy.4.weight"), H, A, H, B, TEPI_F32, bn=128)
     gemm(dmu.ptr(), dmu.units, a4.ptr(), a4.units, GEMM_KMN, dp2.ptr(), U, B, H, A, TEPI_MASK_BF16, mask=p2.ptr(),
          units_mask=U)
-    gemm(dp2.ptr(), U, p1.ptr(), U, GEMM_MNMN, ga("policy.2.weight"), H, H, H, B, TEPI_F32, bn=128)
+    with beside:
+        gemm(dp2.ptr(), U, p1.ptr(), U, GEMM_MNMN, ga("policy.2.weight"), H, H, H, B, TEPI_F32, bn=128)
     gemm(dp2.ptr(), U, a2.ptr(), a2.units, GEMM_KMN, dp1.ptr(), U, B, H, H, TEPI_MASK_BF16, mask=p1.ptr(), units_mask=U)
-    gemm(dp1.ptr(), U, hA.ptr(), hA.units, GEMM_MNMN, ga("policy.0.weight"), Fd, H, Fd, B, TEPI_F32)
+    with beside:
+        gemm(dp1.ptr(), U, hA.ptr(), hA.units, GEMM_MNMN, ga("policy.0.weight"), Fd, H, Fd, B, TEPI_F32)
     gemm(dp1.ptr(), U, a0.ptr(), a0.units, GEMM_KMN, ws.dhA.data_ptr(), Fd, B, Fd, H, TEPI_F32)
     call("drq_ln_tanh_bwd", ws.dhA.data_ptr(), Fd, ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
          pa("trunk.1.weight"), ws.dz.data_ptr(), None, None, bw.dz.ptr(), bw.dz.units,
          B, Fd, 1, 0, s)
-    gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, ga("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
-         TEPI_TRUNK_WGRAD, bn=128)
+    with beside:
+        gemm(bw.dz.ptr(), bw.dz.units, feat.ptr(), feat.units, GEMM_MNMN, ga("trunk.0.weight"), REPR_DIM, Fd, REPR_DIM, B,
+             TEPI_TRUNK_WGRAD, bn=128)
     colsum_multi([ColsumJob(ws.dmu_pre.data_ptr(), A, ga("policy.4.bias"), B, A, 0, 0),
                   ColsumJob(dp2.ptr(), U, ga("policy.2.bias"), B, H, 1, 0), ColsumJob(dp1.ptr(), U, ga("policy.0.bias"), B, H, 1, 0),
                   ColsumJob(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd, 0, 0),
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.weight"), B, Fd, 0, 0, ws.xhatA.data_ptr()),
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.bias"), B, Fd, 0, 0)])
+    beside.join()                                   # the actor's weight gradients are complete
     agent._sync_grads("actor")
     st.step_actor_target()
 

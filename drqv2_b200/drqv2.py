@@ -414,6 +414,7 @@ class DrQV2Agent:
         # bf16 mode: encoder backward + encoder_opt.step() on a second stream beside the actor pass (DRQV2_B200_OVERLAP=0: in line)
         self.overlap_encoder_backward = os.environ.get("DRQV2_B200_OVERLAP", "1") != "0"
         self._side_stream = None
+        self._side_stream2 = None
         self.mode = mode or os.environ.get("DRQV2_B200_MODE", "fp32")
         if self.mode not in ("fp32", "bf16"):
             raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
@@ -475,6 +476,7 @@ class DrQV2Agent:
         st["_prefetch"] = None
         st["_scal_events"] = [None, None]
         st["_side_stream"] = None
+        st["_side_stream2"] = None
         return st
 
     def __setstate__(self, st):
@@ -839,6 +841,14 @@ class DrQV2Agent:
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self._dev)
         return self._side_stream
+
+    def _wgrad_side_stream(self):
+        """Third stream: the weight-gradient GEMMs / bias-gradient sums run beside the data-gradient chain."""
+        if not self.overlap_encoder_backward or self.data_parallel or self.mode != "bf16":
+            return None
+        if self._side_stream2 is None:
+            self._side_stream2 = torch.cuda.Stream(device=self._dev)
+        return self._side_stream2
 
     def _update_body(self, ws, fetch=None, draw=True):
         """Everything of one update that runs on the device, in stream order; no host sync."""
