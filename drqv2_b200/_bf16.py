@@ -250,8 +250,11 @@ class Bf16State:
                "policy.0.weight": (OPT_LINEAR, H, Fd, self.p0.ptr(), None),
                "policy.2.weight": (OPT_LINEAR, H, H, self.p2.ptr(), None),
                "policy.4.weight": (OPT_LINEAR, A, H, self.p4.ptr(), None)}
-        segs = self._segments(ag.actor, a.offsets["actor"], 0, 0, act)
-        segs += self._segments(ag.critic, a.offsets["critic"], a.seg["critic"][0], 1, self._critic_like_packed(self.TARGET, 2))
+        segs_a = self._segments(ag.actor, a.offsets["actor"], 0, 0, act)
+        segs_t = self._segments(ag.critic, a.offsets["critic"], a.seg["critic"][0], 1, self._critic_like_packed(self.TARGET, 2))
+        self.plan_actor_only = (OptSeg * len(segs_a))(*segs_a)
+        self.plan_target = (OptSeg * len(segs_t))(*segs_t)
+        segs = segs_a + segs_t
         self.plan_actor = (OptSeg * len(segs))(*segs)
 
     def step_critic_encoder(self):
@@ -274,6 +277,18 @@ class Bf16State:
     def step_encoder(self):
         """encoder_opt.step() (drqv2.py:202) and the encoder's bf16 operand copies."""
         self._step(self.plan_encoder)
+
+    def step_actor(self):
+        """actor_opt.step() (drqv2.py:221) and the actor's bf16 operand copies."""
+        self._step(self.plan_actor_only)
+
+    def step_target(self):
+        """utils.soft_update_params(critic, critic_target, tau) (drqv2.py:259-260) and the target's bf16 operand copies."""
+        ag = self.agent
+        a = ag._arena
+        tau = float(ag.critic_target_tau)
+        call("drq_adam_pack_step", None, None, None, None, None, a.ptr("params", "critic"), a.target.data_ptr(), tau,
+             float(1 - tau), self.plan_target, len(self.plan_target), _stream())
 
     def step_actor_target(self):
         """actor_opt.step() and the soft target update (drqv2.py:221,259-260) and their bf16 operand copies."""
@@ -350,22 +365,37 @@ def encode(agent, ws, bw):
          B, bw.RB, s)
 
 
-def twin_q_fwd(agent, bw, x, nets, B):
-    """Layers 1-2 and the scalar head of `nets` x 2 Q heads in one launch per layer.  nets = 2: online
-    critic on x[0] and target on x[1] -> q4[0:4]; nets = 1: online critic on x -> q4[0:2]."""
+def twin_q_layers(agent, bw, x, z0, nets, B):
+    """Layers 1-2 of the 2 x nets Q heads of networks z0 .. z0 + nets - 1 (0 = online critic, 1 = target) on
+    x[z0 ..], one launch per layer (drqv2.py:103-111)."""
     st = agent._bf16
     A, Fd, H = agent.action_dim, agent.feature_dim, agent.hidden_dim
     qs_f, tmc = agent._q_strides(), st.target_minus_critic
-    pc = lambda k: agent._p("critic", k)
+    pc = lambda k: agent._p("critic", k) + F32 * z0 * tmc
     c1, c2, w0, w2 = bw.c1, bw.c2, st.q0, st.q2
-    gemm(x.ptr(), x.units, w0.ptr(), w0.units, GEMM_KK, c1.ptr(), c1.units, B, H, Fd + A, TEPI_RELU_BF16,
+    gemm(x.ptr(z0), x.units, w0.ptr(2 * z0), w0.units, GEMM_KK, c1.ptr(2 * z0), c1.units, B, H, Fd + A, TEPI_RELU_BF16,
          bias=pc("Q1.0.bias"), batch=2 * nets, batch_inner=2,
          strides=_strides((0, w0.stride, c1.stride, qs_f, 0), (x.stride, 2 * w0.stride, 2 * c1.stride, tmc, 0)))
-    gemm(c1.ptr(), c1.units, w2.ptr(), w2.units, GEMM_KK, c2.ptr(), c2.units, B, H, H, TEPI_RELU_BF16,
+    gemm(c1.ptr(2 * z0), c1.units, w2.ptr(2 * z0), w2.units, GEMM_KK, c2.ptr(2 * z0), c2.units, B, H, H, TEPI_RELU_BF16,
          bias=pc("Q1.2.bias"), batch=2 * nets, batch_inner=2,
          strides=_strides((c1.stride, w2.stride, c2.stride, qs_f, 0), (2 * c1.stride, 2 * w2.stride, 2 * c2.stride, tmc, 0)))
+
+
+def twin_q_heads(agent, bw, nets, B):
+    """the scalar heads Linear(hidden, 1) of 2 x nets Q heads -> q4[0 : 2 * nets] (drqv2.py:106,111)"""
+    st = agent._bf16
+    H = agent.hidden_dim
+    pc = lambda k: agent._p("critic", k)
+    c2 = bw.c2
     call("drq_q_head_fwd_bf16", c2.ptr(), c2.units, c2.stride, pc("Q1.4.weight"), pc("Q1.4.bias"), bw.q4.data_ptr(),
-         B, H, 2 * nets, qs_f, 2, tmc, _stream())
+         B, H, 2 * nets, agent._q_strides(), 2, st.target_minus_critic, _stream())
+
+
+def twin_q_fwd(agent, bw, x, nets, B):
+    """Layers 1-2 and the scalar head of `nets` x 2 Q heads in one launch per layer.  nets = 2: online
+    critic on x[0] and target on x[1] -> q4[0:4]; nets = 1: online critic on x -> q4[0:2]."""
+    twin_q_layers(agent, bw, x, 0, nets, B)
+    twin_q_heads(agent, bw, nets, B)
 
 
 def actor_mlp_fwd(agent, hA, p1, p2, mu_pre, M):
@@ -436,13 +466,22 @@ def critic_pass(agent, ws, bw):
         job(pz(1, 0), tp, tn, ws.xT.data_ptr(), Fd + A, None, None, bw.x, bw.x.rpad),                          # target(next) -> x[1]
         job(pz(1, FP), pa, tn, bw.hA_next_f32.data_ptr(), Fd, None, None, bw.hA, RB),                          # actor(next)
     ], B, Fd)
+    split_q = beside.side is not None
+    if split_q:                                     # online Q(obs, action) does not wait for the actor: beside the actor MLP
+        with beside:
+            twin_q_layers(agent, bw, bw.x, 0, 1, B)
     # ---- actor MLP on [obs | next] rows at once (drqv2.py:182 and :210 use the same actor parameters)
     actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), RB + B)
     # next action: clipped sample (drqv2.py:183) -> xT's action columns
     call("drq_actor_sample", bw.mu_pre.data_ptr() + F32 * RB * A, ws.eps_c.data_ptr(), std_ptr, float(agent.stddev_clip),
          ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, bw.x.ptr(1), bw.x.units, Fd, B, A, s)
-    # ---- target Q on (next, next action) and online Q on (obs, action): 4 heads per launch
-    twin_q_fwd(agent, bw, bw.x, 2, B)
+    # ---- target Q on (next, next action) and online Q on (obs, action)
+    if split_q:
+        twin_q_layers(agent, bw, bw.x, 1, 1, B)
+        beside.join()
+        twin_q_heads(agent, bw, 2, B)
+    else:
+        twin_q_fwd(agent, bw, bw.x, 2, B)           # 4 heads per launch
     # ---- TD target + critic loss (drqv2.py:185-189) and the backward through the scalar Q heads, one launch
     q = bw.q4.data_ptr()
     c1, c2, dc1, dc2 = bw.c1, bw.c2, bw.dc1, bw.dc2
@@ -529,6 +568,11 @@ def actor_pass(agent, ws, bw):
     ga = lambda k: agent._g("actor", k)
     std_ptr = agent._scal_dev.data_ptr() + F32 * 8
     feat, xA = bw.feat, bw.xA
+    if beside.side is not None:
+        # the soft target update depends on the stepped critic only (drqv2.py:259-260 runs it after update_actor, on the
+        # same critic parameters) and nothing in this pass reads the target: beside the whole pass
+        with beside:
+            st.step_target()
     call("drq_actor_sample", bw.mu_pre.data_ptr(), ws.eps_a.data_ptr(), std_ptr, float(agent.stddev_clip),
          ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6,
          xA.ptr(), xA.units, Fd, B, A, s)
@@ -581,7 +625,10 @@ def actor_pass(agent, ws, bw):
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.bias"), B, Fd, 0, 0)])
     beside.join()                                   # the actor's weight gradients are complete
     agent._sync_grads("actor")
-    st.step_actor_target()
+    if beside.side is not None:
+        st.step_actor()                             # the target's soft update already ran beside this pass
+    else:
+        st.step_actor_target()
 
 
 def act_workspace(agent, n, dev):
