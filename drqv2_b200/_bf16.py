@@ -8,6 +8,10 @@ that work sharing an operand shares a launch:
   * the actor MLP runs once on [obs | next] rows;
   * the online and target twin-Q heads run as one 4-head batched launch per layer.
 
+Inside the captured graph the update runs on three streams: the data-gradient chain on the main
+stream, the encoder backward + encoder_opt.step() beside the actor pass, and the weight-gradient GEMMs, bias sums
+and the soft target update beside both.
+
 Master parameters, gradients and Adam state stay fp32 in the reference layouts; this module owns
 the derived bf16 operand copies (re-packed after every optimiser step) and the bf16 activations:
   * encoder activations / gradients: "WB" layout (include/drqv2_b200.h),
