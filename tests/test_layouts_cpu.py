@@ -1,0 +1,78 @@
+"""CPU checks of the host-side mirror of the C ABI: the ctypes job structs have exactly the layout gcc gives the
+header's structs, and the tile-blocked (TB) layout helpers address what include/drqv2_b200.h documents."""
+import ctypes as C
+import pathlib
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+STRUCTS = {   # header struct -> (ctypes mirror, fields)
+    "drq_pack_job": ("PackJob", ["kind", "rows", "cols", "reserved", "w", "bias", "out", "out2"]),
+    "drq_colsum_job": ("ColsumJob", ["X", "ld", "out", "M", "N", "tb", "reserved", "Y"]),
+    "drq_opt_seg": ("OptSeg", ["kind", "ema", "rows", "cols", "off", "n", "out", "out2"]),
+    "drq_wgrad_reduce_job": ("WgReduceJob", ["partial", "dw", "db", "n_images", "hout", "cin", "reserved"]),
+    "drq_ln_job": ("LnJob", ["partial", "ld_partial", "split_stride", "S", "bias", "gamma", "beta", "h_out", "ld_h", "xhat",
+                             "rstd", "h_bf16", "units_bf16", "row0_bf16", "tail", "ld_tail", "n_tail"]),
+}
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
+def test_ctypes_structs_match_the_header(tmp_path):
+    from drqv2_b200 import _bf16
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{ROOT / "include" / "drqv2_b200.h"}"', "int main(void) {"]
+    for cname, (_, fields) in STRUCTS.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, (pyname, fields) in STRUCTS.items():
+        cls = getattr(_bf16, pyname)
+        assert C.sizeof(cls) == got[(cname, "size")], cname
+        assert [f for f, _ in cls._fields_] == fields, cname
+        for f in fields:
+            assert getattr(cls, f).offset == got[(cname, f)], (cname, f)
+
+
+def test_tb_layout_round_trip_and_addressing():
+    """TB element (row, feat) of entry z sits at z*stride + ((row/R)*units + feat/8)*R*8 + (row%R)*8 + feat%8."""
+    from drqv2_b200._bf16 import TB
+    from drqv2_b200._lib import TB_ACT, TB_W
+    g = torch.Generator().manual_seed(0)
+    for rows, feats, batch, R in ((5, 56, 2, TB_W), (300, 50, 1, TB_ACT), (64, 1024, 4, TB_W), (130, 21, 1, TB_ACT)):
+        t = TB(rows, feats, "cpu", batch=batch, rblk=R)
+        assert t.units == (feats + 15) // 16 * 2 and t.rpad % R == 0 and t.rpad >= rows
+        assert t.buf.numel() == batch * t.stride and t.stride == t.units * t.rpad * 8
+        xs = []
+        for z in range(batch):
+            x = torch.randn(rows, feats, generator=g).to(torch.bfloat16)
+            t.load(x, z)
+            xs.append(x)
+        for z in range(batch):
+            assert torch.equal(t.dense(z), xs[z].float())
+            for row, feat in ((0, 0), (rows - 1, feats - 1), (rows // 2, feats // 3)):
+                idx = z * t.stride + ((row // R) * t.units + feat // 8) * R * 8 + (row % R) * 8 + feat % 8
+                assert t.buf[idx] == xs[z][row, feat]
+            # padding rows / features are zero
+            assert float(t.view(z)[rows:].abs().sum()) == 0 and float(t.view(z)[:, feats:].abs().sum()) == 0
+        assert t.off(batch - 1, R * ((rows - 1) // R), 8 * ((feats - 1) // 8)) < t.buf.numel()
+
+
+def test_splitk_chunks_are_never_empty():
+    """drq_gemm_bf16 rejects a split-K whose last chunk would be empty; the chooser must never produce one."""
+    from drqv2_b200._bf16 import splitk_for
+    from drqv2_b200._lib import REPR_DIM
+    for ctas in range(1, 149):
+        for K in (REPR_DIM, 1024, 4096):
+            S = splitk_for(ctas, K)
+            chunk = -(-(-(-K // S)) // 128) * 128
+            assert S >= 1 and chunk * (S - 1) < K, (ctas, K, S)
