@@ -76,3 +76,45 @@ def test_splitk_chunks_are_never_empty():
             S = splitk_for(ctas, K)
             chunk = -(-(-(-K // S)) // 128) * 128
             assert S >= 1 and chunk * (S - 1) < K, (ctas, K, S)
+
+
+def _lin_tile(cols, tile=1024):
+    """Python restatement of lin_tile() in drqv2_b200/csrc/optim.cu (generic LINEAR segments of drq_adam_pack_step)."""
+    c8 = (cols + 7) // 8 * 8
+    CW = min(c8, 256)
+    rt, p2 = tile // CW, 1
+    while p2 * 2 <= rt and p2 < 32:
+        p2 *= 2
+    chunks = (cols + CW - 1) // CW
+    width = cols if chunks == 1 else CW
+    SW = (CW + 55) // 64 * 64 + 8
+    return CW, p2, SW, chunks, width
+
+
+def test_fused_optimiser_linear_tiling_covers_every_element_once():
+    """The block -> (rows, columns) tiling of a generic Linear weight: every element is visited exactly once, the
+    staged bf16 tile fits the kernel's shared buffer, 16-byte unit reads are aligned and bank-staggered."""
+    SH_BF16 = 32 * 72                              # kOptShBf16
+    for cols in list(range(1, 80)) + [100, 127, 255, 256, 257, 300, 511, 1000, 1025]:
+        if cols % 8 == 0:
+            continue                               # multiples of 8 take the flat float4 path
+        CW, RT, SW, chunks, width = _lin_tile(cols)
+        assert RT * width <= 1024 and RT * SW <= SH_BF16 and SW >= CW and SW % 8 == 0 and SW % 64 == 8
+        rows = 37
+        seen = {}
+        blocks = ((rows + RT - 1) // RT) * chunks
+        for b in range(blocks):
+            rb, ch = divmod(b, chunks)
+            r0, c0 = rb * RT, ch * CW
+            for e in range(RT * width):
+                lr, cc = divmod(e, width)
+                r, c = r0 + lr, c0 + cc
+                if r < rows and c < cols:
+                    assert lr * SW + cc < RT * SW
+                    seen[(r, c)] = seen.get((r, c), 0) + 1
+            # units written by this block cover exactly its columns
+            ul_n = (width + 7) // 8
+            for ul in range(ul_n):
+                if c0 + ul * 8 < cols:
+                    assert (c0 // 8 + ul) * 8 < (cols + 15) // 16 * 16
+        assert len(seen) == rows * cols and set(seen.values()) == {1}, cols
