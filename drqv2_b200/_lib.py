@@ -53,17 +53,13 @@ SIGNATURES = {
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
-    "drq_splitk_reduce": [P, I, L, P, L, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
     "drq_ln_tanh_fwd": [P, I, L, P, P, P, P, L, P, P, P, L, I, I, F, P],
     "drq_ln_tanh_fwd_multi": [P, I, I, I, F, P],
     "drq_ln_tanh_bwd": [P, L, P, L, P, P, P, P, P, P, P, L, I, I, I, L, P],
     "drq_actor_sample": [P, P, P, F, P, L, P, P, P, L, I, I, I, P],
     "drq_actor_sample_bwd": [P, L, P, P, P, L, I, I, I, L, P],
-    "drq_scatter_fb": [P, L, P, L, I, I, I, P],
-    "drq_colsum_fb": [P, L, P, I, I, I, L, L, P],
     "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, I, L, P],
-    "drq_q_head_bwd_bf16": [P, P, L, L, P, P, P, P, I, I, I, L, P],
     "drq_q_head_bwd_loss_bf16": [I, P, P, P, P, P, P, P, L, L, P, P, P, P, I, I, L, P],
     "drq_critic_loss": [P, P, P, P, P, P, P, P, P, P, I, P],
     "drq_actor_loss": [P, P, P, P, P, I, P],

@@ -125,17 +125,6 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
     }
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, long long stride,
-                                     float* __restrict__ out, long long n) {
-    pdl_trigger();
-    pdl_wait();
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    for (int k = 0; k < S; ++k) s += partial[k * stride + i];
-    out[i] = s;
-}
-
 // out[z][n] = sum_m X[z][m][n]; block = 32 columns x 8 row lanes, fixed-order tree.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, long long ld, float* __restrict__ out, int M, int N,
@@ -194,12 +183,6 @@ int drq_gemm_f32(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splitk > 1 ? splitk : batch);
     launch_k(gemm_f32_kernel, grid, 256, 0, as_stream(stream), g);
     return check_launch("gemm_f32_kernel");
-}
-
-int drq_splitk_reduce(const float* partial, int S, int64_t stride, float* out, int64_t n, void* stream) {
-    DRQ_REQUIRE(partial && out && S > 0 && n > 0, "splitk_reduce: bad args");
-    launch_k(splitk_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), partial, S, stride, out, n);
-    return check_launch("splitk_reduce_kernel");
 }
 
 int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,

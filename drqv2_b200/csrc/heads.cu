@@ -297,48 +297,6 @@ actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
 }
 
 // ---------------------------------------------------------------- bf16-mode helpers (TB layout; `rpad` = units per row)
-__global__ void scatter_fb_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
-                                  long long rpad, int feat_off, int rows, int cols) {
-    pdl_trigger();
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int r = i / cols, c = i - r * cols;
-    dst[fb_index(feat_off + c, r, rpad)] = __float2bfloat16_rn(src[r * ld_src + c]);
-}
-
-// out[z][8u..8u+7] = sum_b X_fb[z][u][b][0..7]; one block per unit, fixed-order tree over 256 threads
-__global__ void __launch_bounds__(256)
-colsum_fb_kernel(const __nv_bfloat16* __restrict__ X, long long rpad, float* __restrict__ out, int M, int N,
-                 long long bs_x, long long bs_out) {
-    pdl_trigger();
-    pdl_wait();
-    __shared__ float red[256][9];
-    const int u = blockIdx.x, z = blockIdx.y;
-    const __nv_bfloat16* Xz = X + z * bs_x;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < M; b += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(Xz + fb_index(u * 8, b, rpad));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc[2 * j] += __uint_as_float(w[j] << 16);
-            acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + o][j];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x < 8 && u * 8 + threadIdx.x < N) out[z * bs_out + u * 8 + threadIdx.x] = red[0][threadIdx.x];
-}
-
 // q[z][b] = c2[z][b][:] . w3[z][:] + b3[z]   (the Linear(hidden, 1) of drqv2.py:106,111) on an FB
 // activation.  Block = 32 rows x 8 unit groups: lane = row (one coalesced 512-byte read per unit and
 // warp), warp g sums units g, g+8, ...; the 8 partial sums are combined in fixed order.
@@ -577,22 +535,6 @@ int drq_critic_loss(const float* q1, const float* q2, const float* tq1, const fl
     return check_launch("critic_loss_kernel");
 }
 
-int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
-                   int cols, void* stream) {
-    DRQ_REQUIRE(src && dst && rows > 0 && cols > 0 && feat_off >= 0, "scatter_fb: bad args");
-    launch_k(scatter_fb_kernel, (rows * cols + 255) / 256, 256, 0, as_stream(stream), 
-        src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), rpad, feat_off, rows, cols);
-    return check_launch("scatter_fb_kernel");
-}
-
-int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int batch, int64_t bs_x,
-                  int64_t bs_out, void* stream) {
-    DRQ_REQUIRE(X && out && M > 0 && N > 0 && batch > 0, "colsum_fb: bad args");
-    launch_k(colsum_fb_kernel, dim3((N + 7) / 8, batch), 256, 0, as_stream(stream), 
-        reinterpret_cast<const __nv_bfloat16*>(X), rpad, out, M, N, bs_x, bs_out);
-    return check_launch("colsum_fb_kernel");
-}
-
 int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
                         float* q, int B, int H, int heads, int64_t w_stride, int heads_inner, int64_t w_stride_outer,
                         void* stream) {
@@ -600,16 +542,6 @@ int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const f
     launch_k(q_head_fwd_kernel, dim3((B + 31) / 32, heads), 256, H * sizeof(float), as_stream(stream), 
         reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, b3, q, B, H, w_stride, heads_inner, w_stride_outer);
     return check_launch("q_head_fwd_kernel");
-}
-
-int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
-                        uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
-                        void* stream) {
-    DRQ_REQUIRE(dq && c2 && w3 && dc2 && B > 0 && H > 0 && H % 8 == 0 && heads > 0, "q_head_bwd: bad args");
-    launch_k(q_head_bwd_kernel<0>, dim3(H / 8, heads), 256, 0, as_stream(stream), dq, QLossArgs{},
-             reinterpret_cast<const __nv_bfloat16*>(c2), rpad, bs_c2, w3, reinterpret_cast<__nv_bfloat16*>(dc2), dw3, db3, B,
-             w_stride);
-    return check_launch("q_head_bwd_kernel");
 }
 
 int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const float* reward, const float* discount,

@@ -314,17 +314,13 @@ int drq_conv_wgrad_reduce_multi(const drq_wgrad_reduce_job* jobs, int njobs, voi
  * bs_bias, bs_mask) — the twin Q heads of drqv2.py:103-111.
  * splitk > 1 (batch must be 1): K is cut in `splitk` chunks and chunk s writes
  * its raw partial sum to C + s*bs_c (bias/epilogue ignored) — reduced in fixed
- * order by drq_ln_tanh_fwd / drq_splitk_reduce.
+ * order by drq_ln_tanh_fwd.
  * accumulate != 0: C += result (after epilogue).  mask has C's shape/ld. */
 int drq_gemm_f32(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
                  int64_t sb_n, float* C, int64_t ldc, const float* bias, const float* mask,
                  int64_t ldmask, int M, int N, int K, int epilogue, int accumulate, int batch,
                  int64_t bs_a, int64_t bs_b, int64_t bs_c, int64_t bs_bias, int64_t bs_mask,
                  int splitk, void* stream);
-
-/* out[n] (+)= sum_s partial[s][n]  (fixed order; used for split-K and bias grads) */
-int drq_splitk_reduce(const float* partial, int S, int64_t stride, float* out, int64_t n,
-                      void* stream);
 
 /* out[z][n] = sum_m X[z][m*ld + n]  — bias gradients. */
 int drq_colsum_f32(const float* X, int64_t ld, float* out, int M, int N, int batch, int64_t bs_x,
@@ -401,22 +397,13 @@ int drq_copy2d_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
                    void* stream);
 
 /* bf16-mode helpers of the heads (TB activation layout; every `rpad` argument = units per row) */
-/* dst_fb[(feat_off + c)][r] = src[r*ld_src + c]  (the action half of torch.cat([h, action]), drqv2.py:117) */
-int drq_scatter_fb(const float* src, int64_t ld_src, uint16_t* dst, int64_t rpad, int feat_off, int rows,
-                   int cols, void* stream);
-/* out[z][n] = sum_m X_fb[z](m, n): bias gradients of the hidden layers */
-int drq_colsum_fb(const uint16_t* X, int64_t rpad, float* out, int M, int N, int batch, int64_t bs_x,
-                  int64_t bs_out, void* stream);
 /* final Linear(hidden,1) of the Q heads (drqv2.py:106,111) on an FB hidden activation c2 (head z at
  * c2 + z*bs_c2): q[z][b] = c2[z][b].w3[z] + b3[z]; w3/b3 of head z at w3 + z*w_stride / b3 + z*w_stride. */
 int drq_q_head_fwd_bf16(const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3, const float* b3,
                         float* q, int B, int H, int heads, int64_t w_stride, int heads_inner, int64_t w_stride_outer,
                         void* stream);
-/* its backward: dc2 = dq w3 (c2 > 0) as FB bf16; dw3 / db3 (nullable) in fp32 at the same strides. */
-int drq_q_head_bwd_bf16(const float* dq, const uint16_t* c2, int64_t rpad, int64_t bs_c2, const float* w3,
-                        uint16_t* dc2, float* dw3, float* db3, int B, int H, int heads, int64_t w_stride,
-                        void* stream);
-/* the same with the loss gradient computed in place (one launch less per pass): loss = 1: critic loss of
+/* its backward, with the loss gradient computed in place: dc2 = dq w3 (c2 > 0) as TB bf16, dw3 / db3 (nullable) in
+ * fp32 at the same strides, where dq comes from loss = 1: critic loss of
  * drqv2.py:185-189 from q[2][B], tq[2][B], reward, discount (metrics[0..4] and target_q_out as drq_critic_loss);
  * loss = 2: actor loss of drqv2.py:213-216 from q[2][B] (metrics[0] = actor_loss).  Two heads. */
 int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const float* reward, const float* discount,
