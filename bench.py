@@ -7,17 +7,25 @@ One "step" = one DrQV2Agent.update (critic + actor + soft target update) on a fr
 batch of the walker_walk shape (B=256, 9x84x84 uint8 stacks, A=6, F=50, H=1024, n-step 3).
 
 ours      : `value` = updates/s with the replay ring resident in HBM (sample + n-step
-            gather + update captured in one CUDA graph, timed with CUDA events);
+            gather + update captured in one CUDA graph, timed with CUDA events; the K-step block is
+            repeated --blocks times, `value` is the median block, min / max are reported beside it);
             `e2e` = the same update through the public API fed from HOST batches
             (pinned memory -> H2D inside the timed region, metrics read back D2H).
-reference : the CPU restatement of the reference's update (oracle/ port; the reference is
-            pure PyTorch, there is nothing to compile) on the host cores, bounded sample.
-Multi-GPU : one process per GPU (torchrun); independent agents (ensemble members) with no
+            Before anything is timed, one update at this configuration is checked against the oracle
+            (`parity_checked`).  Every launch of one update is then timed alone (L2 flushed before each) for the
+            roofline record; the unmodified reference runs on the same GPU (`gpu_reference`: eager, TF32 on/off,
+            and captured in a CUDA graph with Adam(capturable=True)) and on the host cores (`cpu_baseline`).
+            Sub-records `ensemble_8_per_gpu` (BASELINE configs[3]) and `dp_humanoid_b4096` (configs[4]) carry
+            the two multi-GPU configurations with their own one-GPU points.
+reference : the reference's own update on the host cores (unmodified sources from baseline/_ref, else the
+            oracle port), bounded sample.
+Multi-GPU : one process per GPU (torchrun); the headline is independent agents (ensemble members) with no
             collective, value = sum over ranks / max-over-ranks time, scaling "weak".
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -32,6 +40,7 @@ sys.path.insert(0, ROOT)
 SCHED = "linear(1.0,0.1,100000)"
 E_F, E_B = 84_561_984, 160_409_664     # encoder fwd / bwd FLOP per sample
 CONV_MACS = {39: 14_017_536, 37: 12_616_704, 35: 11_289_600}
+CONV1_MACS_PER_CIN = 41 * 41 * 32 * 9   # x cin
 
 
 def update_flops(B, A, F, H):
@@ -101,18 +110,6 @@ def fill_ring(loader_dir, A, episodes, rows, device, seed=1):
     return ring
 
 
-def time_kernel(fn, iters=20):
-    fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3
-
-
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -121,8 +118,399 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def new_agent(args, A, Fd, seed, mode=None, dp=False, lr=1e-4):
+    from drqv2_b200 import DrQV2Agent
+    return DrQV2Agent((9, 84, 84), (A,), "cuda", lr, Fd, args.hidden_dim, 0.01, 2000, 2, SCHED, 0.3, False,
+                      use_cuda_graph=True, seed=seed, mode=mode or args.mode, data_parallel=dp)
+
+
+def ring_iter(key, A, episodes, B, dev, seed):
+    from drqv2_b200 import make_replay_loader
+    fill_ring(key, A, episodes, 501, dev, seed=seed)
+    return iter(make_replay_loader(key, episodes * 501, B, 0, False, 3, 0.99))
+
+
+def timed_blocks(step_fn, steps, blocks, world, dev):
+    """`blocks` back-to-back blocks of exactly `steps` updates, each bracketed by barrier + synchronize and timed
+    with CUDA events on the launching stream; per block the max over ranks.  Returns the ms of every block."""
+    out = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(blocks):
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = t.item()
+        out.append(ms)
+    return out
+
+
+def block_stats(ms_blocks, steps, units):
+    per = sorted(m / steps for m in ms_blocks)
+    med = statistics.median(per)
+    return med, {"blocks": len(per), "steps_per_block": steps, "ms_per_step_median": med, "ms_per_step_min": per[0],
+                 "ms_per_step_max": per[-1], "value_median": units * 1e3 / med, "value_best": units * 1e3 / per[0],
+                 "value_worst": units * 1e3 / per[-1]}
+
+
+# ----------------------------------------------------------------------------- parity at the benched configuration
+def parity_check(args):
+    """One update at the benched shape (B, A, F, H, mode) from identical parameters and injected draws against the
+    oracle (bf16 mode: its bf16-faithful variant), through the same CUDA-graph path the timed loop replays.
+    Tolerances are the ones tests/test_gpu_bench_config.py states."""
+    from oracle import drq_oracle as O
+    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    torch.set_num_threads(os.cpu_count())
+    params = O.synthetic_params(9, A, Fd, H, seed=4)
+    agent = new_agent(args, A, Fd, seed=5)
+    agent.use_tb = True
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        getattr(agent, net).load_state_dict(params[net])
+    agent.refresh()
+    bf = args.mode == "bf16"
+    oracle = O.OracleAgent(params, 1e-4, 0.01, SCHED, 0.3, dtype=torch.float64, operands="bf16" if bf else "exact")
+    worst, rec = 0.0, {}
+    keys = ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "critic_loss")
+    for s in range(3):                      # eager warm-up, capture + first replay, replay
+        b = O.synthetic_batch(B, A, seed=10 + s)
+        agent.inject_draws(b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+        m = agent.update(iter([(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])]), 2 * s)
+        mo = oracle.update(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"], 2 * s, b["shift_obs"],
+                           b["shift_next"], b["eps_critic"], b["eps_actor"])
+        tol = (2e-3 if bf else 1e-4) if s == 0 else 2e-2     # after an Adam step: its sign-like noise (SURVEY §8c)
+        for k in keys:
+            err = abs(m[k] - mo[k]) / (abs(mo[k]) + 1e-12)
+            rec[f"update{s}.{k}"] = err
+            worst = max(worst, err / tol)
+    lr = 1e-4
+    dmax = max((p.detach().cpu().double() - oracle.p[net][name]).abs().max().item()
+               for net in ("encoder", "critic", "actor", "critic_target") for name, p in getattr(agent, net).named_parameters())
+    ok = worst <= 1.0 and dmax <= 2.5 * lr * 3
+    graphed = any(isinstance(v, torch.cuda.CUDAGraph) for v in agent._graphs.values())
+    return {"parity_checked": bool(ok and graphed),
+            "parity": {"oracle": "oracle/drq_oracle.py OracleAgent(float64, operands=%s)" % ("bf16" if bf else "exact"),
+                       "updates_compared": 3, "max_rel_err_first_update": max(rec[f"update0.{k}"] for k in keys),
+                       "max_rel_err_later_updates": max(v for k, v in rec.items() if not k.startswith("update0")),
+                       "max_abs_param_diff_over_lr": dmax / lr, "cuda_graph_path": graphed}}
+
+
+# ----------------------------------------------------------------------------- every launch of one update, timed alone
+def profile_update_launches(agent, it, B, reps=5):
+    """Runs eager single-stream updates with every C-ABI call bracketed by CUDA events on its launch stream and a
+    write of a 256 MB buffer (> the 126 MB L2) in front of it: per launch the cold-cache duration, plus the
+    algorithmic FLOP / bytes the call's own arguments imply.  Median over `reps` updates."""
+    import drqv2_b200._bf16 as BF
+    import drqv2_b200.drqv2 as D
+    import drqv2_b200.replay_buffer as R
+    from drqv2_b200 import _lib
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    orig = _lib.call
+    records, cur = [], []
+
+    def work_of(name, a):
+        if name == "drq_conv1_fwd_bf16":
+            return "conv", f"conv1_fwd(N={a[4]})", 2 * CONV1_MACS_PER_CIN * a[5] * a[4], 0
+        if name == "drq_conv1_wgrad_bf16":
+            return "conv", f"conv1_wgrad(N={a[6]})", 2 * CONV1_MACS_PER_CIN * a[7] * a[6], 0
+        if name == "drq_conv3x3_fwd_bf16":
+            return "conv", f"conv3x3_fwd(hout={a[5]},N={a[4]}{',TB' if a[6] == 2 else ''})", 2 * CONV_MACS[a[5]] * a[4], 0
+        if name == "drq_conv3x3_dgrad_bf16":
+            return "conv", f"conv3x3_dgrad(hout={a[6]},N={a[5]})", 2 * CONV_MACS[a[6]] * a[5], 0
+        if name == "drq_conv3x3_wgrad_bf16":
+            return "conv", f"conv3x3_wgrad(hout={a[7]},N={a[6]})", 2 * CONV_MACS[a[7]] * a[6], 0
+        if name == "drq_gemm_bf16":
+            M, N, K, batch = a[11], a[12], a[13], a[16]
+            return "gemm", f"gemm(mode={a[4]},M={M},N={N},K={K},batch={batch},splitk={a[19]},bn={a[20]},epi={a[14]})", 2 * M * N * K * batch, 0
+        if name.startswith("drq_conv") and name.endswith("_f32") or name == "drq_gemm_f32":
+            return "fp32", name, 0, 0
+        if name == "drq_adam_pack_step":
+            plan, n = a[9], a[10]
+            by = sum((12 if plan[i].ema else 28) * plan[i].n + (2 * plan[i].n if plan[i].kind else 0) for i in range(n))
+            return "hbm", f"adam_pack(segs={n})", 0, by
+        if name in ("drq_adam_step", "drq_adam_ema_step"):
+            return "hbm", name, 0, 28 * a[4] + (12 * a[8] if name == "drq_adam_ema_step" else 0)
+        if name == "drq_ring_gather_nstep":
+            return "hbm", "ring_gather", 0, 2 * 2 * a[10] * a[5] * a[6] * 84 * 84
+        return "latency", name, 0, 0
+
+    def timed_call(name, *a):
+        s = torch.cuda.current_stream()
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        orig(name, *a)
+        e1.record(s)
+        cur.append((name, a, e0, e1))
+
+    was_graph, was_overlap = agent.use_cuda_graph, agent.overlap_encoder_backward
+    agent.use_cuda_graph, agent.overlap_encoder_backward = False, False      # one stream: every launch alone
+    step = 10_000
+    try:
+        agent.update(it, step)
+        D.call = R.call = BF.call = timed_call
+        for r in range(reps):
+            cur.clear()
+            step += 2
+            agent.update(it, step)
+            torch.cuda.synchronize()
+            records.append([(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in cur])
+    finally:
+        D.call = R.call = BF.call = orig
+        agent.use_cuda_graph, agent.overlap_encoder_backward = was_graph, was_overlap
+    launches = []
+    for i, (name, a, _) in enumerate(records[0]):
+        ms = statistics.median(rec[i][2] for rec in records)
+        cls, label, flop, by = work_of(name, a)
+        launches.append({"i": i, "kernel": label, "class": cls, "us": ms * 1e3, "flop": flop, "bytes": by})
+    del flush
+    return launches
+
+
+def roofline_record(launches, value, world, flops_update, mode):
+    hbm, tf_burst, tf_sust, src = peaks()
+    traffic_file = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+
+    def cls(c):
+        sel = [l for l in launches if l["class"] == c]
+        us = sum(l["us"] for l in sel)
+        return sel, us
+
+    roof = {"peak_source": src, "timing": "every launch of one eager single-stream update timed alone with CUDA events on "
+            "its launch stream, a 256 MB buffer written in front of each (cold L2); median of 5 updates"}
+    tensor = [l for l in launches if l["class"] in ("conv", "gemm") and l["flop"]]
+    if tensor:
+        dom = max(tensor, key=lambda l: l["us"])
+        ach = dom["flop"] / (dom["us"] * 1e-6) / 1e12
+        roof.update({"bound": "tensor", "kernel": dom["kernel"], "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s",
+                     "frac": ach / tf_burst, "kernel_us": dom["us"],
+                     "traffic": (traffic.get("kernels", {}).get(dom["kernel"].split("(")[0]) or {}).get("dram_bytes"),
+                     "traffic_source": traffic.get("source")})
+        for c in ("conv", "gemm"):
+            sel, us = cls(c)
+            fl = sum(l["flop"] for l in sel)
+            if us:
+                roof[f"{c}_class"] = {"launches": len(sel), "us": us, "flop": fl, "achieved": fl / (us * 1e-6) / 1e12,
+                                      "frac": fl / (us * 1e-6) / 1e12 / tf_burst, "unit": "TFLOP/s"}
+    else:
+        roof.update({"bound": "tensor", "kernel": "fp32 CUDA-core path (parity mode)", "achieved": None, "peak": tf_burst,
+                     "unit": "TFLOP/s", "frac": None, "traffic": None})
+    sel, us = cls("hbm")
+    roof["hbm_kernels"] = [{"kernel": l["kernel"], "us": l["us"], "bytes": l["bytes"], "achieved_gbs": l["bytes"] / (l["us"] * 1e-6) / 1e9,
+                            "frac": l["bytes"] / (l["us"] * 1e-6) / 1e9 / hbm, "peak_gbs": hbm} for l in sel]
+    _, us_lat = cls("latency")
+    roof["latency_class"] = {"launches": len(cls("latency")[0]), "us": us_lat}
+    roof["serial_sum_us"] = sum(l["us"] for l in launches)
+    roof["whole_update"] = {"flop": flops_update, "achieved_per_gpu": flops_update * value / world / 1e12,
+                            "frac_of_burst": flops_update * value / world / 1e12 / tf_burst,
+                            "frac_of_sustained": flops_update * value / world / 1e12 / tf_sust}
+    roof["launches"] = [{k: (round(v, 2) if k == "us" else v) for k, v in l.items() if k != "i"} for l in launches]
+    return roof
+
+
+# ----------------------------------------------------------------------------- the reference on the same GPU
+def gpu_reference(args, steps=30):
+    """The unmodified reference agent (baseline/_ref) on cuda: eager with cudnn.benchmark as train.py:25 sets it,
+    TF32 on (its default) and off, and the same update captured in a CUDA graph with Adam(capturable=True)."""
+    ref = _load_reference()
+    if ref is None:
+        return {"unavailable": "baseline/_ref not present"}
+    B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(1)
+    batch = tuple(t.to(dev) for t in (
+        torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g), torch.rand(B, A, generator=g) * 2 - 1,
+        torch.rand(B, 1, generator=g), torch.full((B, 1), 0.970299065),
+        torch.randint(0, 256, (B, 9, 84, 84), dtype=torch.uint8, generator=g)))
+
+    def it():
+        while True:
+            yield batch
+
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {}
+
+    def time_updates(fn, n):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def count_launches(fn):
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn()
+                torch.cuda.synchronize()
+            return sum(e.count for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA)
+        except Exception as e:                       # CUPTI may be unavailable on the box
+            return f"unavailable: {type(e).__name__}"
+
+    try:
+        torch.backends.cudnn.benchmark = True
+        for tag, tf32 in (("eager_tf32_on", True), ("eager_tf32_off", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.manual_seed(0)
+            agent = ref.DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False)
+            ri, st = it(), [0]
+
+            def one():
+                agent.update(ri, st[0])
+                st[0] += 2
+            ms = time_updates(one, steps)
+            out[tag] = {"updates_per_s": 1e3 / ms, "ms_per_update": ms, "launches_per_update": count_launches(one)}
+        # graph-captured: the reference's own update() with capturable Adam (its ops, no host sync at use_tb=False)
+        try:
+            torch.backends.cudnn.allow_tf32 = True
+            torch.manual_seed(0)
+            agent = ref.DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False)
+            for net in ("encoder", "actor", "critic"):
+                setattr(agent, f"{net}_opt", torch.optim.Adam(getattr(agent, net).parameters(), lr=1e-4, capturable=True))
+            ri = it()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(4):
+                    agent.update(ri, 2 * i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                agent.update(ri, 8)
+            ms = time_updates(graph.replay, steps)
+            out["cuda_graph_capturable_adam_tf32_on"] = {"updates_per_s": 1e3 / ms, "ms_per_update": ms,
+                                                         "launches_per_update": count_launches(graph.replay)}
+            del graph
+        except Exception as e:
+            out["cuda_graph_capturable_adam_tf32_on"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["note"] = "unmodified reference sources (baseline/_ref) on the same GPU, device-resident pre-collated batch, use_tb=False"
+    return out
+
+
+# ----------------------------------------------------------------------------- sub-records: the multi-GPU configurations
+def sub_ensemble(args, rank, world, dev, K=8):
+    """BASELINE configs[3]: K = 8 independent walker-shape agents per GPU (64 on 8 GPUs), no collective.  The
+    one-GPU point (rank 0 alone, the other ranks idle) is measured in the same run."""
+    from drqv2_b200 import AgentEnsemble
+    A, Fd, B = 6, 50, 256
+    ens = AgentEnsemble(K, (9, 84, 84), (A,), "cuda", 1e-4, Fd, args.hidden_dim, 0.01, 2000, 2, SCHED, 0.3, False,
+                        seeds=[10_000 * rank + k for k in range(K)], use_cuda_graph=True, mode=args.mode)
+    its = [ring_iter(f"/bench/ens{rank}_{k}", A, 8, B, dev, seed=77 + 100 * rank + k) for k in range(K)]
+    step = [0]
+
+    def one():
+        ens.update(its, step[0])
+        step[0] += 2
+    for _ in range(4):
+        one()
+    steps = max(10, min(args.steps, 100))
+    solo_ms = None
+    if world > 1:                                    # one-GPU point: rank 0 runs while the others wait
+        if rank == 0:
+            solo_ms = statistics.median(m / steps for m in timed_blocks(one, steps, 3, 1, dev))
+        torch.distributed.barrier()
+    med, stats = block_stats(timed_blocks(one, steps, 3, world, dev), steps, world * K)
+    if solo_ms is None:
+        solo_ms = med
+    del ens, its
+    return {"config": f"{world * K} independent agents (walker_walk shape, B=256), {K} per GPU on {world} GPU(s), no collective",
+            "value": stats["value_median"], "unit": "updates/s (sum over agents)", "ms_per_step": med,
+            "one_gpu_value": K * 1e3 / solo_ms, "efficiency_vs_one_gpu": stats["value_median"] / (world * K * 1e3 / solo_ms),
+            "per_gpu": stats["value_median"] / world, "repeat": stats}
+
+
+def sub_dp(args, rank, world, dev):
+    """BASELINE configs[4]: humanoid shape (A=21, F=100), global batch 4096 sharded over the GPUs, NCCL gradient
+    all-reduce inside the graph; the one-GPU B=4096 point is measured by rank 0 in the same run."""
+    from drqv2_b200 import dist as D
+    A, Fd, Bg = 21, 100, 4096
+    steps = max(10, min(args.steps, 50))
+    rec = {"config": f"humanoid_run shape (A=21, F=100, H={args.hidden_dim}), global batch {Bg} over {world} GPU(s)"}
+    one_gpu = None
+    if rank == 0:                                    # strong-scaling yardstick: the whole batch on one GPU
+        agent = new_agent(args, A, Fd, seed=0)
+        it = ring_iter("/bench/dp_one", A, 16, Bg, dev, seed=5)
+        st = [0]
+
+        def solo():
+            agent.update(it, st[0])
+            st[0] += 2
+        for _ in range(3):
+            solo()
+        one_gpu = statistics.median(m / steps for m in timed_blocks(solo, steps, 3, 1, dev))
+        del agent, it
+        torch.cuda.empty_cache()
+    rec["one_gpu_b4096"] = None if one_gpu is None else {"ms_per_step": one_gpu, "value": 1e3 / one_gpu}
+    if world == 1:
+        rec.update({"value": 1e3 / one_gpu, "unit": "global-batch updates/s", "ms_per_step": one_gpu})
+        return rec
+    torch.distributed.barrier()
+    Bs = Bg // world
+    torch.manual_seed(0)
+    agent = new_agent(args, A, Fd, seed=0, dp=True)
+    it = ring_iter(f"/bench/dp{rank}", A, 16, Bs, dev, seed=5 + rank)
+    st = [0]
+
+    def one():
+        agent.update(it, st[0])
+        st[0] += 2
+    for _ in range(4):
+        one()
+    med, stats = block_stats(timed_blocks(one, steps, 3, world, dev), steps, 1)
+    a = agent._arena
+    identical = D.replicas_identical([a.params, a.target, a.exp_avg, a.exp_avg_sq])
+    # the same shard update without communication, and the collectives alone (eager, same tensors)
+    torch.manual_seed(0)
+    solo_agent = new_agent(args, A, Fd, seed=0)
+    it2 = ring_iter(f"/bench/dp_nocomm{rank}", A, 16, Bs, dev, seed=5 + rank)
+
+    def nocomm():
+        solo_agent.update(it2, st[0])
+        st[0] += 2
+    for _ in range(4):
+        nocomm()
+    nc = statistics.median(m / steps for m in timed_blocks(nocomm, steps, 3, world, dev))
+    ranges = {"critic": a._grads_full[a.seg["critic"][0]:a.seg["critic"][0] + a.seg["critic"][2]],
+              "actor+metrics": a._grads_full[a.seg["actor"][0]:a.total + 8],
+              "encoder": a._grads_full[a.seg["encoder"][0]:a.seg["encoder"][0] + a.seg["encoder"][2]]}
+    ar = {}
+    for name, t in ranges.items():
+        t = t.clone()
+        for _ in range(5):
+            D.average_(t)
+        ms = statistics.median(timed_blocks(lambda: D.average_(t), 20, 3, world, dev)) / 20
+        ar[name] = {"mbytes": t.numel() * 4 / 1e6, "us": ms * 1e3}
+    rec.update({"value": 1e3 / med, "unit": "global-batch updates/s", "ms_per_step": med, "repeat": stats,
+                "shard_batch": Bs, "ms_per_step_same_shard_no_communication": nc, "ratio_vs_no_communication": med / nc,
+                "strong_scaling_efficiency_vs_one_gpu_b4096": None if one_gpu is None else (one_gpu / med) / world,
+                "allreduce_alone": ar, "allreduce_us_per_step": sum(v["us"] for v in ar.values()),
+                "dp_replicas_identical": bool(identical)})
+    agent._graphs.clear()
+    del agent, solo_agent
+    return rec
+
+
+# ----------------------------------------------------------------------------- main arm
 def run_ours(args, rank, world):
-    from drqv2_b200 import DrQV2Agent, _lib, make_replay_loader
+    from drqv2_b200 import _lib
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     dp = args.parallel == "dp" and world > 1
@@ -130,23 +518,19 @@ def run_ours(args, rank, world):
     B = args.batch // world if dp else args.batch  # dp: --batch is the global batch, sharded over the ranks
     if dp and args.batch % world:
         raise SystemExit(f"--batch {args.batch} does not split over {world} ranks")
+    parity = parity_check(args) if (rank == 0 and not args.no_parity) else {}
     torch.manual_seed(0 if dp else rank)          # ensemble member = independent seed; dp = one agent
     np.random.seed(7 + rank)
-    agent = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
-                       use_cuda_graph=True, seed=0 if dp else rank, mode=args.mode, data_parallel=dp)
+    agent = new_agent(args, A, Fd, seed=0 if dp else rank, dp=dp)
     key = f"/bench/ring{rank}"
-    fill_ring(key, A, args.episodes, 501, dev, seed=1 + rank)
-    loader = make_replay_loader(key, args.episodes * 501, B, 0, False, 3, 0.99)
-    it = iter(loader)
+    it = ring_iter(key, A, args.episodes, B, dev, seed=1 + rank)
     K = 1 if dp else max(1, args.agents_per_gpu)
     # further ensemble members of this GPU: own parameters, optimiser state, ring, RNG stream, graph and CUDA stream
     members, member_its = [agent], [it]
     for k in range(1, K):
         torch.manual_seed(1000 * k + rank)
-        members.append(DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False,
-                                  use_cuda_graph=True, seed=1000 * k + rank, mode=args.mode))
-        fill_ring(f"{key}_m{k}", A, args.episodes, 501, dev, seed=1 + rank + 1000 * k)
-        member_its.append(iter(make_replay_loader(f"{key}_m{k}", args.episodes * 501, B, 0, False, 3, 0.99)))
+        members.append(new_agent(args, A, Fd, seed=1000 * k + rank))
+        member_its.append(ring_iter(f"{key}_m{k}", A, args.episodes, B, dev, seed=1 + rank + 1000 * k))
     member_streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
 
     def update_all(iters, step):
@@ -184,37 +568,27 @@ def run_ours(args, rank, world):
     import drqv2_b200._bf16 as BF
     import drqv2_b200.drqv2 as D
     import drqv2_b200.replay_buffer as R
-    step = 0
-    agent.update(it, step); step += 2             # eager warm-up
+    step = [0]
+    agent.update(it, step[0]); step[0] += 2             # eager warm-up
     D.call = R.call = BF.call = counting_call
     agent.use_cuda_graph = False
-    agent.update(it, step); step += 2             # eager, counted
+    agent.update(it, step[0]); step[0] += 2             # eager, counted
     agent.use_cuda_graph = True
     launches_per_update = n_calls[0]
     D.call = R.call = BF.call = orig_call
-    for _ in range(max(args.warmup, 3)):
-        update_all(member_its, step); step += 2
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
+
+    def one_device_step():
+        update_all(member_its, step[0])
+        step[0] += 2
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        one_device_step()
     sampler = ClockSampler(dev.index)
     if rank == 0:                     # one nvidia-smi poller per job: NVML queries perturb the GPUs they touch, and in
         sampler.start()               # data-parallel mode a stall on any rank stalls every rank twice per update
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        update_all(member_its, step); step += 2
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = t.item()
-    ms_per_step = ms / args.steps
-    value = (1 if dp else world * K) * 1e3 / ms_per_step  # dp: global-batch updates/s; ensemble: sum over agents
+    units = 1 if dp else world * K    # dp: global-batch updates/s; ensemble: sum over agents
+    ms_per_step, repeat = block_stats(timed_blocks(one_device_step, args.steps, args.blocks, world, dev), args.steps, units)
+    value = units * 1e3 / ms_per_step
 
     # ---- e2e: public API fed from host batches (pinned), metrics read back.  prefetch: the agent pulls the next
     # host batch one update ahead and overlaps its H2D copy with the running update (a DrQV2Agent option)
@@ -237,114 +611,42 @@ def run_ours(args, rank, world):
             i += 1
 
     hits = [host_iter() for _ in range(K)]
+    last = [None]
+
+    def one_host_step():
+        last[0] = update_all(hits, step[0])
+        step[0] += 2
     for _ in range(4):
-        update_all(hits, step); step += 2
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        m = update_all(hits, step); step += 2
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms = t.item()
-    e2e_value = (1 if dp else world * K) * 1e3 / (e2e_ms / args.steps)
-    h2d = K * (sum(t.numel() * t.element_size() for t in host_batches[0]) + 64)
+        one_host_step()
+    e2e_ms, e2e_repeat = block_stats(timed_blocks(one_host_step, args.steps, args.blocks, world, dev), args.steps, units)
+    clocks = sampler.stop()
+    e2e_value = units * 1e3 / e2e_ms
+    h2d = K * (sum(t.numel() * t.element_size() for t in host_batches[0]) + 4 * 32)
     d2h = K * 8 * 4
-    assert np.isfinite(m["critic_loss"])
+    assert np.isfinite(last[0]["critic_loss"])
     for ag in members:
         ag.use_tb = False
         ag.prefetch = False
 
+    extra = {}
+    if rank == 0:
+        launches = profile_update_launches(agent, it, B) if not args.no_kernels else []
+        roof = roofline_record(launches, value, world, update_flops(B, A, Fd, H) * (world if dp else 1), args.mode) if launches else None
+    for ag in members[1:]:
+        ag._graphs.clear()
+    del members[1:], member_its[1:]
+    torch.cuda.empty_cache()
+    if not args.no_subrecords and not dp and K == 1 and args.mode == "bf16":
+        extra["ensemble_8_per_gpu"] = sub_ensemble(args, rank, world, dev)
+        torch.cuda.empty_cache()
+        extra["dp_humanoid_b4096"] = sub_dp(args, rank, world, dev)
+        torch.cuda.empty_cache()
     out = None
     if rank == 0:
-        hbm, tf_burst, tf_sust, src = peaks()
-        flops = update_flops(B, A, Fd, H) * (world if dp else 1)     # per counted update
-        # ---- dominant kernel, timed alone with CUDA events on its launch stream
-        ws = agent.workspace(B)
-        s = torch.cuda.current_stream().cuda_stream
-        pe = lambda k: agent._p("encoder", k)
-        ge = lambda k: agent._g("encoder", k)
-        if args.mode == "bf16":
-            bw, st = agent.bf16_workspace(B), agent._bf16
-            acts = [a.data_ptr() for a in bw.acts]
-            d = [t.data_ptr() for t in bw.dpre]
-            cand = {
-                "conv3x3_tc_kernel<fwd>(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, 0, 0, 0, s),
-                                                        2 * CONV_MACS[39] * 2 * B),
-                "conv3x3_tc_kernel<dgrad>(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_bf16", d[1], st.conv_wd[0].data_ptr(), acts[0], 2 * B, d[0], B, 39, s),
-                                                         2 * CONV_MACS[39] * B),
-                "conv3x3_wgrad_tc_kernel(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_bf16", acts[0], 2 * B, d[1], bw.wg_ws[1].data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
-                                                        2 * CONV_MACS[39] * B),
-            }
-        else:
-            acts = [a.data_ptr() for a in ws.acts]
-            d = [t.data_ptr() for t in ws.dpre]
-        cand = cand if args.mode == "bf16" else {
-            "conv3x3_fwd_f32(layer2,N=2B)": (lambda: _lib.call("drq_conv3x3_fwd_f32", acts[0], pe("convnet.2.weight"), pe("convnet.2.bias"), acts[1], 2 * B, 39, 0, s),
-                                              2 * CONV_MACS[39] * 2 * B),
-            "conv3x3_dgrad_f32(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_dgrad_f32", d[1], pe("convnet.2.weight"), acts[0], d[0], B, 39, s),
-                                              2 * CONV_MACS[39] * B),
-            "conv3x3_wgrad_f32(layer2,N=B)": (lambda: _lib.call("drq_conv3x3_wgrad_f32", acts[0], d[1], ws.wgrad_ws.data_ptr(), ge("convnet.2.weight"), ge("convnet.2.bias"), B, 39, s),
-                                              2 * CONV_MACS[39] * B),
-        }
-        kt = {k: (time_kernel(fn), fl) for k, (fn, fl) in cand.items()}
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same
-        # launches (profiles/r1_ncu_full_conv_kernels.txt, B = 256)
-        traffic = {"conv3x3_tc_kernel<fwd>(layer2,N=2B)": 69.2e6, "conv3x3_tc_kernel<dgrad>(layer2,N=B)": 59.9e6,
-                   "conv3x3_wgrad_tc_kernel(layer2,N=B)": 56.3e6} if (args.mode == "bf16" and B == 256) else {}
-        # share of the step: fwd x3 layers x(2B), dgrad x3, wgrad x3 are of the same class
-        dom = max(kt, key=lambda k: kt[k][0])
-        dt, fl = kt[dom]
-        roof = {"bound": "tensor", "kernel": dom, "achieved": fl / dt / 1e12, "peak": tf_burst,
-                "unit": "TFLOP/s", "frac": fl / dt / 1e12 / tf_burst, "traffic": traffic.get(dom), "peak_source": src,
-                "kernel_ms": dt * 1e3,
-                "all_kernels_ms": {k: v[0] * 1e3 for k, v in kt.items()},
-                "whole_update": {"flop": flops, "achieved_per_gpu": flops * value / world / 1e12,
-                                 "frac_of_sustained": flops * value / world / 1e12 / tf_sust}}
-        # ---- HBM-bound kernels of the update, timed alone the same way (algorithmic bytes per launch)
-        ar = agent._arena
-        F32 = 4
-        off, n = ar.seg["actor"][0], ar.seg["actor"][2]
-        coff, cn = ar.seg["critic"][0], ar.seg["critic"][2]
-        eoff, en = ar.seg["encoder"][0], ar.seg["encoder"][2] + ar.seg["critic"][2]
-        sc = agent._scal_dev.data_ptr()
-
-        def adam_actor_ema():
-            _lib.call("drq_adam_ema_step", ar.params.data_ptr() + F32 * off, ar.grads.data_ptr() + F32 * off,
-                      ar.exp_avg.data_ptr() + F32 * off, ar.exp_avg_sq.data_ptr() + F32 * off, n, sc,
-                      ar.params.data_ptr() + F32 * coff, ar.target.data_ptr(), cn, 0.01, 0.99, s)
-
-        def adam_enc_critic():
-            _lib.call("drq_adam_step", ar.params.data_ptr() + F32 * eoff, ar.grads.data_ptr() + F32 * eoff,
-                      ar.exp_avg.data_ptr() + F32 * eoff, ar.exp_avg_sq.data_ptr() + F32 * eoff, en, sc, s)
-
-        saved = [t.clone() for t in (ar.params, ar.exp_avg, ar.exp_avg_sq, ar.target)]
-        opt_name, pack_bytes = "adam_ema_kernel(both optimiser phases)", 0
-        if args.mode == "bf16":                    # the bf16 update steps and refreshes the bf16 operands in one launch
-            st = agent._bf16
-            adam_actor_ema, adam_enc_critic = st.step_actor_target, st.step_critic_encoder
-            opt_name = "adam_pack_kernel(both optimiser phases, incl. bf16 operand refresh)"
-            pack_bytes = 2 * (n + en + cn)
-        t_adam = time_kernel(adam_actor_ema) + time_kernel(adam_enc_critic)
-        for t, sv in zip((ar.params, ar.exp_avg, ar.exp_avg_sq, ar.target), saved):
-            t.copy_(sv)                            # the timing launches stepped the optimiser: restore
-        adam_bytes = 28 * (n + en) + 12 * cn + pack_bytes   # p,g,m,v read + p,m,v written; EMA: p, tp read + tp written; bf16 copies
-        t_gather = time_kernel(lambda: it.next_into(ws.obs[:B], ws.action, ws.reward, ws.discount, ws.obs[B:]))
-        gather_bytes = 2 * 2 * B * 9 * 84 * 84     # u8 stacks read from the ring + written to the batch
-        # (timed back to back, so the 126 MB L2 holds part of the working set: fractions above 1 are L2 hits)
-        roof["hbm_kernels"] = {
-            opt_name: {"bytes": adam_bytes, "ms": t_adam * 1e3, "achieved_gbs": adam_bytes / t_adam / 1e9,
-                                                       "peak_gbs": hbm, "frac": adam_bytes / t_adam / 1e9 / hbm},
-            "ring_sample+ring_gather_kernel": {"bytes": gather_bytes, "ms": t_gather * 1e3, "achieved_gbs": gather_bytes / t_gather / 1e9,
-                                               "peak_gbs": hbm, "frac": gather_bytes / t_gather / 1e9 / hbm}}
-        cpu = cpu_baseline(args, steps=2)
+        gref = gpu_reference(args) if not args.no_gpu_reference else None
+        cpu = cpu_baseline(args, steps=5)
         out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
-               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+               "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong" if dp else "weak", "vs_baseline": None,
                "dtype": "bf16" if args.mode == "bf16" else "f32",
                "data": "synthetic",
@@ -353,10 +655,15 @@ def run_ours(args, rank, world):
                                       f"rows), CUDA-graphed, {'bf16 tensor-core mode (fp32 master weights, fp32 accumulation)' if args.mode == 'bf16' else 'fp32 parity mode'}" + (f"; global batch {args.batch} data-parallel over {world} GPUs (NCCL gradient all-reduce in the graph)" if dp else (f"; {world * K} independent agents (ensemble), {K} per GPU on their own streams, no collective" if world * K > 1 else "")),
                           "l2": "inputs larger than L2: each step gathers a fresh 32.5 MB batch from a "
                                 f"{args.episodes * 501 * 21168 / 1e6:.0f} MB ring and streams ~700 MB of activations",
+                          "timed_blocks": f"{args.blocks} blocks of {args.steps} steps; value / ms_per_step = the median block",
                           "mode": args.mode, "agents_per_gpu": K},
-               "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": launches_per_update * args.steps * K, "launches_per_update": launches_per_update,
-               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+               "repeat": repeat,
+               "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "repeat": e2e_repeat},
+               "gpu_launches": launches_per_update * args.steps * args.blocks * K, "launches_per_update": launches_per_update,
+               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gref}
+        out.update(parity)
+        out.update(extra)
     return out
 
 
@@ -391,7 +698,7 @@ def _load_reference():
     return mods["drqv2"]
 
 
-def cpu_baseline(args, steps=2, warm=1):
+def cpu_baseline(args, steps=5, warm=1):
     """The reference's own agent.update (unmodified sources in baseline/_ref, device 'cpu', all host
     threads) on a bounded sample: `steps` updates of the same B=256 workload from pre-collated tensors.
     Falls back to the oracle port of the same path when the reference sources are not present."""
@@ -439,8 +746,8 @@ def cpu_baseline(args, steps=2, warm=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return None
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 3))
     cpu = cpu_baseline(args, steps=steps, warm=warm)
     B, A, Fd, H = args.batch, args.action_dim, args.feature_dim, args.hidden_dim
     return {"impl": "reference", "metric": "DrQ-v2 updates/sec at batch 256", "value": cpu["value"],
@@ -456,8 +763,9 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--blocks", type=int, default=5, help="the K-step timed block is repeated this many times; value = median block")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--action-dim", type=int, default=6)
@@ -471,6 +779,10 @@ def main():
     ap.add_argument("--parallel", default="ensemble", choices=["ensemble", "dp"],
                     help="N > 1: independent agents per GPU (weak scaling, no collective) or one agent with the "
                          "global --batch sharded over the GPUs and NCCL gradient all-reduce (strong scaling)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the first updates")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-launch roofline timings")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip ensemble_8_per_gpu / dp_humanoid_b4096")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-on-GPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -265,26 +265,30 @@ class Bf16State:
         """critic_opt.step(); encoder_opt.step() (drqv2.py:201-202) and their bf16 operand copies."""
         ag = self.agent
         a = ag._arena
+        if ag._opt_steps["encoder"] != ag._opt_steps["critic"]:     # one launch shares one set of Adam scalars
+            self.step_critic()
+            self.step_encoder()
+            return
         call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
-             ag._scal_dev.data_ptr(), None, None, 0.0, 0.0, self.plan_critic, len(self.plan_critic), _stream())
+             ag._sc("critic"), None, None, 0.0, 0.0, self.plan_critic, len(self.plan_critic), _stream())
 
-    def _step(self, plan):
+    def _step(self, plan, net):
         ag = self.agent
         a = ag._arena
         call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
-             ag._scal_dev.data_ptr(), None, None, 0.0, 0.0, plan, len(plan), _stream())
+             ag._sc(net), None, None, 0.0, 0.0, plan, len(plan), _stream())
 
     def step_critic(self):
         """critic_opt.step() (drqv2.py:201) and the critic's bf16 operand copies."""
-        self._step(self.plan_critic_only)
+        self._step(self.plan_critic_only, "critic")
 
     def step_encoder(self):
         """encoder_opt.step() (drqv2.py:202) and the encoder's bf16 operand copies."""
-        self._step(self.plan_encoder)
+        self._step(self.plan_encoder, "encoder")
 
     def step_actor(self):
         """actor_opt.step() (drqv2.py:221) and the actor's bf16 operand copies."""
-        self._step(self.plan_actor_only)
+        self._step(self.plan_actor_only, "actor")
 
     def step_target(self):
         """utils.soft_update_params(critic, critic_target, tau) (drqv2.py:259-260) and the target's bf16 operand copies."""
@@ -300,7 +304,7 @@ class Bf16State:
         a = ag._arena
         tau = float(ag.critic_target_tau)
         call("drq_adam_pack_step", a.params.data_ptr(), a.grads.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
-             ag._scal_dev.data_ptr(), a.ptr("params", "critic"), a.target.data_ptr(), tau, float(1 - tau),
+             ag._sc("actor"), a.ptr("params", "critic"), a.target.data_ptr(), tau, float(1 - tau),
              self.plan_actor, len(self.plan_actor), _stream())
 
     def repack_critic_encoder(self):
@@ -441,7 +445,9 @@ class _Beside:
             self.main.wait_stream(self.side)
 
 
-def critic_pass(agent, ws, bw):
+def critic_pass(agent, ws, bw, encoder_grad=True):
+    """update_critic (drqv2.py:177-204) with critic_opt.step() / encoder_opt.step().  encoder_grad=False (stage API on
+    detached features): no gradient into the encoder, only the critic steps."""
     st, s = agent._bf16, _stream()
     beside = _Beside(agent)
     B, A, Fd, H = ws.B, agent.action_dim, agent.feature_dim, agent.hidden_dim
@@ -450,7 +456,7 @@ def critic_pass(agent, ws, bw):
     gc = lambda k: agent._g("critic", k)
     pa = lambda k: agent._p("actor", k)
     tp = agent._t
-    std_ptr = agent._scal_dev.data_ptr() + F32 * 8
+    std_ptr = agent._sc("stddev")
     qs_f = agent._q_strides()
     feat, part, S = bw.feat, bw.partial, bw.S2
     # ---- all four trunk forwards on this batch's features: z = 0 obs rows x [actor | critic], z = 1 next rows x
@@ -524,6 +530,11 @@ def critic_pass(agent, ws, bw):
     d = [t.data_ptr() for t in bw.dpre]
     acts = [t.data_ptr() for t in bw.acts]
     ge = lambda k: agent._g("encoder", k)
+    if not encoder_grad:
+        beside.join()
+        agent._sync_grads("critic")
+        st.step_critic()
+        return
     gemm(bw.dz.ptr(), bw.dz.units, st.trunk_ptr(st.CRITIC), st.trunk.units, GEMM_KMN, d[3], bw.cs_d, B, REPR_DIM, Fd,
          TEPI_TRUNK_DGRAD, mask=feat.ptr(), units_mask=feat.units, bn=128)
     def encoder_backward():
@@ -556,13 +567,17 @@ def critic_pass(agent, ws, bw):
     side.wait_stream(main)
     with torch.cuda.stream(side):
         encoder_backward()
-        st.step_encoder()
+        if not agent.data_parallel:                 # data-parallel: after the join and the encoder's all-reduce (_update_body)
+            st.step_encoder()
+    agent._sync_grads("critic")                     # data-parallel: beside the encoder backward (no-op otherwise)
     st.step_critic()
 
 
-def actor_pass(agent, ws, bw):
-    """update_actor (drqv2.py:206-228).  The actor's own forward on obs already ran with the critic pass
-    (its parameters have not changed since); here: sample, the stepped critic's Q, and the backward."""
+def actor_pass(agent, ws, bw, soft_update=True, standalone=False):
+    """update_actor (drqv2.py:206-228).  Inside update() the actor's own forward on obs already ran with the critic
+    pass (its parameters have not changed since); here: sample, the stepped critic's Q, and the backward.
+    standalone=True (stage API): run that forward on the obs rows first.  soft_update=False: leave the target
+    critic alone (update() applies drqv2.py:259-260 beside / after this pass)."""
     st, s = agent._bf16, _stream()
     beside = _Beside(agent)
     B, A, Fd, H = ws.B, agent.action_dim, agent.feature_dim, agent.hidden_dim
@@ -570,9 +585,16 @@ def actor_pass(agent, ws, bw):
     pc = lambda k: agent._p("critic", k)
     pa = lambda k: agent._p("actor", k)
     ga = lambda k: agent._g("actor", k)
-    std_ptr = agent._scal_dev.data_ptr() + F32 * 8
+    std_ptr = agent._sc("stddev")
     feat, xA = bw.feat, bw.xA
-    if beside.side is not None:
+    if standalone:
+        gemm(feat.ptr(), feat.units, st.trunk_ptr(st.ACTOR), st.trunk.units, GEMM_KK, bw.partial.data_ptr(), FP, B, FP,
+             REPR_DIM, TEPI_F32, splitk=bw.S1, strides=_strides(split=B * FP))
+        ln_tanh_multi([LnJob(bw.partial.data_ptr(), FP, B * FP, bw.S1, pa("trunk.0.bias"), pa("trunk.1.weight"),
+                             pa("trunk.1.bias"), ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
+                             bw.hA.buf.data_ptr(), bw.hA.units, 0)], B, Fd)
+        actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), B)
+    if beside.side is not None and soft_update:
         # the soft target update depends on the stepped critic only (drqv2.py:259-260 runs it after update_actor, on the
         # same critic parameters) and nothing in this pass reads the target: beside the whole pass
         with beside:
@@ -628,9 +650,9 @@ def actor_pass(agent, ws, bw):
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.weight"), B, Fd, 0, 0, ws.xhatA.data_ptr()),
                   ColsumJob(ws.dz.data_ptr() + F32 * B * Fd, Fd, ga("trunk.1.bias"), B, Fd, 0, 0)])
     beside.join()                                   # the actor's weight gradients are complete
-    agent._sync_grads("actor")
-    if beside.side is not None:
-        st.step_actor()                             # the target's soft update already ran beside this pass
+    agent._sync_grads("actor", metrics=True)
+    if beside.side is not None or not soft_update:
+        st.step_actor()                             # the target's soft update already ran beside this pass (or is not wanted)
     else:
         st.step_actor_target()
 
@@ -670,4 +692,4 @@ def act_body(agent, w, n, sample):
                          w["h"].data_ptr(), Fd, None, None, w["h_b"].ptr(), w["h_b"].units, 0)], n, Fd)
     actor_mlp_fwd(agent, w["h_b"], w["p1_b"], w["p2_b"], w["mu_pre"].data_ptr(), n)
     call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
-         agent._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, s)
+         agent._sc("stddev"), 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, s)

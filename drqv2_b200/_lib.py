@@ -52,6 +52,7 @@ SIGNATURES = {
     "drq_colsum_multi": [P, I, P],
     "drq_pack_linear_tb": [P, P, I, I, P],
     "drq_pack_trunk_tb": [P, P, I, P],
+    "drq_pack_features_tb": [P, P, I, P],
     "drq_gemm_f32": [P, L, L, P, L, L, P, L, P, P, L, I, I, I, I, I, I, L, L, L, L, L, I, P],
     "drq_colsum_f32": [P, L, P, I, I, I, L, L, P],
     "drq_ln_tanh_fwd": [P, I, L, P, P, P, P, L, P, P, P, L, I, I, F, P],

@@ -433,6 +433,16 @@ pack_trunk_tb_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ou
     pack_trunk_tb_block(w, out, rows, blockIdx.x, blockIdx.y, threadIdx.x, tile);
 }
 
+// features fp32 [rows][39200] in the reference's flatten order (drqv2.py:66) -> TB(128) bf16 in the encoder-output
+// order (stage API: update_critic / update_actor on externally supplied features)
+__global__ void __launch_bounds__(256)
+pack_features_tb_kernel(const float* __restrict__ f, __nv_bfloat16* __restrict__ out, int rows) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float tile[32][33];
+    pack_trunk_tb_block<DRQ_TB_ACT>(f, out, rows, blockIdx.x, blockIdx.y, threadIdx.x, tile);
+}
+
 }  // namespace drq
 
 using namespace drq;
@@ -519,6 +529,15 @@ int drq_pack_trunk_tb(const float* w, uint16_t* out, int rows, void* stream) {
     launch_k(pack_trunk_tb_kernel, dim3((1225 + 31) / 32, rpad), 256, 0, as_stream(stream), 
         w, reinterpret_cast<__nv_bfloat16*>(out), rows);
     return check_launch("pack_trunk_tb_kernel");
+}
+
+int drq_pack_features_tb(const float* feat, uint16_t* out, int rows, void* stream) {
+    DRQ_REQUIRE(feat && out && rows > 0, "pack_features_tb: bad args");
+    DRQ_REQUIRE(((uintptr_t)out % 16) == 0, "pack_features_tb: output must be 16-byte aligned");
+    const int rpad = (rows + RA - 1) / RA * RA;
+    launch_k(pack_features_tb_kernel, dim3((1225 + 31) / 32, rpad), 256, 0, as_stream(stream),
+        feat, reinterpret_cast<__nv_bfloat16*>(out), rows);
+    return check_launch("pack_features_tb_kernel");
 }
 
 }  // extern "C"

@@ -31,6 +31,7 @@ __device__ __forceinline__ void pack_linear_tb_block(const float* __restrict__ w
 
 // trunk weight fp32 [rows][32*1225] (reference NCHW-flatten columns c*1225+yx) -> TB(64) bf16 with the feature
 // order of the bf16 encoder output, n' = (c/8)*9800 + yx*8 + c%8: unit (c/8)*1225 + yx.  Block (bx, r): 32 pixels of weight row r, 32x32 transpose in `tile`.
+template <int R = DRQ_TB_W>
 __device__ __forceinline__ void pack_trunk_tb_block(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows,
                                                     int bx, int r, int tid, float (*tile)[33]) {
     const int yx0 = bx * 32;
@@ -50,7 +51,7 @@ __device__ __forceinline__ void pack_trunk_tb_block(const float* __restrict__ w,
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) pk[j] = tc::pack_bf16x2(tile[cu * 8 + 2 * j][i], tile[cu * 8 + 2 * j + 1][i]);
-            *reinterpret_cast<uint4*>(out + tb_off(r, cu * 1225 + yx, DRQ_REPR_DIM / 8, DRQ_TB_W)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(out + tb_off(r, cu * 1225 + yx, DRQ_REPR_DIM / 8, R)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
 }

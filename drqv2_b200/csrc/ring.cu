@@ -27,11 +27,16 @@ int check_launch(const char* what) {
 }
 
 int ensure_smem(const void* kernel, size_t bytes, const char* what) {
-    static const void* seen_fn[64];
-    static size_t seen_bytes[64];
+    // the opt-in is a per-device function attribute: the cache is keyed by (device, kernel)
+    constexpr int kMax = 512;
+    static const void* seen_fn[kMax];
+    static size_t seen_bytes[kMax];
+    static int seen_dev[kMax];
     static int n_seen = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
     for (int i = 0; i < n_seen; ++i)
-        if (seen_fn[i] == kernel && seen_bytes[i] >= bytes) return DRQ_OK;
+        if (seen_fn[i] == kernel && seen_dev[i] == dev && seen_bytes[i] >= bytes) return DRQ_OK;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         set_error("%s: cudaFuncSetAttribute(%zu): %s", what, bytes, cudaGetErrorString(e));
@@ -39,9 +44,9 @@ int ensure_smem(const void* kernel, size_t bytes, const char* what) {
     }
     int slot = -1;
     for (int i = 0; i < n_seen; ++i)
-        if (seen_fn[i] == kernel) slot = i;
-    if (slot < 0 && n_seen < 64) slot = n_seen++;
-    if (slot >= 0) { seen_fn[slot] = kernel; seen_bytes[slot] = bytes; }
+        if (seen_fn[i] == kernel && seen_dev[i] == dev) slot = i;
+    if (slot < 0 && n_seen < kMax) slot = n_seen++;
+    if (slot >= 0) { seen_fn[slot] = kernel; seen_bytes[slot] = bytes; seen_dev[slot] = dev; }
     return DRQ_OK;
 }
 
@@ -178,10 +183,10 @@ __global__ void __launch_bounds__(1024) update_prologue_kernel(const float* scal
                                                                float* __restrict__ eps_c, float* __restrict__ eps_a, int B, int A) {
     pdl_trigger();
     pdl_wait();
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < DRQ_SCAL_SLOT) {
         const unsigned long long cur = *cursor;
-        scal_out[threadIdx.x] = *reinterpret_cast<const volatile float*>(scal_ring + (cur % (unsigned long long)slots) * 16 + threadIdx.x);
-        __syncwarp(0xFFFFu);
+        scal_out[threadIdx.x] = *reinterpret_cast<const volatile float*>(scal_ring + (cur % (unsigned long long)slots) * DRQ_SCAL_SLOT + threadIdx.x);
+        __syncwarp();
         if (threadIdx.x == 0) *cursor = cur + 1ull;
     }
     if (shift_obs) {
@@ -214,14 +219,14 @@ __global__ void counter_advance_kernel(unsigned long long* counter) {
     pdl_trigger();
     pdl_wait(); *counter += 1ull; }
 
-// out[0..16) = ring[cursor % slots][0..16); cursor += 1.  The ring is pinned host memory the host fills one
+// out[0..DRQ_SCAL_SLOT) = ring[cursor % slots][..]; cursor += 1.  The ring is pinned host memory the host fills one
 // update ahead of the device: a CUDA graph cannot take new scalars per replay, and a fixed staging buffer
 // would be overwritten by a host that enqueues updates faster than the device runs them.
 __global__ void scalars_fetch_kernel(const float* ring, int slots, unsigned long long* cursor, float* out) {
     pdl_trigger();
     pdl_wait();
     const unsigned long long c = *cursor;
-    const float v = *reinterpret_cast<const volatile float*>(ring + (c % (unsigned long long)slots) * 16 + threadIdx.x);
+    const float v = *reinterpret_cast<const volatile float*>(ring + (c % (unsigned long long)slots) * DRQ_SCAL_SLOT + threadIdx.x);
     out[threadIdx.x] = v;
     __syncwarp();
     if (threadIdx.x == 0) *cursor = c + 1ull;
@@ -362,7 +367,7 @@ int drq_update_prologue(const float* scal_ring, int slots, uint64_t* cursor, flo
 
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream) {
     DRQ_REQUIRE(ring && cursor && out && slots > 0, "scalars_fetch: bad arguments");
-    launch_k(scalars_fetch_kernel, 1, 16, 0, as_stream(stream), ring, slots, (unsigned long long*)cursor, out);
+    launch_k(scalars_fetch_kernel, 1, DRQ_SCAL_SLOT, 0, as_stream(stream), ring, slots, (unsigned long long*)cursor, out);
     return check_launch("scalars_fetch_kernel");
 }
 

@@ -11,6 +11,7 @@ built extension or without a CUDA device these classes raise.
 from __future__ import annotations
 
 import contextlib
+import functools
 import gc
 import math
 
@@ -24,10 +25,26 @@ from . import _bf16, _lib, dist as _dist, utils
 from ._lib import EPI_MASK, EPI_MASK_WIDE, EPI_NONE, EPI_RELU, PLANE, REPR_DIM, call
 
 F32 = 4
+# One slot of per-update host scalars (include/drqv2_b200.h DRQ_SCAL_SLOT): Adam scalars (utils.adam_scalars, 8 floats)
+# of critic_opt at [0, 8), stddev(step) at [8], encoder_opt at [16, 24), actor_opt at [24, 32).
+SCAL_SLOT = 32
+SCAL_OFF = dict(critic=0, stddev=8, encoder=16, actor=24)
 
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run a DrQV2Agent method with the agent's device current: kernels are launched on the current device and
+    stream while the tensors live on self._dev (DrQV2Agent(device='cuda:1') must not need a set_device call)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_device() == self._dev.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self._dev):
+            return fn(self, *a, **kw)
+    return wrapped
 
 
 def _need_cuda(t, what):
@@ -278,7 +295,10 @@ class _Arena:
             off += n
         self.total = off
         self.params = torch.zeros(off, device=device)
-        self.grads = torch.zeros(off, device=device)
+        # data-parallel updates average the 8 metrics with the last gradient all-reduce: they live right behind the
+        # actor's gradients (the last segment), see DrQV2Agent._sync_grads
+        self._grads_full = torch.zeros(off + 8, device=device)
+        self.grads, self.metrics_tail = self._grads_full[:off], self._grads_full[off:]
         self.moments = torch.zeros(2, off, device=device)        # [exp_avg | exp_avg_sq], one range (L2 persistence)
         self.exp_avg, self.exp_avg_sq = self.moments[0], self.moments[1]
         n_t = self.seg["critic"][2]
@@ -369,7 +389,7 @@ class _Opt:
 
     def state_dict(self):
         a = self._agent._arena
-        return dict(step=self._agent._opt_step, exp_avg=self._flat(a.exp_avg), exp_avg_sq=self._flat(a.exp_avg_sq),
+        return dict(step=self._agent._opt_steps[self.net], exp_avg=self._flat(a.exp_avg), exp_avg_sq=self._flat(a.exp_avg_sq),
                     **self.defaults)
 
     def zero_grad(self, set_to_none=True):
@@ -388,7 +408,8 @@ class DrQV2Agent:
         """Reference signature (drqv2.py:125-127) plus three keyword-only extras: use_cuda_graph,
         seed (device RNG key) and mode — "fp32" (parity mode, CUDA-core kernels, <= 1e-4 vs the
         reference on pre-optimiser quantities) or "bf16" (tcgen05 tensor-core kernels, bf16
-        operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "fp32".
+        operands / fp32 accumulation).  Default: $DRQV2_B200_MODE or "bf16" (the performance mode; its
+        parity against the bf16-faithful oracle is pinned in tests/test_gpu_bench_config.py).
         data_parallel=True (torch.distributed initialised, one process per GPU): the batch given to
         update() is this rank's shard; gradients are averaged over ranks before each optimiser step and
         parameters are broadcast from rank 0 at construction (drqv2_b200/dist.py).
@@ -400,6 +421,8 @@ class DrQV2Agent:
             raise RuntimeError(f"DrQV2Agent(device={device!r}): drqv2_b200 has no CPU path; use a CUDA device")
         if not torch.cuda.is_available():
             raise RuntimeError("DrQV2Agent: no CUDA device available (drqv2_b200 has no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         _lib.lib()   # fail loudly if the extension is missing
         self.device = device
         self.critic_target_tau = critic_target_tau
@@ -415,10 +438,16 @@ class DrQV2Agent:
         self.overlap_encoder_backward = os.environ.get("DRQV2_B200_OVERLAP", "1") != "0"
         self._side_stream = None
         self._side_stream2 = None
-        self.mode = mode or os.environ.get("DRQV2_B200_MODE", "fp32")
+        self.mode = mode or os.environ.get("DRQV2_B200_MODE", "bf16")
         if self.mode not in ("fp32", "bf16"):
             raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
         self.obs_shape = tuple(int(v) for v in obs_shape)
+        # conv1's loaders stage a fixed number of input channels: the fp32 kernel up to 16, the tensor-core im2col
+        # (K = 9 cin + 1 <= 96) up to 10 (csrc/encoder_f32.cu, csrc/conv1_tc.cu); frame_stack 3 x RGB is 9
+        max_cin = 10 if self.mode == "bf16" else 16
+        if len(self.obs_shape) != 3 or self.obs_shape[1:] != (84, 84) or not 1 <= self.obs_shape[0] <= max_cin:
+            raise ValueError(f"obs_shape {self.obs_shape}: mode={self.mode!r} supports [C, 84, 84] observations with "
+                             f"1 <= C <= {max_cin} stacked channels (drqv2.py:53 fixes 84 x 84)")
         self.action_dim = int(action_shape[0])
         self.feature_dim, self.hidden_dim = int(feature_dim), int(hidden_dim)
 
@@ -434,7 +463,7 @@ class DrQV2Agent:
         self.actor_opt = _Opt(self, "actor", lr)
         self.critic_opt = _Opt(self, "critic", lr)
         self.aug = RandomShiftsAug(pad=4)
-        self._opt_step = 0
+        self._opt_steps = dict(encoder=0, critic=0, actor=0)   # torch.optim.Adam keeps one step count per optimiser
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self.data_parallel = bool(data_parallel) and _dist.world() > 1
         if self.data_parallel:
@@ -454,8 +483,8 @@ class DrQV2Agent:
         self._ws = {}
         self._graphs = {}
         self._act_ws = {}
-        self._scal_host = torch.zeros(16, dtype=torch.float32).pin_memory()
-        self._scal_dev = torch.zeros(16, device=dev)        # [0..7] adam scalars, [8] stddev
+        self._scal_host = torch.zeros(SCAL_SLOT, dtype=torch.float32).pin_memory()
+        self._scal_dev = torch.zeros(SCAL_SLOT, device=dev)   # layout: SCAL_OFF
         self._init_scalar_ring()
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -499,6 +528,7 @@ class DrQV2Agent:
         self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None
         self._bf16_dirty = True
 
+    @_on_device
     def refresh(self):
         """Re-derive the bf16 operand copies after parameters were changed from outside
         (load_state_dict, manual edits).  No-op in fp32 mode."""
@@ -515,9 +545,10 @@ class DrQV2Agent:
         with torch.no_grad():
             for net in self._NETS + ("critic_target",):
                 getattr(self, net).load_state_dict(getattr(ref, net).state_dict())
-            a, step = self._arena, 0
+            a = self._arena
             for net in self._NETS:
                 opt = getattr(ref, f"{net}_opt")
+                step = 0
                 for (pname, _), rp in zip(getattr(self, net).named_parameters(), getattr(ref, net).parameters()):
                     st = opt.state.get(rp, {})
                     off = a.offsets[net][pname]
@@ -529,7 +560,7 @@ class DrQV2Agent:
                     else:
                         a.exp_avg[off:off + n].zero_()
                         a.exp_avg_sq[off:off + n].zero_()
-            self._opt_step = step
+                self._opt_steps[net] = step
         self._bf16_dirty = True
         return self
 
@@ -545,8 +576,8 @@ class DrQV2Agent:
             state = {}
             for i, (pname, p) in enumerate(getattr(self, net).named_parameters()):
                 off, n = a.offsets[net][pname], p.numel()
-                if self._opt_step > 0:
-                    state[i] = dict(step=torch.tensor(float(self._opt_step)),
+                if self._opt_steps[net] > 0:
+                    state[i] = dict(step=torch.tensor(float(self._opt_steps[net])),
                                     exp_avg=a.exp_avg[off:off + n].view(p.shape).clone(),
                                     exp_avg_sq=a.exp_avg_sq[off:off + n].view(p.shape).clone())
             group = dict(lr=self.lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False,
@@ -566,6 +597,8 @@ class DrQV2Agent:
         if ws is None:
             ws = _Workspace(B, self.action_dim, self.feature_dim, self.hidden_dim, self.obs_shape[0], self._dev,
                             fp32_encoder=self.mode == "fp32")
+            if self.data_parallel:
+                ws.metrics = self._arena.metrics_tail      # averaged over the ranks with the actor's gradients
             self._ws[B] = ws
         return ws
 
@@ -582,15 +615,20 @@ class DrQV2Agent:
         in order (drqv2.py:241-242, utils.py:119 twice)."""
         self._injected = (shift_obs, shift_next, eps_critic, eps_actor)
 
-    def _sync_grads(self, first, last=None):
-        """Data-parallel: average the gradient range of nets first..last over the ranks (in stream order,
-        inside the graph).  No-op for a single process."""
+    def _sync_grads(self, first, last=None, metrics=False):
+        """Data-parallel: average the gradient range of nets first..last over the ranks (in stream order, on the
+        current stream, inside the graph); metrics=True (with the actor, the arena's last segment) takes the
+        update's 8 metrics along in the same all-reduce - they are batch means (drqv2.py:191-196,223-226), so
+        the mean over ranks of the shard means is the global-batch value.  No-op for a single process."""
         if not self.data_parallel:
             return
         a = self._arena
         off = a.seg[first][0]
         end = a.seg[last or first][0] + a.seg[last or first][2]
-        _dist.average_(a.grads[off:end])
+        if metrics:
+            assert end == a.total
+            end += 8
+        _dist.average_(a._grads_full[off:end])
 
     def _p(self, net, pname):
         return self._arena.ptr("params", net, pname)
@@ -602,6 +640,7 @@ class DrQV2Agent:
         return self._arena.target.data_ptr() + F32 * self._arena.offsets["critic"][pname] - F32 * self._arena.seg["critic"][0]
 
     # ------------------------------------------------------------------ act
+    @_on_device
     def act(self, obs, step, eval_mode):
         """drqv2.py:164-175: encoder + actor at batch 1, mean in eval mode, else an
         exploration sample (noise not clipped), uniform before num_expl_steps."""
@@ -654,7 +693,8 @@ class DrQV2Agent:
         torch.cuda.current_stream().synchronize()
         action = w["host_out"].numpy().copy()
         if sample and step < self.num_expl_steps:
-            action = np.random.uniform(-1.0, 1.0, size=action.shape).astype(np.float32)
+            # drqv2.py:174 action.uniform_(-1.0, 1.0): torch's global generator, so torch.manual_seed reproduces it
+            action = torch.empty(action.shape, dtype=torch.float32).uniform_(-1.0, 1.0).numpy()
         return action if batched else action[0]
 
     def _act_body(self, w, n, sample):
@@ -675,7 +715,7 @@ class DrQV2Agent:
         _linear_fwd(w["p1"].data_ptr(), H, pa("policy.2.weight"), pa("policy.2.bias"), w["p2"].data_ptr(), H, n, H, H, True)
         _linear_fwd(w["p2"].data_ptr(), H, pa("policy.4.weight"), pa("policy.4.bias"), w["mu_pre"].data_ptr(), A, n, A, H, False)
         call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
-             self._scal_dev.data_ptr() + F32 * 8, 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, _stream())
+             self._sc("stddev"), 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, _stream())
 
     # ------------------------------------------------------------------ update
     def update(self, replay_iter, step):
@@ -686,6 +726,7 @@ class DrQV2Agent:
             return dict()
         return self.read_metrics(ws)
 
+    @_on_device
     def read_metrics(self, ws):
         """The metrics of the update last enqueued on the current stream (one 32-byte D2H copy and a
         stream synchronise; drqv2.py:191-196,223-226)."""
@@ -693,6 +734,7 @@ class DrQV2Agent:
         torch.cuda.current_stream().synchronize()
         return dict(zip(METRIC_KEYS, self._metrics_host.tolist()))
 
+    @_on_device
     def update_async(self, replay_iter, step):
         """update() without the metrics read-back: enqueues the whole update on the current stream and
         returns its workspace (None when step % update_every_steps != 0) - no host synchronisation, so
@@ -732,24 +774,39 @@ class DrQV2Agent:
             ws.shift[B:].copy_(torch.as_tensor(inj[1]).to(torch.int32).view(B, 2))
             ws.eps_c.copy_(torch.as_tensor(inj[2]).view(B, -1))
             ws.eps_a.copy_(torch.as_tensor(inj[3]).view(B, -1))
-        key = (B, fetch is not None, inj is None)
+        # a captured graph bakes in the ring iterator's pointers and constants (frames, episode table, sampler
+        # counter, n-step, discount): one graph per source, not per batch size alone
+        src = getattr(replay_iter, "graph_key", None) if fetch is not None else None
+        if fetch is not None and src is None:
+            src = id(replay_iter)
+        key = (B, src, inj is None)
+        if fetch is not None and hasattr(replay_iter, "check_ready"):
+            replay_iter.check_ready()              # a replayed graph cannot raise: an empty ring is refused here
         state = self._graphs.get(key) if self.use_cuda_graph else None
-        if not self.use_cuda_graph:
-            self._update_body(ws, fetch, draw=inj is None)
-        elif state is None:
-            # first call at this shape runs eagerly: it is the warm-up (lazy module loading,
-            # shared-memory opt-in) that must not happen inside a capture
-            self._update_body(ws, fetch, draw=inj is None)
-            self._graphs[key] = "warm"
-        else:
-            if state == "warm":
-                torch.cuda.synchronize()
-                state = torch.cuda.CUDAGraph()
-                with _capture(state):
-                    self._update_body(ws, fetch, draw=inj is None)
-                self._graphs[key] = state
-            state.replay()
-        self._opt_step += 1
+        try:
+            if not self.use_cuda_graph:
+                self._update_body(ws, fetch, draw=inj is None)
+            elif state is None:
+                # first call at this shape runs eagerly: it is the warm-up (lazy module loading,
+                # shared-memory opt-in) that must not happen inside a capture
+                self._update_body(ws, fetch, draw=inj is None)
+                self._graphs[key] = "warm"
+            else:
+                if state == "warm":
+                    torch.cuda.synchronize()
+                    state = torch.cuda.CUDAGraph()
+                    with _capture(state):
+                        self._update_body(ws, fetch, draw=inj is None)
+                    self._graphs[key] = state
+                state.replay()
+        except BaseException:
+            # the device cursor of the scalar ring may or may not have advanced: put it back in step with the host's
+            # count, so that later updates do not read another update's slot
+            torch.cuda.synchronize()
+            self._scal_cursor.fill_(self._scal_enq)
+            raise
+        for net in self._opt_steps:
+            self._opt_steps[net] += 1
         self._scalars_enqueued()
         if fetch is None and self.prefetch:
             self._start_prefetch(replay_iter, ws)
@@ -798,13 +855,23 @@ class DrQV2Agent:
     def _init_scalar_ring(self):
         """Pinned ring of per-update scalars the device reads in stream order (drq_scalars_fetch): the host may
         enqueue up to _SCAL_SLOTS / 2 updates ahead of the device without overwriting a slot still to be read."""
-        self._scal_ring = torch.zeros(self._SCAL_SLOTS, 16, dtype=torch.float32).pin_memory()
+        self._scal_ring = torch.zeros(self._SCAL_SLOTS, SCAL_SLOT, dtype=torch.float32).pin_memory()
         self._scal_cursor = torch.zeros(1, dtype=torch.int64, device=self._dev)
         self._scal_enq = 0
         self._scal_events = [None, None]
 
-    def _host_scalars(self, step):
-        """Adam scalars of the coming optimiser step and stddev(step) into the ring slot the device reads next."""
+    @property
+    def _opt_step(self):
+        """optimiser steps taken by update() (the three counts differ only when the stage API is driven unevenly)"""
+        return self._opt_steps["critic"]
+
+    def _sc(self, net):
+        """device pointer of `net`'s Adam scalars (or of 'stddev') for the update being enqueued"""
+        return self._scal_dev.data_ptr() + F32 * SCAL_OFF[net]
+
+    def _host_scalars(self, step, stepping=("encoder", "critic", "actor")):
+        """Adam scalars of the coming step of the optimisers in `stepping` (each with its own step count, as
+        torch.optim.Adam) and stddev(step) into the ring slot the device reads next."""
         half = self._SCAL_SLOTS // 2
         slot = self._scal_enq % self._SCAL_SLOTS
         if slot % half == 0:                       # entering a half of the ring: its previous readers must be done
@@ -812,9 +879,10 @@ class DrQV2Agent:
             if ev is not None:
                 ev.synchronize()
         stddev = utils.schedule(self.stddev_schedule, step)
-        sc = utils.adam_scalars(self.lr, self._opt_step + 1)
-        self._scal_host[:8] = torch.from_numpy(sc)
-        self._scal_host[8] = stddev
+        for net in stepping:
+            o = SCAL_OFF[net]
+            self._scal_host[o:o + 8] = torch.from_numpy(utils.adam_scalars(self.lr, self._opt_steps[net] + 1))
+        self._scal_host[SCAL_OFF["stddev"]] = stddev
         self._scal_ring[slot].copy_(self._scal_host)
         self._stddev = stddev
 
@@ -835,8 +903,9 @@ class DrQV2Agent:
 
     def _encoder_side_stream(self):
         """Second stream for the encoder backward + encoder_opt.step() of the bf16 update (None: run in line).
-        Data-parallel updates keep one stream: their gradient all-reduce covers encoder and critic together."""
-        if not self.overlap_encoder_backward or self.data_parallel or self.mode != "bf16":
+        Data-parallel updates use it too: the critic's gradient all-reduce, critic_opt.step() and the actor pass run
+        beside the encoder backward; the encoder's own (30 k floats) all-reduce follows the join (_update_body)."""
+        if not self.overlap_encoder_backward or self.mode != "bf16":
             return None
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self._dev)
@@ -844,7 +913,7 @@ class DrQV2Agent:
 
     def _wgrad_side_stream(self):
         """Third stream: the weight-gradient GEMMs / bias-gradient sums run beside the data-gradient chain."""
-        if not self.overlap_encoder_backward or self.data_parallel or self.mode != "bf16":
+        if not self.overlap_encoder_backward or self.mode != "bf16":
             return None
         if self._side_stream2 is None:
             self._side_stream2 = torch.cuda.Stream(device=self._dev)
@@ -870,6 +939,9 @@ class DrQV2Agent:
             side = self._encoder_side_stream()
             if side is not None:                    # the encoder backward ran beside the actor pass
                 torch.cuda.current_stream().wait_stream(side)
+                if self.data_parallel:              # encoder_opt.step() of a data-parallel update: after its all-reduce
+                    self._sync_grads("encoder")
+                    self._bf16.step_encoder()
             return
         self._encode(ws)
         self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=True)
@@ -904,7 +976,7 @@ class DrQV2Agent:
         pc = lambda k: self._p("critic", k)
         gc = lambda k: self._g("critic", k)
         pa = lambda k: self._p("actor", k)
-        std_ptr = self._scal_dev.data_ptr() + F32 * 8
+        std_ptr = self._sc("stddev")
         qs = self._q_strides()
         featp, featn = feat.data_ptr(), feat_next.data_ptr()
         # --- target: online actor on next features -> clipped sample (drqv2.py:181-183)
@@ -953,15 +1025,18 @@ class DrQV2Agent:
             self._encoder_bwd(ws, featp)
         # --- critic_opt.step(); encoder_opt.step() (drqv2.py:201-202): [encoder|critic] is one range
         a = self._arena
+        ranges = [("critic", a.seg["critic"][0], a.seg["critic"][2])]
         if encoder_grad:
-            off, n = a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2]
             self._sync_grads("encoder", "critic")
+            if self._opt_steps["encoder"] == self._opt_steps["critic"]:   # same Adam scalars: [encoder|critic] is one range
+                ranges = [("critic", a.seg["encoder"][0], a.seg["encoder"][2] + a.seg["critic"][2])]
+            else:
+                ranges.append(("encoder", a.seg["encoder"][0], a.seg["encoder"][2]))
         else:
-            off, n = a.seg["critic"][0], a.seg["critic"][2]
             self._sync_grads("critic")
-        call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
-             a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n,
-             self._scal_dev.data_ptr(), s)
+        for net, off, n in ranges:
+            call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+                 a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, self._sc(net), s)
 
     def _encoder_bwd(self, ws, featp):
         """Backward of the 4-conv encoder on the obs half of the batch (drqv2.py:200)."""
@@ -984,14 +1059,15 @@ class DrQV2Agent:
         call("drq_conv1_wgrad_f32", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], wsp, ge("convnet.0.weight"),
              ge("convnet.0.bias"), B, self.obs_shape[0], self.aug.pad, s)
 
-    def _actor_pass(self, ws, feat):
-        """update_actor (drqv2.py:206-228) + actor Adam + soft target update (drqv2.py:259-260)."""
+    def _actor_pass(self, ws, feat, soft_update=True):
+        """update_actor (drqv2.py:206-228) + actor Adam and, when called from update(), the soft target update
+        (drqv2.py:259-260) in the same launch."""
         B, A, Fd, H = ws.B, self.action_dim, self.feature_dim, self.hidden_dim
         s = _stream()
         pc = lambda k: self._p("critic", k)
         pa = lambda k: self._p("actor", k)
         ga = lambda k: self._g("actor", k)
-        std_ptr = self._scal_dev.data_ptr() + F32 * 8
+        std_ptr = self._sc("stddev")
         qs = self._q_strides()
         featp = feat.data_ptr()
         BH = B * H
@@ -1032,15 +1108,19 @@ class DrQV2Agent:
              ga("trunk.1.bias"), None, 0, B, Fd, 1, 0, s)
         _linear_wgrad(ws.dz.data_ptr(), Fd, featp, REPR_DIM, ga("trunk.0.weight"), B, Fd, REPR_DIM)
         _colsum(ws.dz.data_ptr(), Fd, ga("trunk.0.bias"), B, Fd)
-        self._sync_grads("actor")
-        # actor_opt.step() fused with the soft target update of the (already stepped) critic
+        self._sync_grads("actor", metrics=True)
+        # actor_opt.step(), in update() fused with the soft target update of the (already stepped) critic
         a = self._arena
         off, n = a.seg["actor"][0], a.seg["actor"][2]
         coff, cn = a.seg["critic"][0], a.seg["critic"][2]
         tau = float(self.critic_target_tau)
-        call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
-             a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, self._scal_dev.data_ptr(),
-             a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, tau, float(1 - tau), s)
+        if soft_update:
+            call("drq_adam_ema_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+                 a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, self._sc("actor"),
+                 a.params.data_ptr() + F32 * coff, a.target.data_ptr(), cn, tau, float(1 - tau), s)
+        else:
+            call("drq_adam_step", a.params.data_ptr() + F32 * off, a.grads.data_ptr() + F32 * off,
+                 a.exp_avg.data_ptr() + F32 * off, a.exp_avg_sq.data_ptr() + F32 * off, n, self._sc("actor"), s)
 
     # ------------------------------------------------------------------ public stage API
     def _stage_inputs(self, ws, **named):
@@ -1050,48 +1130,85 @@ class DrQV2Agent:
             if v.data_ptr() != dst.data_ptr():
                 dst.copy_(v.view(dst.shape))
 
-    def update_critic(self, obs, action, reward, discount, next_obs, step):
-        """drqv2.py:177-204 on encoded features [B, 39200].  When `obs` is the feature
-        buffer produced by this agent's own encode (as in update()), the encoder is
-        updated too, as autograd would; detached features leave it untouched."""
-        if self.mode != "fp32":
-            raise RuntimeError("update_critic on externally supplied features is available in mode='fp32' only "
-                               "(bf16 mode keeps features in its own NHWC bf16 layout); use update()")
-        B = obs.shape[0]
-        ws = self.workspace(B)
-        own = obs.data_ptr() == ws.feat.data_ptr()
-        if not own:
-            ws.feat[:B].copy_(obs)
-        if next_obs.data_ptr() != ws.feat[B:].data_ptr():
-            ws.feat[B:].copy_(next_obs)
-        self._stage_inputs(ws, action=action, reward=reward, discount=discount)
-        self._host_scalars(step)
+    def _stage_features(self, ws, feat, row0):
+        """Encoded features [B, 39200] (reference order c*1225 + yx, drqv2.py:66) into the update's buffers: the
+        fp32 feature matrix, or in bf16 mode the TB operand in the encoder-output order (one pack kernel)."""
+        B = ws.B
+        feat = torch.as_tensor(feat, device=self._dev)
+        if self.mode == "fp32":
+            dst = ws.feat[row0 * B:(row0 + 1) * B]
+            if feat.data_ptr() != dst.data_ptr():
+                dst.copy_(feat)
+            return
+        bw = self.bf16_workspace(B)
+        feat = feat.float().contiguous()
+        call("drq_pack_features_tb", feat.data_ptr(), bw.feat.ptr(row=row0 * bw.RB), B, _stream())
+
+    def _stage_noise(self, dst, which):
+        """N(0,1) draw of a stage-API call (utils.py:119): the injected one (inject_draws slot `which`), else the
+        device generator."""
+        inj = self._injected
+        if inj is not None and inj[which] is not None:
+            dst.copy_(torch.as_tensor(inj[which]).view(dst.shape))
+            inj = list(inj)
+            inj[which] = None
+            self._injected = inj if any(v is not None for v in inj[2:]) else None
+            return
+        call("drq_rng_normal_f32", self._seed, self._counter.data_ptr(), dst.data_ptr(), dst.numel(), _stream())
+        call("drq_counter_advance", self._counter.data_ptr(), _stream())
+
+    def _stage_scalars(self, step, stepping):
+        self._host_scalars(step, stepping)
         self._fetch_scalars()
         self._scalars_enqueued()
-        self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=own)
-        metrics = dict()
-        if self.use_tb:
-            m = ws.metrics.tolist()
-            metrics = dict(critic_target_q=m[1], critic_q1=m[2], critic_q2=m[3], critic_loss=m[4])
-        return metrics
+        if self._bf16_dirty:
+            self.refresh()
+
+    def update_critic(self, obs, action, reward, discount, next_obs, step):
+        """drqv2.py:177-204 on encoded features [B, 39200]: critic loss, backward, critic_opt.step().
+        fp32 mode: when `obs` is the feature buffer this agent's own encode produced (as inside update()), the
+        encoder receives its gradient and steps too, as autograd would; any other tensor is a detached input
+        and leaves the encoder untouched (a reference encoder whose gradients are None is skipped by Adam in the
+        same way).  bf16 mode: features are always external (the tensor-core encoder keeps its output in its own
+        bf16 layout), so only the critic is updated."""
+        with torch.cuda.device(self._dev):
+            B = obs.shape[0]
+            ws = self.workspace(B)
+            own = self.mode == "fp32" and obs.data_ptr() == ws.feat.data_ptr()
+            self._stage_features(ws, obs, 0)
+            self._stage_features(ws, next_obs, 1)
+            self._stage_inputs(ws, action=action, reward=reward, discount=discount)
+            stepping = ("encoder", "critic") if own else ("critic",)
+            self._stage_noise(ws.eps_c, 2)
+            self._stage_scalars(step, stepping)
+            if self.mode == "fp32":
+                self._critic_pass(ws, ws.feat[:B], ws.feat[B:], encoder_grad=own)
+            else:
+                _bf16.critic_pass(self, ws, self.bf16_workspace(B), encoder_grad=False)
+            for net in stepping:
+                self._opt_steps[net] += 1
+            metrics = dict()
+            if self.use_tb:
+                m = ws.metrics.tolist()
+                metrics = dict(critic_target_q=m[1], critic_q1=m[2], critic_q2=m[3], critic_loss=m[4])
+            return metrics
 
     def update_actor(self, obs, step):
-        """drqv2.py:206-228 on (detached) features; also performs the actor Adam step.
-        The soft target update that the fused kernel applies belongs to update(); callers of
-        this stage API who do not want it should snapshot the target first."""
-        if self.mode != "fp32":
-            raise RuntimeError("update_actor on externally supplied features is available in mode='fp32' only; "
-                               "use update()")
-        B = obs.shape[0]
-        ws = self.workspace(B)
-        if obs.data_ptr() != ws.feat.data_ptr():
-            ws.feat[:B].copy_(obs)
-        self._host_scalars(step)
-        self._fetch_scalars()
-        self._scalars_enqueued()
-        self._actor_pass(ws, ws.feat[:B])
-        metrics = dict()
-        if self.use_tb:
-            m = ws.metrics.tolist()
-            metrics = dict(actor_loss=m[5], actor_logprob=m[6], actor_ent=m[7])
-        return metrics
+        """drqv2.py:206-228 on (detached) features: actor loss, backward, actor_opt.step().  The target critic is
+        not touched (its soft update belongs to update(), drqv2.py:259-260)."""
+        with torch.cuda.device(self._dev):
+            B = obs.shape[0]
+            ws = self.workspace(B)
+            self._stage_features(ws, obs, 0)
+            self._stage_noise(ws.eps_a, 3)
+            self._stage_scalars(step, ("actor",))
+            if self.mode == "fp32":
+                self._actor_pass(ws, ws.feat[:B], soft_update=False)
+            else:
+                _bf16.actor_pass(self, ws, self.bf16_workspace(B), soft_update=False, standalone=True)
+            self._opt_steps["actor"] += 1
+            metrics = dict()
+            if self.use_tb:
+                m = ws.metrics.tolist()
+                metrics = dict(actor_loss=m[5], actor_logprob=m[6], actor_ent=m[7])
+            return metrics

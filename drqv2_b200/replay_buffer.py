@@ -260,6 +260,18 @@ class RingIterator:
         self._l = loader
         self.batch_size = loader.batch_size
 
+    @property
+    def graph_key(self):
+        """what a CUDA graph captured over next_into() bakes in: the ring's buffers and this loader's sampler
+        state and constants (DrQV2Agent keys its graphs by it)"""
+        l = self._l
+        ring = l.ring()
+        return (ring.frames.data_ptr(), ring.ep_table.data_ptr(), l._counter.data_ptr(), l.nstep, l.discount, l.seed)
+
+    def check_ready(self):
+        if getattr(self._l.ring(), "_n_eligible", 0) == 0:
+            raise RuntimeError("replay ring has no episode long enough to sample from")
+
     def __iter__(self):
         return self
 
@@ -275,17 +287,18 @@ class RingIterator:
         l = self._l
         ring = l.ring()
         B = l.batch_size
-        s = _stream()
-        if ep_start is None:
-            if getattr(ring, "_n_eligible", 0) == 0:
-                raise RuntimeError("replay ring has no episode long enough to sample from")
-            call("drq_ring_sample_step", ring.ep_table.data_ptr(), ring.n_episodes.data_ptr(), l.nstep, l.seed,
-                 l._counter.data_ptr(), l._ep_start.data_ptr(), l._idx.data_ptr(), B, s)     # draws, then counter += 1
-            ep_start, idx = l._ep_start, l._idx
-        call("drq_ring_gather_nstep", ring.frames.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
-             ring.discount.data_ptr(), ring.capacity, ring.frame_c, ring.stack, ring.A, ep_start.data_ptr(),
-             idx.data_ptr(), B, l.nstep, float(l.discount), obs.data_ptr(), next_obs.data_ptr(),
-             action.data_ptr(), reward.data_ptr(), discount.data_ptr(), s)
+        if ep_start is None and getattr(ring, "_n_eligible", 0) == 0:
+            raise RuntimeError("replay ring has no episode long enough to sample from")
+        with torch.cuda.device(ring.device):           # kernels launch on the current device: the ring's
+            s = _stream()
+            if ep_start is None:
+                call("drq_ring_sample_step", ring.ep_table.data_ptr(), ring.n_episodes.data_ptr(), l.nstep, l.seed,
+                     l._counter.data_ptr(), l._ep_start.data_ptr(), l._idx.data_ptr(), B, s)     # draws, then counter += 1
+                ep_start, idx = l._ep_start, l._idx
+            call("drq_ring_gather_nstep", ring.frames.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(),
+                 ring.discount.data_ptr(), ring.capacity, ring.frame_c, ring.stack, ring.A, ep_start.data_ptr(),
+                 idx.data_ptr(), B, l.nstep, float(l.discount), obs.data_ptr(), next_obs.data_ptr(),
+                 action.data_ptr(), reward.data_ptr(), discount.data_ptr(), s)
 
 
 class RingLoader:
@@ -298,7 +311,8 @@ class RingLoader:
             seed = int(np.random.get_state()[1][0])   # as replay_buffer.py:167-170 seeds its workers
         self.seed = seed
         self._obs = None
-        dev = torch.device("cuda")
+        ring = entry.get("ring")
+        dev = ring.device if ring is not None else torch.device("cuda", torch.cuda.current_device())
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._ep_start = torch.zeros(self.batch_size, dtype=torch.int32, device=dev)
         self._idx = torch.zeros(self.batch_size, dtype=torch.int32, device=dev)

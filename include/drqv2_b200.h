@@ -41,6 +41,7 @@
 extern "C" {
 #endif
 
+#define DRQ_SCAL_SLOT 32   /* floats per slot of the per-update host scalar ring (drq_scalars_fetch) */
 #define DRQ_ABI_VERSION 1
 
 #define DRQ_OK 0
@@ -119,8 +120,10 @@ int drq_rng_update_draws(uint64_t seed, const uint64_t* counter, int pad, int32_
 int drq_rng_normal_f32(uint64_t seed, const uint64_t* counter, float* out, int n, void* stream);
 int drq_counter_advance(uint64_t* counter, void* stream);
 
-/* Per-update host scalars for graph replays: out[0..16) = ring[*cursor % slots][0..16), then *cursor += 1.
- * `ring` is pinned (device-visible) host memory of slots x 16 floats that the host fills ahead of the device -
+/* Per-update host scalars for graph replays: out[0..DRQ_SCAL_SLOT) = ring[*cursor % slots][..], then *cursor += 1.
+ * One slot: Adam scalars (8 floats, see drq_adam_step) of critic_opt at [0, 8), stddev(step) at [8], encoder_opt at
+ * [16, 24), actor_opt at [24, 32) - torch.optim.Adam keeps a step count per optimiser (drqv2.py:148-150).
+ * `ring` is pinned (device-visible) host memory of slots x DRQ_SCAL_SLOT floats that the host fills ahead of the device -
  * the Adam bias corrections of torch/optim/adam.py:531-547 and the exploration stddev of utils.py:130-146 change
  * every update, a captured graph cannot take new arguments, and a single staging buffer would be overwritten by
  * a host that enqueues updates faster than the device runs them.  `cursor` is a device counter. */
@@ -279,6 +282,10 @@ int drq_pack_linear_tb(const float* w, uint16_t* out, int rows, int cols, void* 
 /* trunk Linear(39200->rows) weight -> TB(DRQ_TB_W) bf16 in the feature order (c/8)*9800 + (y*35+x)*8 + c%8
  * of the bf16 encoder output (reference column c*1225+y*35+x, drqv2.py:66). */
 int drq_pack_trunk_tb(const float* w, uint16_t* out, int rows, void* stream);
+/* encoded features fp32 [rows][39200] in the reference's flatten order (drqv2.py:66) -> TB(DRQ_TB_ACT) bf16 in the
+ * encoder-output feature order; `out` points at a 128-row block boundary of the feature operand.  Behind the stage
+ * API DrQV2Agent.update_critic / update_actor (drqv2.py:177,206), which take features, in the tensor-core mode. */
+int drq_pack_features_tb(const float* feat, uint16_t* out, int rows, void* stream);
 
 /* all bf16 operand re-packs of one optimiser phase in one launch.  kind LINEAR: drq_pack_linear_tb(w, out,
  * rows, cols); TRUNK: drq_pack_trunk_tb(w, out, rows); CONV: drq_pack_conv_w_bf16(w, out, out2);

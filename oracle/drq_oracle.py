@@ -279,6 +279,89 @@ def truncated_normal_sample(mu, std, eps, clip):
     return x - x.detach() + clamped.detach()
 
 
+# --------------------------------------------------------------------------- bf16-faithful variants
+# The tensor-core mode of the CUDA path (drqv2_b200/_bf16.py) keeps fp32 master parameters and fp32
+# accumulation but STORES its GEMM / conv operands in bf16: the weights' operand copies, every hidden
+# activation, the features, and the gradient operands of the backward GEMMs.  These variants restate the
+# same reference functions (file:line cited per function) with a round-to-bf16 at exactly those points, so
+# that a comparison with the kernels is not dominated by ReLU units that sit on the other side of zero
+# once an activation is rounded (tests/test_gpu_bf16.py).  Math between the rounding points is in self.dtype
+# (float64 in the tests).
+class _RoundBf16(torch.autograd.Function):
+    """value -> nearest bf16, gradient passed through (an operand copy of an fp32 master value)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGradBf16(torch.autograd.Function):
+    """identity whose incoming gradient is rounded to bf16 (a gradient stored as a bf16 GEMM operand)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def rb(x):
+    return _RoundBf16.apply(x)
+
+
+def gb(x):
+    return _RoundGradBf16.apply(x)
+
+
+def encoder_fwd_bf16(p, obs):
+    """Encoder.forward drqv2.py:63-67 as the tensor-core path computes it: exact pixels (conv1 feeds the
+    integers x - 128 and folds the affine map into its epilogue, csrc/conv1_tc.cu), bf16 weights, every
+    post-ReLU activation stored in bf16, every pre-activation gradient stored in bf16."""
+    h = obs / 255.0 - 0.5
+    for i, stride in zip((0, 2, 4, 6), (2, 1, 1, 1)):
+        pre = gb(F.conv2d(h, rb(p[f"convnet.{i}.weight"]), p[f"convnet.{i}.bias"], stride=stride))
+        h = rb(F.relu(pre))
+    return h.reshape(h.shape[0], -1)
+
+
+def trunk_fwd_bf16(p, feat):
+    """drqv2.py:74-75,100-101: bf16 features x bf16 weight, fp32 bias / LayerNorm / tanh; the gradient of the
+    Linear output feeds the weight- and data-gradient GEMMs in bf16, the bias gradient in fp32."""
+    z = gb(F.linear(feat, rb(p["trunk.0.weight"]))) + p["trunk.0.bias"]
+    z = F.layer_norm(z, (z.shape[-1],), p["trunk.1.weight"], p["trunk.1.bias"], eps=1e-5)
+    return torch.tanh(z)
+
+
+def _hidden_bf16(x, w, b):
+    return rb(F.relu(gb(F.linear(x, rb(w), b))))
+
+
+def actor_mu_bf16(p, feat):
+    """Actor.forward drqv2.py:85-89."""
+    h = rb(trunk_fwd_bf16(p, feat))
+    h = _hidden_bf16(h, p["policy.0.weight"], p["policy.0.bias"])
+    h = _hidden_bf16(h, p["policy.2.weight"], p["policy.2.bias"])
+    return torch.tanh(gb(F.linear(h, rb(p["policy.4.weight"]))) + p["policy.4.bias"])
+
+
+def critic_q_bf16(p, feat, action):
+    """Critic.forward drqv2.py:115-121; the scalar heads read the fp32 weights (csrc/heads.cu q_head_*)."""
+    h = trunk_fwd_bf16(p, feat)
+    x = rb(torch.cat([h, action], dim=-1))
+    qs = []
+    for q in ("Q1", "Q2"):
+        y = _hidden_bf16(x, p[f"{q}.0.weight"], p[f"{q}.0.bias"])
+        y = _hidden_bf16(y, p[f"{q}.2.weight"], p[f"{q}.2.bias"])
+        qs.append(F.linear(y, p[f"{q}.4.weight"], p[f"{q}.4.bias"]))
+    return qs[0], qs[1]
+
+
 # --------------------------------------------------------------------------- optimiser
 def adam_scalars(lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
     """Host-side float64 scalar math of torch/optim/adam.py:531-547, in the order of the
@@ -310,8 +393,16 @@ class OracleAgent:
     float64 = REF-64 of SURVEY §8c."""
 
     def __init__(self, params, lr, critic_target_tau, stddev_schedule, stddev_clip,
-                 dtype=torch.float32, aug="exact"):
+                 dtype=torch.float32, aug="exact", operands="exact"):
+        """operands="bf16": the bf16-faithful variants above (rounding where the tensor-core path stores
+        bf16 operands); "exact": the reference's arithmetic in `dtype`."""
         self.dtype = dtype
+        assert operands in ("exact", "bf16")
+        self.operands = operands
+        bf = operands == "bf16"
+        self._encoder_fwd = encoder_fwd_bf16 if bf else encoder_fwd
+        self._actor_mu = actor_mu_bf16 if bf else actor_mu
+        self._critic_q = critic_q_bf16 if bf else critic_q
         self.p = OrderedDict((net, OrderedDict((k, v.detach().clone().to(dtype)) for k, v in d.items()))
                              for net, d in params.items())
         self.lr, self.tau = lr, critic_target_tau
@@ -340,63 +431,60 @@ class OracleAgent:
             x = torch.as_tensor(obs_u8).to(self.dtype)
             if x.dim() == 3:
                 x = x.unsqueeze(0)
-            feat = encoder_fwd(self.p["encoder"], x)
-            mu = actor_mu(self.p["actor"], feat)
+            feat = self._encoder_fwd(self.p["encoder"], x)
+            mu = self._actor_mu(self.p["actor"], feat)
             if eval_mode:
                 return mu
             std = schedule(self.stddev_schedule, step)
             return truncated_normal_sample(mu, std, eps.to(self.dtype), None)
 
-    def update(self, obs_u8, action, reward, discount, next_obs_u8, step, shift_obs, shift_next,
-               eps_critic, eps_actor):
-        """One DrQV2Agent.update (drqv2.py:230-262) on an explicit batch.  Returns the
-        metrics dict; gradients of the three nets are kept in self.grads."""
+    def update_critic(self, feat, action, reward, discount, feat_next, step, eps_critic, enc=None):
+        """drqv2.py:177-204 on encoded features.  `enc`: the encoder parameters `feat` is attached to (as inside
+        update(), drqv2.py:244) - they receive the critic loss' gradient and encoder_opt steps (drqv2.py:202);
+        with detached features (enc=None) only critic_opt steps."""
         dt = self.dtype
         metrics = {}
         action, reward, discount = action.to(dt), reward.to(dt), discount.to(dt)
-        enc = {k: v.requires_grad_(True) for k, v in self.p["encoder"].items()}
         cri = {k: v.requires_grad_(True) for k, v in self.p["critic"].items()}
-        act = {k: v.requires_grad_(True) for k, v in self.p["actor"].items()}
-        tgt = self.p["critic_target"]
-        # augment + encode, drqv2.py:241-246
-        obs = self._aug(obs_u8.to(dt), shift_obs)
-        nxt = self._aug(next_obs_u8.to(dt), shift_next)
-        feat = encoder_fwd(enc, obs)
-        with torch.no_grad():
-            feat_next = encoder_fwd(enc, nxt)
-        metrics["batch_reward"] = reward.mean().item()
+        act, tgt = self.p["actor"], self.p["critic_target"]
         std = schedule(self.stddev_schedule, step)
-        # update_critic, drqv2.py:177-204
         with torch.no_grad():
-            mu_n = actor_mu(act, feat_next)
+            mu_n = self._actor_mu(act, feat_next)
             next_action = truncated_normal_sample(mu_n, std, eps_critic.to(dt), self.stddev_clip)
-            tq1, tq2 = critic_q(tgt, feat_next, next_action)
+            tq1, tq2 = self._critic_q(tgt, feat_next, next_action)
             target_q = reward + discount * torch.min(tq1, tq2)
-        q1, q2 = critic_q(cri, feat, action)
+        q1, q2 = self._critic_q(cri, feat, action)
         critic_loss = F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q)
         metrics.update(critic_target_q=target_q.mean().item(), critic_q1=q1.mean().item(),
                        critic_q2=q2.mean().item(), critic_loss=critic_loss.item())
         self.stage = dict(feat=feat.detach().clone(), feat_next=feat_next.clone(),
                           next_action=next_action.clone(), target_q=target_q.clone(),
                           q1=q1.detach().clone(), q2=q2.detach().clone())
-        names = list(enc) + list(cri)
+        enc = enc or {}
         gs = torch.autograd.grad(critic_loss, list(enc.values()) + list(cri.values()))
         g_enc = OrderedDict(zip(list(enc), gs[:len(enc)]))
         g_cri = OrderedDict(zip(list(cri), gs[len(enc):]))
-        del names
         for d in (enc, cri):
             for v in d.values():
                 v.requires_grad_(False)
         self._opt_step("critic", g_cri)
-        self._opt_step("encoder", g_enc)
-        # update_actor on detached features with the stepped critic, drqv2.py:206-228
+        if enc:
+            self._opt_step("encoder", g_enc)
+        self.grads.update(encoder=g_enc, critic=g_cri)
+        return metrics
+
+    def update_actor(self, feat, step, eps_actor):
+        """drqv2.py:206-228 on detached features, with the current (stepped) critic."""
+        dt = self.dtype
+        act = {k: v.requires_grad_(True) for k, v in self.p["actor"].items()}
+        std = schedule(self.stddev_schedule, step)
         feat_d = feat.detach()
-        mu = actor_mu(act, feat_d)
+        mu = self._actor_mu(act, feat_d)
         a = truncated_normal_sample(mu, std, eps_actor.to(dt), self.stddev_clip)
         var = torch.as_tensor(std, dtype=dt) ** 2
         log_prob = (-((a - mu) ** 2) / (2 * var) - math.log(std) - math.log(math.sqrt(2 * math.pi)))
         log_prob = log_prob.sum(-1, keepdim=True)
-        aq1, aq2 = critic_q(self.p["critic"], feat_d, a)
+        aq1, aq2 = self._critic_q(self.p["critic"], feat_d, a)
         actor_loss = -torch.min(aq1, aq2).mean()
         ga = torch.autograd.grad(actor_loss, list(act.values()))
         g_act = OrderedDict(zip(list(act), ga))
@@ -405,13 +493,34 @@ class OracleAgent:
         self.stage.update(actor_action=a.detach().clone(), actor_q1=aq1.detach().clone(),
                           actor_q2=aq2.detach().clone())
         self._opt_step("actor", g_act)
-        metrics.update(actor_loss=actor_loss.item(), actor_logprob=log_prob.mean().item(),
-                       actor_ent=float(mu.shape[-1] * (0.5 + 0.5 * math.log(2 * math.pi) + math.log(std))))
+        self.grads.update(actor=g_act)
+        return dict(actor_loss=actor_loss.item(), actor_logprob=log_prob.mean().item(),
+                    actor_ent=float(mu.shape[-1] * (0.5 + 0.5 * math.log(2 * math.pi) + math.log(std))))
+
+    def encode(self, obs_u8, shift, enc=None):
+        """aug + encoder (drqv2.py:241-246) with the shift draw injected"""
+        x = self._aug(torch.as_tensor(obs_u8).to(self.dtype), shift)
+        return self._encoder_fwd(enc if enc is not None else self.p["encoder"], x)
+
+    def update(self, obs_u8, action, reward, discount, next_obs_u8, step, shift_obs, shift_next,
+               eps_critic, eps_actor):
+        """One DrQV2Agent.update (drqv2.py:230-262) on an explicit batch.  Returns the
+        metrics dict; gradients of the three nets are kept in self.grads."""
+        dt = self.dtype
+        metrics = {}
+        enc = {k: v.requires_grad_(True) for k, v in self.p["encoder"].items()}
+        # augment + encode, drqv2.py:241-246
+        feat = self.encode(obs_u8, shift_obs, enc)
+        with torch.no_grad():
+            feat_next = self.encode(next_obs_u8, shift_next, enc)
+        metrics["batch_reward"] = reward.to(dt).mean().item()
+        # update_critic, drqv2.py:249-250; update_actor on detached features, drqv2.py:256
+        metrics.update(self.update_critic(feat, action, reward, discount, feat_next, step, eps_critic, enc=enc))
+        metrics.update(self.update_actor(feat.detach(), step, eps_actor))
         # soft target update, drqv2.py:259-260
         with torch.no_grad():
             for k in self.p["critic"]:
-                soft_update(self.p["critic"][k], tgt[k], self.tau)
-        self.grads = dict(encoder=g_enc, critic=g_cri, actor=g_act)
+                soft_update(self.p["critic"][k], self.p["critic_target"][k], self.tau)
         return metrics
 
 

@@ -1,0 +1,297 @@
+"""Parity at the configurations bench.py measures ("What's weak" #1): the whole update at
+B=256 / H=1024 (walker shape, BENCH) and B=512 (humanoid shape, one data-parallel shard), `act` at B=1024
+(quadruped shape), and the tcgen05 conv kernels at 512 images - enough tiles per CTA (>= 22) that the
+shared-memory stage ring and the TMEM accumulator ring of the persistent pipelines wrap several times.
+
+bf16 mode is compared with the oracle's bf16-faithful variant (oracle/drq_oracle.py: fp64 math, rounding to
+bf16 exactly where the kernels store bf16 operands), which removes the ReLU-flip noise of a comparison with
+pure fp64 and lets the gradient bound be 2e-2 instead of 0.15-0.3; the loose bound against pure fp64 stays
+in tests/test_gpu_bf16.py.  Reference: drqv2.py:230-262 on cfgs/config.yaml:21,32,44 shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import drq_oracle as O
+from tests.helpers import nchw_from_wb, rel_l2, wb_from_nchw
+
+pytestmark = pytest.mark.gpu
+
+SCHED = "linear(1.0,0.1,100000)"
+WALKER = dict(B=256, A=6, F=50, H=1024, lr=1e-4)          # BASELINE configs[1], the BENCH configuration
+HUMANOID_SHARD = dict(B=512, A=21, F=100, H=1024, lr=8e-5)   # configs[4]: B=4096 over 8 GPUs
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _make_agent(c, lr, params, mode, use_graph):
+    from drqv2_b200 import DrQV2Agent
+    agent = DrQV2Agent((9, 84, 84), (c["A"],), "cuda", lr, c["F"], c["H"], 0.01, 2000, 2, SCHED, 0.3, True,
+                       use_cuda_graph=use_graph, seed=5, mode=mode)
+    for net in ("encoder", "actor", "critic", "critic_target"):
+        getattr(agent, net).load_state_dict(params[net])
+    agent.refresh()
+    return agent
+
+
+def _run(agent, b, step):
+    agent.inject_draws(b["shift_obs"], b["shift_next"], b["eps_critic"], b["eps_actor"])
+    return agent.update(iter([(b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"])]), step)
+
+
+def _oracle_args(b, step):
+    return (b["obs"], b["action"], b["reward"], b["discount"], b["next_obs"], step, b["shift_obs"],
+            b["shift_next"], b["eps_critic"], b["eps_actor"])
+
+
+def _tb_features_nchw(tb, row0, n):
+    """rows [row0, row0 + n) of a TB feature matrix in the encoder-output order (c/8, yx, c%8) -> the
+    reference's flatten order c*1225 + yx (drqv2.py:66)."""
+    rows = tb.view()[row0:row0 + n, :O.REPR_DIM].float()
+    return rows.view(n, 4, 1225, 8).permute(0, 1, 3, 2).reshape(n, O.REPR_DIM)
+
+
+# bf16 mode vs the bf16-faithful oracle, stated tolerances:
+BF16_FAITHFUL_METRIC_RTOL = 2e-3      # Q values / TD target / losses (+1e-4 absolute)
+BF16_FAITHFUL_GRAD_TOL = 2e-2         # per-tensor rel-L2 of every gradient
+
+
+@pytest.mark.parametrize("case", [WALKER, HUMANOID_SHARD], ids=["walker_B256", "humanoid_B512"])
+def test_update_bf16_at_bench_config(dev, case, capsys):
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    c = case
+    B = c["B"]
+    params = O.synthetic_params(9, c["A"], c["F"], c["H"], seed=4)
+    b = O.synthetic_batch(B, c["A"], seed=10)
+    # ---- lr = 0: every stage comparable (the actor stage sees the same critic as the oracle)
+    agent = _make_agent(c, 0.0, params, "bf16", use_graph=False)
+    ob = O.OracleAgent(params, 0.0, 0.01, SCHED, 0.3, dtype=torch.float64, operands="bf16")
+    m, mo = _run(agent, b, 0), ob.update(*_oracle_args(b, 0))
+    torch.cuda.synchronize()
+    report = {k: abs(m[k] - mo[k]) / (abs(mo[k]) + 1e-12) for k in mo}
+    bw = agent.bf16_workspace(B)
+    feat = _tb_features_nchw(bw.feat, 0, B).cpu().numpy()
+    feat_next = _tb_features_nchw(bw.feat, bw.RB, B).cpu().numpy()
+    report["feat"] = rel_l2(feat, ob.stage["feat"].numpy())
+    report["feat_next"] = rel_l2(feat_next, ob.stage["feat_next"].numpy())
+    ws = agent.workspace(B)
+    report["target_q"] = rel_l2(ws.target_q.cpu().numpy(), ob.stage["target_q"].numpy().ravel())
+    for net in ("encoder", "critic", "actor"):
+        for name, p in getattr(agent, net).named_parameters():
+            report[f"{net}.{name}"] = rel_l2(p.grad.cpu().numpy(), ob.grads[net][name].numpy())
+    with capsys.disabled():
+        print(f"\nbf16 update at B={B} vs bf16-faithful oracle:", {k: float(f"{v:.2e}") for k, v in report.items()})
+    assert report["feat"] <= 1e-3 and report["feat_next"] <= 1e-3
+    assert report["target_q"] <= BF16_FAITHFUL_METRIC_RTOL
+    for k in mo:
+        assert abs(m[k] - mo[k]) <= BF16_FAITHFUL_METRIC_RTOL * abs(mo[k]) + 1e-4, (k, m[k], mo[k])
+    for net in ("encoder", "critic", "actor"):
+        for name, _ in getattr(agent, net).named_parameters():
+            assert report[f"{net}.{name}"] <= BF16_FAITHFUL_GRAD_TOL, (net, name, report[f"{net}.{name}"])
+    del agent
+    # ---- real lr, the CUDA-graph path the bench replays: eager warm-up, capture, replay
+    agent = _make_agent(c, c["lr"], params, "bf16", use_graph=True)
+    ob = O.OracleAgent(params, c["lr"], 0.01, SCHED, 0.3, dtype=torch.float64, operands="bf16")
+    steps = 3
+    for s in range(steps):
+        bs = O.synthetic_batch(B, c["A"], seed=10 + s)
+        m, mo = _run(agent, bs, 2 * s), ob.update(*_oracle_args(bs, 2 * s))
+        # Adam's first steps are sign-like: entries with |g| ~ 0 move by up to 2 lr either way, so
+        # quantities downstream of a step are compared at the parameter-noise level
+        tol = BF16_FAITHFUL_METRIC_RTOL if s == 0 else 2e-2
+        for k in ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "critic_loss"):
+            assert abs(m[k] - mo[k]) <= tol * abs(mo[k]) + 1e-3, (s, k, m[k], mo[k])
+    torch.cuda.synchronize()
+    assert any(isinstance(v, torch.cuda.CUDAGraph) for v in agent._graphs.values())
+    for net in ("encoder", "critic", "actor", "critic_target"):
+        for name, p in getattr(agent, net).named_parameters():
+            got, want = p.detach().cpu().double(), ob.p[net][name]
+            assert (got - want).abs().max().item() <= 2.5 * c["lr"] * steps, (net, name)
+
+
+def test_update_fp32_at_bench_config(dev, capsys):
+    """fp32 parity mode at the BENCH configuration: <= 1e-4 relative on the pre-optimiser quantities,
+    gradients against the fp64 oracle with the fp32 oracle's own error as the yardstick."""
+    from tests.test_gpu_parity import _check_update_against_oracle
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    c = WALKER
+    B, lr = c["B"], c["lr"]
+    params = O.synthetic_params(9, c["A"], c["F"], c["H"], seed=4)
+    agent = _make_agent(c, lr, params, "fp32", use_graph=True)
+    o32 = O.OracleAgent(params, lr, 0.01, SCHED, 0.3, dtype=torch.float32)
+    o64 = O.OracleAgent(params, lr, 0.01, SCHED, 0.3, dtype=torch.float64)
+    b = O.synthetic_batch(B, c["A"], seed=10)
+    m = _run(agent, b, 0)
+    m32, m64 = o32.update(*_oracle_args(b, 0)), o64.update(*_oracle_args(b, 0))
+    ws = agent.workspace(B)
+    assert rel_l2(ws.feat[:B].cpu().numpy(), o64.stage["feat"].numpy()) < 1e-5
+    assert rel_l2(ws.feat[B:].cpu().numpy(), o64.stage["feat_next"].numpy()) < 1e-5
+    assert rel_l2(ws.target_q.cpu().numpy(), o64.stage["target_q"].numpy().ravel()) < 1e-4
+    _check_update_against_oracle(agent, o32, o64, b, 0, lr, m, m32, m64)
+    # second and third update: the captured graph
+    for s in (1, 2):
+        bs = O.synthetic_batch(B, c["A"], seed=10 + s)
+        m, m64 = _run(agent, bs, 2 * s), o64.update(*_oracle_args(bs, 2 * s))
+        for k in ("batch_reward", "critic_target_q", "critic_q1", "critic_q2", "critic_loss"):
+            assert abs(m[k] - m64[k]) <= 2e-2 * abs(m64[k]) + 1e-3, (s, k, m[k], m64[k])
+    assert any(isinstance(v, torch.cuda.CUDAGraph) for v in agent._graphs.values())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_act_batch_1024_quadruped(dev, mode):
+    """configs[2]: the vectorised rollout, encoder + actor at batch 1024, action_dim 12 (drqv2.py:164-175)."""
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    c = dict(A=12, F=50, H=1024)
+    n = 1024
+    params = O.synthetic_params(9, c["A"], c["F"], c["H"], seed=8)
+    agent = _make_agent(c, 1e-4, params, mode, use_graph=True)
+    oracle = O.OracleAgent(params, 1e-4, 0.01, SCHED, 0.3, dtype=torch.float64,
+                           operands="bf16" if mode == "bf16" else "exact")
+    g = torch.Generator().manual_seed(3)
+    obs = torch.randint(0, 256, (n, 9, 84, 84), dtype=torch.uint8, generator=g)
+    want = oracle.act(obs, 5000, True).numpy()
+    tol = 2e-5 if mode == "fp32" else 2e-3
+    for rep in range(2):                              # first call eager + capture, second the replay
+        got = agent.act(obs.numpy(), 5000, True)
+        assert got.shape == (n, c["A"]) and got.dtype == np.float32
+        assert np.abs(got - want).max() < tol, (rep, np.abs(got - want).max())
+    # exploration samples stay in range and are centred on the mean
+    a = agent.act(obs.numpy(), 5000, False)
+    assert np.abs(a).max() <= 1.0
+    assert np.abs((a - want).mean()) < 0.05
+    # batch 1 (the latency path) agrees with row 0 of the batch
+    a1 = agent.act(obs[0].numpy(), 5000, True)
+    assert np.abs(a1 - want[0]).max() < tol
+
+
+# ----------------------------------------------------------------------------- conv kernels, 512 images
+def _pack_w(w, dev):
+    from drqv2_b200 import _lib
+    wf = torch.zeros(36 * 32 * 8, dtype=torch.bfloat16, device=dev)
+    wd = torch.zeros_like(wf)
+    _lib.call("drq_pack_conv_w_bf16", w.data_ptr(), wf.data_ptr(), wd.data_ptr(), _stream())
+    return wf, wd
+
+
+@pytest.mark.parametrize("hout", [39, 37, 35])
+def test_conv3x3_bf16_kernels_512_images(dev, hout):
+    """forward on 512 images (6656 / 6144 / 5120 tiles over 296 CTAs), data and weight gradient on 256."""
+    from drqv2_b200 import _lib
+    from drqv2_b200._bf16 import TB
+    N, NB = 512, 256
+    g = torch.Generator().manual_seed(hout)
+    hin = hout + 2
+    x = (torch.rand(N, 32, hin, hin, generator=g) - 0.3).clamp_min(0).to(dev)
+    w = ((torch.rand(32, 32, 3, 3, generator=g) * 2 - 1) * 0.1).to(dev)
+    b = ((torch.rand(32, generator=g) * 2 - 1) * 0.1).to(dev)
+    xin = wb_from_nchw(x)
+    wf, wd = _pack_w(w, dev)
+    out = torch.zeros(_lib.lib().drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
+    _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), out.data_ptr(), N, hout, 0, 0, 0, 0, _stream())
+    torch.cuda.synchronize()
+    want = torch.relu(torch.nn.functional.conv2d(_bf(x).double(), _bf(w).double(), b.double()))
+    got = nchw_from_wb(out.view(4, -1, 8), N, hout, hout).double()
+    assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6
+    if hout == 35:       # conv4's TB feature epilogue: [obs | next] halves on their own row blocks
+        half = N // 2
+        fb = TB(2 * half, hout * hout * 32, dev)
+        _lib.call("drq_conv3x3_fwd_bf16", xin.data_ptr(), wf.data_ptr(), b.data_ptr(), fb.ptr(), N, hout, 2, fb.units,
+                  half, half, _stream())
+        torch.cuda.synchronize()
+        rows = fb.view()[:, :hout * hout * 32].float()
+        got3 = rows.view(N, 4, hout * hout, 8).permute(0, 1, 3, 2).reshape(N, 32, hout, hout).double()
+        assert torch.equal(got3, got)
+    del out, got, want
+    # data gradient on the first 256 images
+    dout = ((torch.rand(NB, 32, hout, hout, generator=g) * 2 - 1) * 1e-3).to(dev)
+    d_wb = wb_from_nchw(dout)
+    din = torch.full((_lib.lib().drq_wb_elems(NB),), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.call("drq_conv3x3_dgrad_bf16", d_wb.data_ptr(), wd.data_ptr(), xin.data_ptr(), N, din.data_ptr(), NB, hout, _stream())
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv_transpose2d(_bf(dout).double(), _bf(w).double()) * (_bf(x[:NB]).double() > 0)
+    got = nchw_from_wb(din.view(4, -1, 8), NB, hin, hin).double()
+    assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-9
+    # weight / bias gradient
+    ws = torch.zeros(_lib.lib().drq_conv_wgrad_bf16_ws_floats(), device=dev)
+    dw, db = torch.zeros(32, 32, 3, 3, device=dev), torch.zeros(32, device=dev)
+    _lib.call("drq_conv3x3_wgrad_bf16", xin.data_ptr(), N, d_wb.data_ptr(), ws.data_ptr(), dw.data_ptr(),
+              db.data_ptr(), NB, hout, _stream())
+    torch.cuda.synchronize()
+    xr, dr = _bf(x[:NB]).double(), _bf(dout).double()
+    want_w = torch.nn.grad.conv2d_weight(xr, (32, 32, 3, 3), dr)
+    want_b = dr.sum(dim=(0, 2, 3))
+    assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item() + 1e-9
+    assert (db.double() - want_b).abs().max().item() <= 2e-5 * want_b.abs().max().item() + 1e-9
+
+
+def test_conv1_bf16_kernels_512_images(dev):
+    """conv1 forward (fused shift + normalise) on 512 stacks, weight gradient on 256."""
+    from drqv2_b200 import _lib
+    N, NB, cin = 512, 256, 9
+    g = torch.Generator().manual_seed(77)
+    obs = torch.randint(0, 256, (N, cin, 84, 84), dtype=torch.uint8, generator=g)
+    shift = torch.randint(0, 9, (N, 2), dtype=torch.int32, generator=g)
+    w = ((torch.rand(32, cin, 3, 3, generator=g) - 0.5) * 0.3).to(dev)
+    b = ((torch.rand(32, generator=g) - 0.5) * 0.1).to(dev)
+    wp = torch.zeros(_lib.lib().drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)
+    _lib.call("drq_pack_conv1_w_bf16", w.data_ptr(), b.data_ptr(), wp.data_ptr(), cin, _stream())
+    out = torch.zeros(_lib.lib().drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
+    obs_d, shift_d = obs.to(dev), shift.to(dev)
+    _lib.call("drq_conv1_fwd_bf16", obs_d.data_ptr(), shift_d.data_ptr(), wp.data_ptr(), out.data_ptr(), N, cin, 4, _stream())
+    torch.cuda.synchronize()
+    x = (O.random_shift_exact(obs.float(), shift).to(dev).double() / 255.0 - 0.5)
+    want = torch.relu(torch.nn.functional.conv2d(x, _bf(w).double(), b.double(), stride=2))
+    got = nchw_from_wb(out.view(4, -1, 8), N, 41, 41).double()
+    assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-6
+    d = ((torch.rand(NB, 32, 41, 41, generator=g) - 0.5) * 1e-2).to(dev)
+    d_wb = wb_from_nchw(d)
+    ws = torch.zeros(_lib.lib().drq_conv1_wgrad_bf16_ws_floats(), device=dev)
+    dw, db = torch.zeros(32, cin, 3, 3, device=dev), torch.zeros(32, device=dev)
+    _lib.call("drq_conv1_wgrad_bf16", obs_d.data_ptr(), shift_d.data_ptr(), d_wb.data_ptr(), ws.data_ptr(),
+              dw.data_ptr(), db.data_ptr(), NB, cin, 4, _stream())
+    torch.cuda.synchronize()
+    dr = _bf(d).double()
+    want_w = torch.nn.grad.conv2d_weight(x[:NB], (32, cin, 3, 3), dr, stride=2)
+    want_b = dr.sum(dim=(0, 2, 3))
+    assert (dw.double() - want_w).abs().max().item() <= 2e-5 * want_w.abs().max().item() + 1e-9
+    assert (db.double() - want_b).abs().max().item() <= 2e-5 * want_b.abs().max().item() + 1e-9
+
+
+def test_trunk_gemm_bench_shapes(dev):
+    """The merged split-K trunk forward exactly as critic_pass issues it at B=256 (batch of two halves,
+    S=70 K chunks, 128-wide tiles) and the persistent 1-D grids of the trunk data / weight gradient."""
+    from drqv2_b200 import _lib
+    from drqv2_b200._bf16 import TB, _strides, gemm, splitk_for
+    from drqv2_b200._lib import GEMM_KK, TEPI_F32
+    g = torch.Generator().manual_seed(11)
+    B, RB, FP, K = 256, 256, 64, O.REPR_DIM
+    NT = 2 * FP
+    feat = (torch.rand(2 * RB, K, generator=g) - 0.3).clamp_min(0).to(dev)
+    w = ((torch.rand(3 * FP, K, generator=g) - 0.5) * 0.01).to(dev)        # slots [target | actor | critic]
+    fb, wb = TB(2 * RB, K, dev), TB(3 * FP, K, dev, rblk=64)
+    fb.load(feat)
+    wb.load(w)
+    S = splitk_for(2 * (RB // 128) * (NT // 128))
+    part = torch.zeros(S, 2, B, NT, device=dev)
+    gemm(fb.ptr(), fb.units, wb.ptr(row=FP), wb.units, GEMM_KK, part.data_ptr(), NT, B, NT, K, TEPI_F32, batch=2,
+         batch_inner=1, splitk=S, bn=128,
+         strides=_strides(outer=(fb.off(row=RB), -wb.off(row=FP), B * NT, 0, 0), split=2 * B * NT))
+    torch.cuda.synchronize()
+    got = part.double().sum(0)
+    fr, wr = _bf(feat).double(), _bf(w).double()
+    want0 = fr[:B] @ wr[FP:3 * FP].T          # obs rows x [actor | critic]
+    want1 = fr[RB:RB + B] @ wr[0:2 * FP].T    # next rows x [target | actor]
+    assert (got[0] - want0).abs().max().item() <= 2e-5 * want0.abs().max().item()
+    assert (got[1] - want1).abs().max().item() <= 2e-5 * want1.abs().max().item()

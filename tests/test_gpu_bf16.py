@@ -441,7 +441,8 @@ def test_fused_optimiser_step_equals_adam_then_pack(dev, A, Fd, H):
     c0, cn = a.seg["critic"][0], a.seg["critic"][2]
     a.target.mul_(live[c0:c0 + cn])
     t = 7
-    agent._scal_dev[:6] = torch.tensor([0.1, 0.999, 0.001, math.sqrt(1 - 0.999 ** t), 1e-8, -1e-3 / (1 - 0.9 ** t)])
+    for o in (0, 16, 24):                       # critic_opt / encoder_opt / actor_opt scalars of one slot (drqv2.SCAL_OFF)
+        agent._scal_dev[o:o + 6] = torch.tensor([0.1, 0.999, 0.001, math.sqrt(1 - 0.999 ** t), 1e-8, -1e-3 / (1 - 0.9 ** t)])
     arenas = (a.params, a.exp_avg, a.exp_avg_sq, a.target)
     packed = [st.trunk.buf, st.q0.buf, st.q2.buf, st.p0.buf, st.p2.buf, st.p4.buf, st.conv1_w] + st.conv_wf + st.conv_wd
     snap = [x.clone() for x in arenas]

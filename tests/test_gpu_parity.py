@@ -35,7 +35,7 @@ def _stream():
 def make_agent(A, Fd, H, lr, params, use_graph=False, use_tb=True, B=None):
     from drqv2_b200 import DrQV2Agent
     agent = DrQV2Agent((9, 84, 84), (A,), "cuda", lr, Fd, H, 0.01, 2000, 2, SCHED, 0.3, use_tb,
-                       use_cuda_graph=use_graph, seed=5)
+                       use_cuda_graph=use_graph, seed=5, mode="fp32")
     agent.encoder.load_state_dict(params["encoder"])
     agent.actor.load_state_dict(params["actor"])
     agent.critic.load_state_dict(params["critic"])
@@ -573,7 +573,7 @@ def test_reference_snapshot_interop(dev):
     batch = tuple(b[k].cuda() for k in ("obs", "action", "reward", "discount", "next_obs"))
     for i in range(2):                                         # two reference updates: Adam state, step = 2
         ragent.update(iter([batch]), 2 * i)
-    mine = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False, seed=1)
+    mine = DrQV2Agent((9, 84, 84), (A,), "cuda", 1e-4, Fd, H, 0.01, 2000, 2, SCHED, 0.3, False, seed=1, mode="fp32")
     mine.load_reference_agent(ragent)
     assert mine._opt_step == 2
     for net in ("encoder", "actor", "critic", "critic_target"):
