@@ -65,7 +65,13 @@ def _tb_features_nchw(tb, row0, n):
 
 # bf16 mode vs the bf16-faithful oracle, stated tolerances:
 BF16_FAITHFUL_METRIC_RTOL = 2e-3      # Q values / TD target / losses (+1e-4 absolute)
-BF16_FAITHFUL_GRAD_TOL = 2e-2         # per-tensor rel-L2 of every gradient
+BF16_FAITHFUL_GRAD_TOL = 2e-2         # per-tensor rel-L2 of every gradient, or 1.5x the oracle's own fp32-vs-fp64 distance
+# The second term: the kernels accumulate in fp32, the oracle in fp64.  A sum that lands within ~1e-6 of a bf16
+# rounding boundary is stored one bf16 ulp apart by the two, that 3e-4 relative noise in the activations moves ~3e-4 of
+# the ReLU units across zero, and a flipped unit contributes its whole gradient as error (sqrt(3e-4) ~ 2 %), growing
+# down the backward chain to conv1.  The oracle shows the same effect against itself: its bf16-faithful variant run in
+# fp32 differs from the fp64 one by 3.2e-2 on convnet.0.weight and 0.2-2e-2 elsewhere at B=256 (measured on CPU; the
+# kernels measured 3.6e-2 and 0.2-2e-2).  The yardstick is computed in the test, not assumed.
 
 
 @pytest.mark.parametrize("case", [WALKER, HUMANOID_SHARD], ids=["walker_B256", "humanoid_B512"])
@@ -78,7 +84,9 @@ def test_update_bf16_at_bench_config(dev, case, capsys):
     # ---- lr = 0: every stage comparable (the actor stage sees the same critic as the oracle)
     agent = _make_agent(c, 0.0, params, "bf16", use_graph=False)
     ob = O.OracleAgent(params, 0.0, 0.01, SCHED, 0.3, dtype=torch.float64, operands="bf16")
+    ob32 = O.OracleAgent(params, 0.0, 0.01, SCHED, 0.3, dtype=torch.float32, operands="bf16")
     m, mo = _run(agent, b, 0), ob.update(*_oracle_args(b, 0))
+    ob32.update(*_oracle_args(b, 0))
     torch.cuda.synchronize()
     report = {k: abs(m[k] - mo[k]) / (abs(mo[k]) + 1e-12) for k in mo}
     bw = agent.bf16_workspace(B)
@@ -99,7 +107,8 @@ def test_update_bf16_at_bench_config(dev, case, capsys):
         assert abs(m[k] - mo[k]) <= BF16_FAITHFUL_METRIC_RTOL * abs(mo[k]) + 1e-4, (k, m[k], mo[k])
     for net in ("encoder", "critic", "actor"):
         for name, _ in getattr(agent, net).named_parameters():
-            assert report[f"{net}.{name}"] <= BF16_FAITHFUL_GRAD_TOL, (net, name, report[f"{net}.{name}"])
+            own = rel_l2(ob32.grads[net][name].numpy(), ob.grads[net][name].numpy())
+            assert report[f"{net}.{name}"] <= max(BF16_FAITHFUL_GRAD_TOL, 1.5 * own), (net, name, report[f"{net}.{name}"], own)
     del agent
     # ---- real lr, the CUDA-graph path the bench replays: eager warm-up, capture, replay
     agent = _make_agent(c, c["lr"], params, "bf16", use_graph=True)

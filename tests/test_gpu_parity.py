@@ -297,7 +297,11 @@ def _check_update_against_oracle(agent, oracle32, oracle64, b, step, lr, m_gpu, 
             got, want = p.detach().cpu().double(), oracle64.p[net][name]
             assert (got - want).abs().max().item() <= 2.5 * lr * (step // 2 + 1), (net, name)
             if got.numel() > 64 and want.norm() > 0:
-                assert rel_l2(got.numpy(), want.numpy()) < 2e-4, (net, name)
+                # the sign-like first Adam steps move entries with |g| ~ 0 by up to 2 lr either way: on
+                # tensors of small entries (the 39200-wide trunk rows at lr / |w| ~ 2 %) the fp32 oracle's own distance
+                # to fp64 is the yardstick
+                own = rel_l2(oracle32.p[net][name].numpy(), want.numpy())
+                assert rel_l2(got.numpy(), want.numpy()) < max(2e-4, 3 * own), (net, name, own)
 
 
 @pytest.mark.parametrize("case", [dict(B=16, A=6, F=50, H=256, lr=1e-4), dict(B=5, A=21, F=100, H=128, lr=8e-5)])
