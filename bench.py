@@ -221,6 +221,10 @@ def profile_update_launches(agent, it, B, reps=5):
             return "conv", f"conv1_fwd(N={a[4]})", 2 * CONV1_MACS_PER_CIN * a[5] * a[4], 0
         if name == "drq_conv1_wgrad_bf16":
             return "conv", f"conv1_wgrad(N={a[6]})", 2 * CONV1_MACS_PER_CIN * a[7] * a[6], 0
+        if name == "drq_conv1_fwd_bf16_ring":        # 9 stacked channels (3 frames x RGB), rows straight from the ring
+            return "conv", f"conv1_fwd(N={a[5]},from ring)", 2 * CONV1_MACS_PER_CIN * 9 * a[5], 0
+        if name == "drq_conv1_wgrad_bf16_ring":
+            return "conv", f"conv1_wgrad(N={a[7]},from ring)", 2 * CONV1_MACS_PER_CIN * 9 * a[7], 0
         if name == "drq_conv3x3_fwd_bf16":
             return "conv", f"conv3x3_fwd(hout={a[5]},N={a[4]}{',TB' if a[6] == 2 else ''})", 2 * CONV_MACS[a[5]] * a[4], 0
         if name == "drq_conv3x3_dgrad_bf16":
@@ -561,7 +565,8 @@ def run_ours(args, rank, world):
     def counting_call(name, *a):
         # drq_ln_tanh_bwd launches its parameter-gradient kernel only when dgamma (argument 8) is given
         # the bf16 wgrad entry points skip their reduce kernel when dw (argument 4) is NULL (reduced by one launch later)
-        two = (name in two_kernel_calls and (not name.endswith("_bf16") or a[4])) or (name == "drq_ln_tanh_bwd" and a[8])
+        two = ((name in two_kernel_calls and (not name.endswith("_bf16") or a[4])) or (name == "drq_ln_tanh_bwd" and a[8])
+               or (name == "drq_conv1_wgrad_bf16_ring" and a[5]))
         n_calls[0] += 2 if two else 1
         return orig_call(name, *a)
 

@@ -365,8 +365,13 @@ def encode(agent, ws, bw):
     st, B, s = agent._bf16, ws.B, _stream()
     be = lambda i: agent._p("encoder", f"convnet.{i}.bias")
     acts = [a.data_ptr() for a in bw.acts]
-    call("drq_conv1_fwd_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), st.conv1_w.data_ptr(), acts[0],
-         2 * B, agent.obs_shape[0], agent.aug.pad, s)
+    src = getattr(ws, "ring_src", None)
+    if src is not None:          # frame stacks by index, straight from the replay ring
+        call("drq_conv1_fwd_bf16_ring", C.byref(src), B, ws.shift.data_ptr(), st.conv1_w.data_ptr(), acts[0], 2 * B,
+             agent.aug.pad, s)
+    else:
+        call("drq_conv1_fwd_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), st.conv1_w.data_ptr(), acts[0],
+             2 * B, agent.obs_shape[0], agent.aug.pad, s)
     call("drq_conv3x3_fwd_bf16", acts[0], st.conv_wf[0].data_ptr(), be(2), acts[1], 2 * B, 39, 0, 0, 0, 0, s)
     call("drq_conv3x3_fwd_bf16", acts[1], st.conv_wf[1].data_ptr(), be(4), acts[2], 2 * B, 37, 0, 0, 0, 0, s)
     call("drq_conv3x3_fwd_bf16", acts[2], st.conv_wf[2].data_ptr(), be(6), bw.feat.ptr(), 2 * B, 35, 2, bw.feat.units,
@@ -546,8 +551,13 @@ def critic_pass(agent, ws, bw, encoder_grad=True):
             jobs.append(WgReduceJob(bw.wg_ws[layer].data_ptr(), ge(f"convnet.{k}.weight"), ge(f"convnet.{k}.bias"), B, hout, 0, 0))
             call("drq_conv3x3_dgrad_bf16", d[layer], st.conv_wd[layer - 1].data_ptr(), acts[layer - 1], 2 * B,
                  d[layer - 1], B, hout, s2)
-        call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
-             B, agent.obs_shape[0], agent.aug.pad, s2)
+        src = getattr(ws, "ring_src", None)
+        if src is not None:
+            call("drq_conv1_wgrad_bf16_ring", C.byref(src), B, ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+                 B, agent.aug.pad, s2)
+        else:
+            call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+                 B, agent.obs_shape[0], agent.aug.pad, s2)
         jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], 0))
         arr = (WgReduceJob * len(jobs))(*jobs)
         call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s2)   # all four layers' partials -> dW, db in one launch

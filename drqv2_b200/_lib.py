@@ -26,6 +26,9 @@ SIGNATURES = {
     "drq_rng_update_draws": [U, P, I, P, P, P, P, I, I, P],
     "drq_ring_sample_step": [P, P, I, U, P, P, P, I, P],
     "drq_update_prologue": [P, I, P, P, U, P, I, P, P, P, P, I, I, P],
+    "drq_update_prologue_ring": [P, I, P, P, U, P, I, P, P, P, P, I, I, P, P, P, P, P],
+    "drq_conv1_fwd_bf16_ring": [P, I, P, P, P, I, I, P],
+    "drq_conv1_wgrad_bf16_ring": [P, I, P, P, P, P, P, I, I, P],
     "drq_rng_normal_f32": [U, P, P, I, P],
     "drq_counter_advance": [P, P],
     "drq_scalars_fetch": [P, I, P, P, P],
@@ -45,6 +48,7 @@ SIGNATURES = {
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
     "drq_set_pdl": [I],
     "drq_debug_gemm_stamps": [P],
+    "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],
     "drq_debug_conv1_stamps": [P],
     "drq_pack_multi": [P, I, P],
@@ -117,6 +121,8 @@ def lib():
             raise ImportError("libdrqv2_b200.so ABI version mismatch")
         # programmatic dependent launch between the library's kernels (opt-in with DRQV2_B200_PDL=1: measured neutral without early trigger, -25 % with it)
         h.drq_set_pdl(0 if os.environ.get("DRQV2_B200_PDL", "0") == "0" else 1)
+        if os.environ.get("DRQV2_B200_OPT_MINB"):       # tuning: register target of the fused optimiser kernel
+            h.drq_debug_opt_min_blocks(int(os.environ["DRQV2_B200_OPT_MINB"]))
         _lib = h
     return _lib
 

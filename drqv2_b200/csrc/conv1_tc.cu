@@ -52,7 +52,24 @@ struct Conv1TcArgs {
     float* partial;                                // wgrad: [grid][32][96]
     int n_images;
     long long* stamps;                             // debug: builder cycle totals of block 0 (or null)
+    // rows straight from the replay ring (ring_frames != null; obs unused): see drq_conv1_fwd_bf16_ring
+    const uint8_t* ring_frames; const int* ring_ep_start; const int* ring_idx;
+    long long ring_capacity; int ring_B, ring_nstep, ring_stack, ring_frame_c;
 };
+
+// first byte of channel `c` of image `n`: the gathered stack, or the ring frame the stack is made of
+// (replay_buffer.py:151,153 rows idx-1 / idx+nstep-1; dmc.py:98-109 stack of the last frames, reset frame repeated)
+__device__ __forceinline__ const uint8_t* channel_plane(const Conv1TcArgs& a, int n, int c) {
+    if (!a.ring_frames) return a.obs + ((long long)n * a.cin + c) * (kImg * kImg);
+    const int j = c / a.ring_frame_c, cc = c - j * a.ring_frame_c;
+    const bool is_next = n >= a.ring_B;
+    const int b = is_next ? n - a.ring_B : n;
+    const int t = is_next ? a.ring_idx[b] + a.ring_nstep - 1 : a.ring_idx[b] - 1;
+    int r = t - (a.ring_stack - 1 - j);
+    r = r < 0 ? 0 : r;
+    const long long slot = ((long long)a.ring_ep_start[b] + r) % a.ring_capacity;
+    return a.ring_frames + (slot * a.ring_frame_c + cc) * (long long)(kImg * kImg);
+}
 
 static long long* g_c1_stamps = nullptr;
 #ifdef DRQ_STAMPS
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
             int rs = 0; uint32_t rphase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileGeom g = tile_geom(t, a.shift, a.pad);
-                const uint8_t* src = a.obs + ((long long)g.n * a.cin + lane) * (kImg * kImg) + g.rlo * kImg;
+                const uint8_t* src = channel_plane(a, g.n, lane) + g.rlo * kImg;
                 const int off0 = (g.rlo * kImg) & 15;            // every channel plane starts 16-byte aligned
                 const uint32_t nbytes = (uint32_t)((off0 + g.nrows * kImg + 15) & ~15);
                 mbar_wait(rempty + rs, rphase ^ 1);
@@ -437,14 +454,54 @@ int drq_pack_conv1_w_bf16(const float* w, const float* bias, uint16_t* out, int 
     return check_launch("pack_conv1_w_kernel");
 }
 
+// the ring view of a batch as kernel arguments
+static int ring_args(Conv1TcArgs& a, const drq_ring_src* src, int B, int N) {
+    DRQ_REQUIRE(src && src->frames && src->ep_start && src->idx, "conv1_*_ring: incomplete ring source");
+    DRQ_REQUIRE(src->capacity > 0 && src->frame_c > 0 && src->stack > 0 && src->nstep > 0, "conv1_*_ring: bad ring dims");
+    DRQ_REQUIRE(B > 0 && N > 0 && N <= 2 * B, "conv1_*_ring: N images must be B (obs) or 2B (obs | next_obs)");
+    DRQ_REQUIRE(((uintptr_t)src->frames % 16) == 0, "conv1_*_ring: ring frames must be 16-byte aligned");
+    a.ring_frames = src->frames; a.ring_ep_start = src->ep_start; a.ring_idx = src->idx;
+    a.ring_capacity = src->capacity; a.ring_B = B; a.ring_nstep = src->nstep; a.ring_stack = src->stack;
+    a.ring_frame_c = src->frame_c;
+    a.cin = src->frame_c * src->stack;
+    return DRQ_OK;
+}
+
+static int conv1_fwd_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t* w_packed, uint16_t* out, int N, int pad,
+                            cudaStream_t stream);
+static int conv1_wgrad_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t* dpre, float* partial, float* dw, float* db,
+                              int N, int pad, cudaStream_t stream);
+
+int drq_conv1_fwd_bf16_ring(const drq_ring_src* src, int B, const int32_t* shift, const uint16_t* w_packed,
+                            uint16_t* out, int N, int pad, void* stream) {
+    Conv1TcArgs a{};
+    if (int rc = ring_args(a, src, B, N)) return rc;
+    return conv1_fwd_launch(a, shift, w_packed, out, N, pad, as_stream(stream));
+}
+
+int drq_conv1_wgrad_bf16_ring(const drq_ring_src* src, int B, const int32_t* shift, const uint16_t* dpre,
+                              float* partial, float* dw, float* db, int N, int pad, void* stream) {
+    Conv1TcArgs a{};
+    if (int rc = ring_args(a, src, B, N)) return rc;
+    return conv1_wgrad_launch(a, shift, dpre, partial, dw, db, N, pad, as_stream(stream));
+}
+
 int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* w_packed, uint16_t* out, int N,
                        int cin, int pad, void* stream) {
-    DRQ_REQUIRE(obs && w_packed && out, "conv1_fwd_bf16: null pointer");
+    DRQ_REQUIRE(obs, "conv1_fwd_bf16: null pointer");
+    Conv1TcArgs a{};
+    a.obs = obs; a.cin = cin;
+    return conv1_fwd_launch(a, shift, w_packed, out, N, pad, as_stream(stream));
+}
+
+static int conv1_fwd_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t* w_packed, uint16_t* out, int N, int pad,
+                            cudaStream_t stream) {
+    const int cin = a.cin;
+    DRQ_REQUIRE(w_packed && out, "conv1_fwd_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0 && pad <= 4, "conv1_fwd_bf16: bad dims (cin <= 10, pad <= 4)");
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<false, 9>, kConv1FwdSmem, "conv1_fwd_bf16")) return rc;
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<false, 0>, kConv1FwdSmem, "conv1_fwd_bf16")) return rc;
-    Conv1TcArgs a{};
-    a.obs = obs; a.shift = shift; a.cin = cin; a.pad = pad;
+    a.shift = shift; a.pad = pad;
     a.w = reinterpret_cast<const __nv_bfloat16*>(w_packed);
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
     a.cs_out = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
@@ -452,8 +509,8 @@ int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t*
     a.stamps = g_c1_stamps;
     const int tiles = N * 14;
     const int G = tiles < 148 ? tiles : 148;
-    if (cin == 9) launch_k(conv1_tc_kernel<false, 9>, G, kC1Threads, kConv1FwdSmem, as_stream(stream), a);
-    else launch_k(conv1_tc_kernel<false, 0>, G, kC1Threads, kConv1FwdSmem, as_stream(stream), a);
+    if (cin == 9) launch_k(conv1_tc_kernel<false, 9>, G, kC1Threads, kConv1FwdSmem, stream, a);
+    else launch_k(conv1_tc_kernel<false, 0>, G, kC1Threads, kConv1FwdSmem, stream, a);
     return check_launch("conv1_tc_kernel<fwd>");
 }
 
@@ -461,22 +518,30 @@ int64_t drq_conv1_wgrad_bf16_ws_floats(void) { return 148ll * 32 * kC1K; }
 
 int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
                          float* dw, float* db, int N, int cin, int pad, void* stream) {
-    DRQ_REQUIRE(obs && dpre && partial && (dw != nullptr) == (db != nullptr), "conv1_wgrad_bf16: null pointer");
+    DRQ_REQUIRE(obs, "conv1_wgrad_bf16: null pointer");
+    Conv1TcArgs a{};
+    a.obs = obs; a.cin = cin;
+    return conv1_wgrad_launch(a, shift, dpre, partial, dw, db, N, pad, as_stream(stream));
+}
+
+static int conv1_wgrad_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t* dpre, float* partial, float* dw, float* db,
+                              int N, int pad, cudaStream_t stream) {
+    const int cin = a.cin;
+    DRQ_REQUIRE(dpre && partial && (dw != nullptr) == (db != nullptr), "conv1_wgrad_bf16: null pointer");
     DRQ_REQUIRE(N > 0 && cin > 0 && cin * 9 + 1 <= kC1K && pad >= 0 && pad <= 4, "conv1_wgrad_bf16: bad dims (cin <= 10, pad <= 4)");
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 9>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
     if (int rc = ensure_smem((const void*)conv1_tc_kernel<true, 0>, kConv1WgSmem, "conv1_wgrad_bf16")) return rc;
-    Conv1TcArgs a{};
-    a.obs = obs; a.shift = shift; a.cin = cin; a.pad = pad;
+    a.shift = shift; a.pad = pad;
     a.d = reinterpret_cast<const __nv_bfloat16*>(dpre);
     a.cs_d = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
     a.partial = partial;
     a.n_images = N;
     const int G = conv1_wgrad_ctas(N);
-    if (cin == 9) launch_k(conv1_tc_kernel<true, 9>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
-    else launch_k(conv1_tc_kernel<true, 0>, G, kC1Threads, kConv1WgSmem, as_stream(stream), a);
+    if (cin == 9) launch_k(conv1_tc_kernel<true, 9>, G, kC1Threads, kConv1WgSmem, stream, a);
+    else launch_k(conv1_tc_kernel<true, 0>, G, kC1Threads, kConv1WgSmem, stream, a);
     if (int rc = check_launch("conv1_tc_kernel<wgrad>")) return rc;
     if (!dw) return DRQ_OK;                                   // partials only: reduced later by drq_conv_wgrad_reduce_multi
-    launch_k(conv1_wgrad_reduce_kernel, kC1ReduceBlocks, 256, 0, as_stream(stream), partial, G, cin, dw, db);
+    launch_k(conv1_wgrad_reduce_kernel, kC1ReduceBlocks, 256, 0, stream, partial, G, cin, dw, db);
     return check_launch("conv1_wgrad_reduce_kernel");
 }
 

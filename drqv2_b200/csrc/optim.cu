@@ -195,7 +195,11 @@ __device__ __forceinline__ void upd_scalar(const Upd& u, const int (&o)[K], cons
     }
 }
 
-__global__ void __launch_bounds__(256, OPT_MIN_BLOCKS) adam_pack_kernel(const OptArgs a) {
+// MINB = resident blocks per SM the register allocation aims for (3: 80 registers; 4: 64 registers, a few spilled
+// words on the generic LINEAR / CONV1 paths): more loads in flight per SM against fewer registers per thread
+static int g_opt_min_blocks = OPT_MIN_BLOCKS;
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) adam_pack_kernel(const OptArgs a) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) unsigned char smraw[kOptShBytes];
@@ -435,9 +439,12 @@ int drq_adam_pack_step(float* p, const float* g, float* m, float* v, const float
     }
     DRQ_REQUIRE(blocks < (1ll << 31), "adam_pack: too many blocks");
     a.first_block[nsegs] = (int)blocks;
-    launch_k(adam_pack_kernel, (unsigned)blocks, 256, 0, as_stream(stream), a);
+    if (g_opt_min_blocks >= 4) launch_k(adam_pack_kernel<4>, (unsigned)blocks, 256, 0, as_stream(stream), a);
+    else launch_k(adam_pack_kernel<3>, (unsigned)blocks, 256, 0, as_stream(stream), a);
     return check_launch("adam_pack_kernel");
 }
+
+int drq_debug_opt_min_blocks(int min_blocks) { g_opt_min_blocks = min_blocks; return DRQ_OK; }
 
 int drq_set_l2_persist(const void* base, int64_t bytes) {
     if (!base || bytes <= 0) { g_persist_base = nullptr; g_persist_bytes = 0; return DRQ_OK; }

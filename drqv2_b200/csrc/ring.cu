@@ -198,6 +198,56 @@ __global__ void __launch_bounds__(1024) update_prologue_kernel(const float* scal
     }
 }
 
+// The head of a ring-fed update in one block: update_prologue_kernel, then ring_sample_step_kernel, then the scalar
+// part of ring_gather_kernel (action copy + un-fused fp32 n-step chain) on the indices just drawn.  The frame stacks
+// stay in the ring (conv1_tc_kernel's row producer reads them through ep_start / idx).
+__global__ void __launch_bounds__(1024) update_prologue_ring_kernel(const float* scal_ring, int slots, unsigned long long* cursor,
+                                                                    float* scal_out, unsigned long long seed, unsigned long long* counter,
+                                                                    int pad, int* __restrict__ shift_obs, int* __restrict__ shift_next,
+                                                                    float* __restrict__ eps_c, float* __restrict__ eps_a, int B, int A,
+                                                                    const drq_ring_src src, float* __restrict__ action_out,
+                                                                    float* __restrict__ reward_out, float* __restrict__ discount_out) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x < DRQ_SCAL_SLOT) {
+        const unsigned long long cur = *cursor;
+        scal_out[threadIdx.x] = *reinterpret_cast<const volatile float*>(scal_ring + (cur % (unsigned long long)slots) * DRQ_SCAL_SLOT + threadIdx.x);
+        __syncwarp();
+        if (threadIdx.x == 0) *cursor = cur + 1ull;
+    }
+    unsigned long long c = 0;
+    if (shift_obs) {
+        c = *counter;
+        const int n = B * A > B ? B * A : B;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) update_draws_elem(seed, c, pad, shift_obs, shift_next, eps_c, eps_a, B, A, i);
+    }
+    const unsigned long long cs = *src.counter;
+    const int E = *src.n_episodes;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) ring_sample_elem(src.ep_table, E, src.nstep, src.seed, cs, src.ep_start, src.idx, b);
+    __syncthreads();                                  // indices visible to the block; every counter read is done
+    if (threadIdx.x == 0) {
+        if (shift_obs) *counter = c + 1ull;
+        *src.counter = cs + 1ull;
+    }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const long long start = src.ep_start[b];
+        const int row = src.idx[b];
+        float rew = 0.f, disc = 1.f;                  // replay_buffer.py:154-159
+        for (int i = 0; i < src.nstep; ++i) {
+            const long long sl = (start + row + i) % src.capacity;
+            rew = __fadd_rn(rew, __fmul_rn(disc, src.reward[sl]));
+            disc = __fmul_rn(disc, __fmul_rn(src.discount[sl], src.gamma));
+        }
+        reward_out[b] = rew;
+        discount_out[b] = disc;
+    }
+    for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+        const int b = i / A, a = i - b * A;
+        const long long s0 = ((long long)src.ep_start[b] + src.idx[b]) % src.capacity;
+        action_out[i] = src.action[s0 * A + a];       // replay_buffer.py:152
+    }
+}
+
 // out[i] ~ N(0,1): stream 5, Box-Muller on pair (i >> 1)
 __global__ void rng_normal_kernel(unsigned long long seed, const unsigned long long* counter,
                                   float* __restrict__ out, int n) {
@@ -363,6 +413,22 @@ int drq_update_prologue(const float* scal_ring, int slots, uint64_t* cursor, flo
     launch_k(update_prologue_kernel, 1, 1024, 0, as_stream(stream), scal_ring, slots, (unsigned long long*)cursor, scal_out,
              (unsigned long long)seed, (unsigned long long*)counter, pad, shift_obs, shift_next, eps_critic, eps_actor, B, A);
     return check_launch("update_prologue_kernel");
+}
+
+int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
+                             uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
+                             float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
+                             float* reward_out, float* discount_out, void* stream) {
+    DRQ_REQUIRE(scal_ring && cursor && scal_out && slots > 0, "update_prologue_ring: bad scalar ring");
+    DRQ_REQUIRE(!shift_obs || (counter && shift_next && eps_critic && eps_actor && pad >= 0), "update_prologue_ring: bad draw arguments");
+    DRQ_REQUIRE(src && src->action && src->reward && src->discount && src->ep_table && src->n_episodes && src->counter &&
+                    src->ep_start && src->idx, "update_prologue_ring: incomplete ring source");
+    DRQ_REQUIRE(B > 0 && A > 0 && A == src->A && src->capacity > 0 && src->nstep > 0, "update_prologue_ring: bad dims");
+    DRQ_REQUIRE(action_out && reward_out && discount_out, "update_prologue_ring: null output");
+    launch_k(update_prologue_ring_kernel, 1, 1024, 0, as_stream(stream), scal_ring, slots, (unsigned long long*)cursor, scal_out,
+             (unsigned long long)seed, (unsigned long long*)counter, pad, shift_obs, shift_next, eps_critic, eps_actor, B, A,
+             *src, action_out, reward_out, discount_out);
+    return check_launch("update_prologue_ring_kernel");
 }
 
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream) {

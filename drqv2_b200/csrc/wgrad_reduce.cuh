@@ -9,7 +9,7 @@ constexpr int kWgPartialFloats = 10 * 32 * 32;     // conv3x3: [9 taps + bias][c
 constexpr int kC1PartialFloats = 32 * 96;          // conv1: [co][96 K entries] per CTA
 
 inline int conv_wgrad_ctas(int n_images, int hout) {             // tile walkers of conv3x3_wgrad_tc_kernel
-    const int tiles = n_images * ((hout * DRQ_PW + 127) / 128);
+    const int tiles = n_images * ((hout * DRQ_PW + 255) / 256);   // 256-position tiles
     return tiles < 148 ? tiles : 148;
 }
 inline int conv1_wgrad_ctas(int n_images) {

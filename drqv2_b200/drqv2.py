@@ -11,6 +11,7 @@ built extension or without a CUDA device these classes raise.
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import functools
 import gc
 import math
@@ -436,6 +437,9 @@ class DrQV2Agent:
         self.prefetch = bool(prefetch)
         # bf16 mode: encoder backward + encoder_opt.step() on a second stream beside the actor pass (DRQV2_B200_OVERLAP=0: in line)
         self.overlap_encoder_backward = os.environ.get("DRQV2_B200_OVERLAP", "1") != "0"
+        # bf16 mode fed from the HBM ring: conv1 reads the frame stacks from the ring by index (DRQV2_B200_RING_DIRECT=0:
+        # gather them into a batch buffer first)
+        self.ring_direct = os.environ.get("DRQV2_B200_RING_DIRECT", "1") != "0"
         self._side_stream = None
         self._side_stream2 = None
         self.mode = mode or os.environ.get("DRQV2_B200_MODE", "bf16")
@@ -741,11 +745,15 @@ class DrQV2Agent:
         several agents can be driven from one thread (ensemble.AgentEnsemble)."""
         if step % self.update_every_steps != 0:
             return None
+        ring = None
         if hasattr(replay_iter, "next_into"):
-            # GPU-resident ring: sample + n-step gather straight into the static buffers
+            # GPU-resident ring: sample + n-step gather straight into the static buffers - or, in the tensor-core mode,
+            # no gather of the frame stacks at all: conv1's loader reads them from the ring by index
             B = replay_iter.batch_size
             ws = self.workspace(B)
             fetch = lambda: replay_iter.next_into(ws.obs[:B], ws.action, ws.reward, ws.discount, ws.obs[B:])
+            if self.mode == "bf16" and self.ring_direct and hasattr(replay_iter, "ring_source"):
+                ring = replay_iter
         else:
             fetch = None
             pf, self._prefetch = self._prefetch, None
@@ -779,24 +787,24 @@ class DrQV2Agent:
         src = getattr(replay_iter, "graph_key", None) if fetch is not None else None
         if fetch is not None and src is None:
             src = id(replay_iter)
-        key = (B, src, inj is None)
+        key = (B, src, inj is None, ring is not None)
         if fetch is not None and hasattr(replay_iter, "check_ready"):
             replay_iter.check_ready()              # a replayed graph cannot raise: an empty ring is refused here
         state = self._graphs.get(key) if self.use_cuda_graph else None
         try:
             if not self.use_cuda_graph:
-                self._update_body(ws, fetch, draw=inj is None)
+                self._update_body(ws, fetch, draw=inj is None, ring=ring)
             elif state is None:
                 # first call at this shape runs eagerly: it is the warm-up (lazy module loading,
                 # shared-memory opt-in) that must not happen inside a capture
-                self._update_body(ws, fetch, draw=inj is None)
+                self._update_body(ws, fetch, draw=inj is None, ring=ring)
                 self._graphs[key] = "warm"
             else:
                 if state == "warm":
                     torch.cuda.synchronize()
                     state = torch.cuda.CUDAGraph()
                     with _capture(state):
-                        self._update_body(ws, fetch, draw=inj is None)
+                        self._update_body(ws, fetch, draw=inj is None, ring=ring)
                     self._graphs[key] = state
                 state.replay()
         except BaseException:
@@ -919,18 +927,27 @@ class DrQV2Agent:
             self._side_stream2 = torch.cuda.Stream(device=self._dev)
         return self._side_stream2
 
-    def _update_body(self, ws, fetch=None, draw=True):
+    def _update_body(self, ws, fetch=None, draw=True, ring=None):
         """Everything of one update that runs on the device, in stream order; no host sync."""
         B = ws.B
         s = _stream()
         # one launch: this update's host scalars (Adam bias corrections, stddev) out of the pinned ring and - unless
         # the draws were injected - the four random draws of drqv2.py:34 (x2) and utils.py:119 (x2), counter += 1
-        call("drq_update_prologue", self._scal_ring.data_ptr(), self._SCAL_SLOTS, self._scal_cursor.data_ptr(),
-             self._scal_dev.data_ptr(), self._seed, self._counter.data_ptr(), self.aug.pad,
-             ws.shift[:B].data_ptr() if draw else None, ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
-             B, self.action_dim, s)
-        if fetch is not None:
-            fetch()
+        head = (self._scal_ring.data_ptr(), self._SCAL_SLOTS, self._scal_cursor.data_ptr(),
+                self._scal_dev.data_ptr(), self._seed, self._counter.data_ptr(), self.aug.pad,
+                ws.shift[:B].data_ptr() if draw else None, ws.shift[B:].data_ptr(), ws.eps_c.data_ptr(), ws.eps_a.data_ptr(),
+                B, self.action_dim)
+        ws.ring_src = None
+        if ring is not None:
+            # ... and in the same launch the replay sample (replay_buffer.py:142-160): indices, action, n-step reward and
+            # discount.  The frame stacks stay in the ring; conv1 reads them through (ep_start, idx).
+            ws.ring_src = ring.ring_source()
+            call("drq_update_prologue_ring", *head, ctypes.byref(ws.ring_src), ws.action.data_ptr(), ws.reward.data_ptr(),
+                 ws.discount.data_ptr(), s)
+        else:
+            call("drq_update_prologue", *head, s)
+            if fetch is not None:
+                fetch()
         if self.mode == "bf16":
             bw = self.bf16_workspace(B)
             _bf16.encode(self, ws, bw)

@@ -23,6 +23,8 @@ import io
 import pathlib
 from collections import defaultdict
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -253,6 +255,15 @@ class ReplayBufferStorage:
             save_episode(episode, self._replay_dir / f"{ts}_{eps_idx}_{eps_len}.npz")
 
 
+class RingSrc(C.Structure):
+    """drq_ring_src (include/drqv2_b200.h): a sampled batch as a view of the ring"""
+    _fields_ = [("frames", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p), ("discount", C.c_void_p),
+                ("capacity", C.c_int64), ("frame_c", C.c_int32), ("stack", C.c_int32), ("A", C.c_int32),
+                ("nstep", C.c_int32), ("gamma", C.c_float), ("reserved", C.c_int32),
+                ("ep_table", C.c_void_p), ("n_episodes", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_void_p),
+                ("ep_start", C.c_void_p), ("idx", C.c_void_p)]
+
+
 class RingIterator:
     """Endless iterator of (obs, action, reward, discount, next_obs) device tensors."""
 
@@ -267,6 +278,16 @@ class RingIterator:
         l = self._l
         ring = l.ring()
         return (ring.frames.data_ptr(), ring.ep_table.data_ptr(), l._counter.data_ptr(), l.nstep, l.discount, l.seed)
+
+    def ring_source(self):
+        """The drq_ring_src of this loader over its ring: lets an update read the sampled frame stacks straight from
+        the ring (drq_update_prologue_ring + drq_conv1_*_bf16_ring) instead of gathering them first."""
+        l = self._l
+        ring = l.ring()
+        return RingSrc(ring.frames.data_ptr(), ring.action.data_ptr(), ring.reward.data_ptr(), ring.discount.data_ptr(),
+                       ring.capacity, ring.frame_c, ring.stack, ring.A, l.nstep, float(l.discount), 0,
+                       ring.ep_table.data_ptr(), ring.n_episodes.data_ptr(), l.seed, l._counter.data_ptr(),
+                       l._ep_start.data_ptr(), l._idx.data_ptr())
 
     def check_ready(self):
         if getattr(self._l.ring(), "_n_eligible", 0) == 0:

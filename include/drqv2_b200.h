@@ -129,6 +129,29 @@ int drq_counter_advance(uint64_t* counter, void* stream);
  * a host that enqueues updates faster than the device runs them.  `cursor` is a device counter. */
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream);
 
+/* A sampled batch as a view of the replay ring: everything the sampler and the consumers of one batch need, so that
+ * the frame stacks never have to be materialised (north_star (1)/(2): "builds the frame stack by index", "augmented
+ * frames are never materialised").  Filled by the host once per (ring, loader); all pointers are device pointers.
+ * Reference: ReplayBuffer._sample replay_buffer.py:142-160 and the stack layout of dmc.py:86-109. */
+typedef struct {
+    const uint8_t* frames; const float* action; const float* reward; const float* discount;   /* ring arrays */
+    int64_t capacity;                     /* ring slots */
+    int32_t frame_c, stack, A, nstep;     /* channels per frame, frames per stack, action dim, n-step */
+    float gamma; int32_t reserved;
+    const int32_t* ep_table; const int32_t* n_episodes;   /* sampler input: (start slot, rows) per eligible episode */
+    uint64_t seed; uint64_t* counter;                     /* sampler key and draw counter (device) */
+    int32_t* ep_start; int32_t* idx;                      /* [B] sampled (episode start slot, idx) - written by the
+                                                             prologue, read by the conv1 loaders */
+} drq_ring_src;
+
+/* drq_update_prologue + drq_ring_sample_step + the action / n-step reward / discount part of drq_ring_gather_nstep in
+ * ONE one-block launch: the head of a ring-fed update.  The frame stacks are not gathered: drq_conv1_*_bf16_ring read
+ * them from the ring through (ep_start, idx).  Results are bit-identical to the three separate calls. */
+int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
+                             uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
+                             float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
+                             float* reward_out, float* discount_out, void* stream);
+
 /* drq_ring_sample followed by *counter += 1 in one launch (one block). */
 int drq_ring_sample_step(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed, uint64_t* counter,
                          int32_t* ep_start_out, int32_t* idx_out, int B, void* stream);
@@ -229,6 +252,16 @@ int drq_conv1_fwd_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t*
 /* conv1 weight + bias gradient (fp32, reference layout) from dpre (WB bf16 of N images). */
 int drq_conv1_wgrad_bf16(const uint8_t* obs, const int32_t* shift, const uint16_t* dpre, float* partial,
                          float* dw, float* db, int N, int cin, int pad, void* stream);
+/* The same two kernels with the row producer addressing the replay ring directly: image n < B is the stack of
+ * sample n at rows idx-1 (obs), image n >= B the stack of sample n-B at rows idx+nstep-1 (next_obs), channel
+ * c = frame (c / frame_c) of the stack = ring frame max(t - (stack-1-j), 0) of the episode (dmc.py:98-109,
+ * replay_buffer.py:151,153).  cin = frame_c * stack.  Bit-identical to drq_ring_gather_nstep followed by the
+ * plain kernels (tests/test_gpu_ring_direct.py). */
+int drq_conv1_fwd_bf16_ring(const drq_ring_src* src, int B, const int32_t* shift, const uint16_t* w_packed,
+                            uint16_t* out, int N, int pad, void* stream);
+int drq_conv1_wgrad_bf16_ring(const drq_ring_src* src, int B, const int32_t* shift, const uint16_t* dpre,
+                              float* partial, float* dw, float* db, int N, int pad, void* stream);
+
 int64_t drq_conv1_wgrad_bf16_ws_floats(void);
 
 /* ------------------------------------------------------------------ dense, bf16 tensor cores */
@@ -425,6 +458,9 @@ int drq_q_head_bwd_loss_bf16(int loss, const float* q, const float* tq, const fl
  * float64 exactly as torch/optim/adam.py:531-547 and cast to fp32.
  * One launch updates the contiguous range p[0..n): torch.optim.Adam x3 of
  * drqv2.py:148-150,201-202,221 over the flat parameter arena. */
+/* tuning switch: register allocation target of the fused optimiser kernel (3 or 4 resident blocks per SM) */
+int drq_debug_opt_min_blocks(int min_blocks);
+
 /* Optional: keep [base, base+bytes) (the Adam moment arenas) in the persisting L2 set-aside - the optimiser
  * kernels are then launched with a persisting access-policy window over it (clamped to the device limits).
  * base == NULL switches it off. */
