@@ -301,7 +301,11 @@ def _check_update_against_oracle(agent, oracle32, oracle64, b, step, lr, m_gpu, 
                 # tensors of small entries (the 39200-wide trunk rows at lr / |w| ~ 2 %) the fp32 oracle's own distance
                 # to fp64 is the yardstick
                 own = rel_l2(oracle32.p[net][name].numpy(), want.numpy())
-                assert rel_l2(got.numpy(), want.numpy()) < max(2e-4, 3 * own), (net, name, own)
+                # ... or, where the oracle's two precisions happen to agree, an rms parameter error of 5 % of lr
+                # (0.06 % of the entries on the other side of a sign-like step): measured 2.4 % of lr on the
+                # actor's 39200-wide trunk rows at B=256, whose gradients pass through the stepped critic
+                floor = 0.05 * lr * (got.numel() ** 0.5) / float(want.norm())
+                assert rel_l2(got.numpy(), want.numpy()) < max(2e-4, 3 * own, floor), (net, name, own, floor)
 
 
 @pytest.mark.parametrize("case", [dict(B=16, A=6, F=50, H=256, lr=1e-4), dict(B=5, A=21, F=100, H=128, lr=8e-5)])
