@@ -512,6 +512,40 @@ def sub_dp(args, rank, world, dev):
     return rec
 
 
+def sub_act(args):
+    """BASELINE configs[2]: act() = encoder + actor, quadruped shape (A=12), through the public API (host numpy in,
+    host numpy out, as drqv2.py:164-175): latency at batch 1 (what train.py calls every environment step) and
+    throughput at batch 1024 (the vectorised rollout / batched eval of drqv2_b200.loop)."""
+    agent = new_agent(args, 12, 50, seed=0)
+    rng = np.random.default_rng(0)
+    rec = {"config": "quadruped_walk shape (A=12, F=50), exploration sample, host numpy -> host numpy"}
+    for n, reps in ((1, 300), (1024, 20)):
+        obs = rng.integers(0, 256, (n, 9, 84, 84) if n > 1 else (9, 84, 84), dtype=np.uint8)
+        for _ in range(5):
+            agent.act(obs, 5000, False)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            a = agent.act(obs, 5000, False)
+        dt = (time.perf_counter() - t) / reps
+        assert np.all(np.abs(a) <= 1.0)
+        rec[f"batch_{n}"] = {"ms_per_call": dt * 1e3, "observations_per_s": n / dt}
+    ref = _load_reference()
+    if ref is not None:                              # the unmodified reference's act on the same GPU, batch 1
+        torch.manual_seed(0)
+        ragent = ref.DrQV2Agent((9, 84, 84), (12,), "cuda", 1e-4, 50, args.hidden_dim, 0.01, 2000, 2, SCHED, 0.3, False)
+        obs = rng.integers(0, 256, (9, 84, 84), dtype=np.uint8)
+        with torch.no_grad():
+            for _ in range(10):
+                ragent.act(obs, 5000, False)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(100):
+                ragent.act(obs, 5000, False)
+        rec["reference_on_gpu_batch_1_ms_per_call"] = (time.perf_counter() - t) / 100 * 1e3
+    return rec
+
+
 # ----------------------------------------------------------------------------- main arm
 def run_ours(args, rank, world):
     from drqv2_b200 import _lib
@@ -648,6 +682,8 @@ def run_ours(args, rank, world):
         torch.cuda.empty_cache()
     out = None
     if rank == 0:
+        if not args.no_subrecords and args.mode == "bf16":
+            extra["act_quadruped"] = sub_act(args)
         gref = gpu_reference(args) if not args.no_gpu_reference else None
         cpu = cpu_baseline(args, steps=5)
         out = {"metric": "DrQ-v2 updates/sec at batch 256", "value": value, "unit": "updates/s", "n_gpus": world,
@@ -797,8 +833,13 @@ def main():
             print(json.dumps(out), flush=True)
         return
     if world > 1:
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-        torch.distributed.init_process_group("nccl")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"              # rank 0's stdout carries exactly one JSON line
+        # the data-parallel sub-record overlaps its all-reduces with persistent kernels that leave 8 SMs free
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8"))
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = run_ours(args, rank, world)
     if out is not None:
         print(json.dumps(out), flush=True)

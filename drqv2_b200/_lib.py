@@ -47,6 +47,7 @@ SIGNATURES = {
     "drq_conv1_wgrad_bf16": [P, P, P, P, P, P, I, I, I, P],
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
     "drq_set_pdl": [I],
+    "drq_set_sm_limit": [I],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],

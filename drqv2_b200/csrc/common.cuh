@@ -27,6 +27,10 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // entry (pdl_trigger, -DDRQ_PDL_ENTRY_TRIGGER) parks the next kernel's CTAs on the SMs for the whole run of a
 // multi-wave kernel and was measured 25 % slower.  Without the launch attribute the instructions are no-ops.
 extern int g_pdl;
+// SMs the persistent kernels size their grids for (drq_set_sm_limit): all of them, or fewer when a concurrent
+// collective's CTAs need SMs of their own (a persistent kernel never yields an SM once its CTAs are resident).
+extern int g_sm_limit;
+inline int sm_budget() { return g_sm_limit; }
 __device__ __forceinline__ void pdl_trigger() {
 #ifdef DRQ_PDL_ENTRY_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

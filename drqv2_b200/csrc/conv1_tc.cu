@@ -508,7 +508,7 @@ static int conv1_fwd_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t
     a.n_images = N;
     a.stamps = g_c1_stamps;
     const int tiles = N * 14;
-    const int G = tiles < 148 ? tiles : 148;
+    const int G = tiles < sm_budget() ? tiles : sm_budget();
     if (cin == 9) launch_k(conv1_tc_kernel<false, 9>, G, kC1Threads, kConv1FwdSmem, stream, a);
     else launch_k(conv1_tc_kernel<false, 0>, G, kC1Threads, kConv1FwdSmem, stream, a);
     return check_launch("conv1_tc_kernel<fwd>");

@@ -264,16 +264,11 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // gradient tile: 3 UMMAs of 5 KB per K step instead of 10 of 3 KB.  Units 13..15 read whatever follows
 // in shared memory; their accumulator rows are ignored.  Every CTA keeps its 3 accumulators (96 TMEM columns)
 // across all of its tiles and writes one fp32 partial at the end; partials are reduced in fixed order.
-// Tiles are 256 positions: the kernel is bound by the bulk-copy engine (33 ns + bytes / 105 GB/s per copy,
-// 16 copies per tile), and longer tiles halve the copies per position and re-read less halo.
-constexpr int kWgStages = 2;
-constexpr int kWgTM = 256;                                 // positions (K) per tile
-constexpr int kWgDRows = kWgTM;                            // d tile rows per block
-constexpr int kWgRows = kWgTM + kHaloTC + 4;               // 344 staged rows per unit (8-row aligned)
-constexpr int kWgPlane = kWgRows * 16;                     // one MN unit: 344 positions x 8 channels
+constexpr int kWgStages = 3;
+constexpr int kWgDRows = kTM;                              // d tile rows per block
+constexpr int kWgPlane = kStageRows * 16;                  // one MN unit: 216 positions x 8 channels
 constexpr int kWgABytes = 13 * kWgPlane;                   // 3 shifted windows x 4 channel blocks + ones
 constexpr int kWgStageBytes = kWgABytes + 4 * kWgDRows * 16;
-static_assert(kWgRows % 8 == 0 && kWgStageBytes % 128 == 0, "stage alignment");
 constexpr int kWgAcc = 10;
 constexpr int kWgPartial = kWgAcc * 32 * 32;
 static_assert(kWgPartial == kWgPartialFloats, "wgrad_reduce.cuh");               // floats per CTA: [9 taps + bias][ci][co]
@@ -282,15 +277,8 @@ struct WgradTcArgs {
     const __nv_bfloat16* in; long long cs_in;
     const __nv_bfloat16* d; long long cs_d;
     float* partial;
-    int n_images, ntiles, n_pos;                           // n_pos = hout * PW: positions with a gradient
+    int n_images, ntiles;
 };
-
-// K steps (16 positions) of the tile at p0: the last tile of an image stops where the gradient rows end - the
-// rows behind them belong to the next image
-__device__ __forceinline__ int wg_ksteps(int n_pos, int p0) {
-    const int left = (n_pos - p0 + 15) >> 4;
-    return left < kWgTM / 16 ? left : kWgTM / 16;
-}
 
 __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -329,17 +317,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         // lanes 0..11: input window, shift lane / 4, channel block lane % 4; lanes 12..15: gradient tile channel blocks
         int stage = 0; uint32_t phase = 0;
         for (int t = cta; t < total_tiles; t += ncta) {
-            const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kWgTM;
-            const int drows = wg_ksteps(a.n_pos, p0) * 16, xrows = drows + kHaloTC;
+            const int n = t / a.ntiles, p0 = (t - n * a.ntiles) * kTM;
             mbar_wait(empty + stage, phase ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(full + stage, (12 * xrows + 4 * drows) * 16);
+            if (lane == 0) mbar_arrive_expect_tx(full + stage, (12 * kWinRows + 4 * kWgDRows) * 16);
             __syncwarp();
             const long long row0 = (long long)n * kPLB + kGuard + p0;
             uint8_t* dst = st_s + stage * kWgStageBytes;
             if (lane < 12)
-                bulk_g2s(dst + lane * kWgPlane, a.in + ((lane & 3) * a.cs_in + row0 + (lane >> 2)) * 8, xrows * 16, full + stage);
+                bulk_g2s(dst + lane * kWgPlane, a.in + ((lane & 3) * a.cs_in + row0 + (lane >> 2)) * 8, kWinRows * 16, full + stage);
             else if (lane < 16)
-                bulk_g2s(dst + kWgABytes + (lane - 12) * kWgDRows * 16, a.d + ((lane - 12) * a.cs_d + row0) * 8, drows * 16, full + stage);
+                bulk_g2s(dst + kWgABytes + (lane - 12) * kWgDRows * 16, a.d + ((lane - 12) * a.cs_d + row0) * 8, kWgDRows * 16, full + stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
         pdl_release();
@@ -351,13 +338,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv3x3_wgrad_tc_kernel(WgradTc
         const uint64_t da0 = make_smem_desc(smem_u32(st_s), 128, kWgPlane);
         const uint64_t db0 = make_smem_desc(smem_u32(st_s) + kWgABytes, 128, kWgDRows * 16);
         for (int t = cta; t < total_tiles; t += ncta) {
-            const int nks = wg_ksteps(a.n_pos, (t % a.ntiles) * kWgTM);
             mbar_wait(full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t so = (uint64_t)(stage * (kWgStageBytes >> 4));
 #pragma unroll 1
-                for (int ks = 0; ks < nks; ++ks) {
+                for (int ks = 0; ks < kTM / 16; ++ks) {
                     const uint64_t db = db0 + so + (uint64_t)(ks * 16);
                     const uint64_t da = da0 + so + (uint64_t)(ks * 16);
                     const uint32_t accum = (first && ks == 0) ? 0u : 1u;
@@ -414,7 +400,7 @@ constexpr size_t kConvTcSmem = kWBytes + kStagesTC * kStageBytes + (2 * kStagesT
 // ctas_per_sm = 2 for forward / dgrad (74 KB smem, 128 TMEM columns each): independent pipelines per SM
 // keep the tensor pipe fed while one CTA's issuing thread waits for data or a free accumulator
 static int conv_tc_grid(int total_tiles, int ctas_per_sm = 1) {
-    const int slots = 148 * ctas_per_sm;
+    const int slots = sm_budget() * ctas_per_sm;
     return total_tiles < slots ? total_tiles : slots;
 }
 
@@ -499,8 +485,7 @@ int drq_conv3x3_wgrad_bf16(const uint16_t* in, int n_in, const uint16_t* dpre, f
     a.cs_d = (long long)N * kPLB + kSlack;
     a.partial = partial;
     a.n_images = N;
-    a.n_pos = hout * kPW;
-    a.ntiles = (a.n_pos + kWgTM - 1) / kWgTM;
+    a.ntiles = (hout * kPW + kTM - 1) / kTM;
     const int G = conv_wgrad_ctas(N, hout);                   // tile walkers, one per SM
     launch_k(conv3x3_wgrad_tc_kernel, G, kThreadsTC, kWgradTcSmem, as_stream(stream), a);
     if (int rc = check_launch("conv3x3_wgrad_tc_kernel")) return rc;

@@ -9,6 +9,7 @@ namespace drq {
 
 static thread_local char g_err[512] = "";
 int g_pdl = 0;
+int g_sm_limit = 148;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -318,6 +319,12 @@ extern "C" {
 
 int drq_set_pdl(int on) { g_pdl = on ? 1 : 0; return DRQ_OK; }
 
+int drq_set_sm_limit(int sms) {
+    DRQ_REQUIRE(sms >= 1 && sms <= 148, "set_sm_limit: 1..148");
+    drq::g_sm_limit = sms;
+    return DRQ_OK;
+}
+
 int drq_abi_version(void) { return DRQ_ABI_VERSION; }
 const char* drq_last_error(void) { return drq::g_err; }
 
@@ -328,7 +335,7 @@ int drq_device_sm_count(void) {
         cudaGetLastError();
         return 0;
     }
-    return n;
+    return n < drq::g_sm_limit ? n : drq::g_sm_limit;
 }
 
 int drq_ring_gather_nstep(const uint8_t* frames, const float* action, const float* reward,

@@ -9,12 +9,12 @@ constexpr int kWgPartialFloats = 10 * 32 * 32;     // conv3x3: [9 taps + bias][c
 constexpr int kC1PartialFloats = 32 * 96;          // conv1: [co][96 K entries] per CTA
 
 inline int conv_wgrad_ctas(int n_images, int hout) {             // tile walkers of conv3x3_wgrad_tc_kernel
-    const int tiles = n_images * ((hout * DRQ_PW + 255) / 256);   // 256-position tiles
-    return tiles < 148 ? tiles : 148;
+    const int tiles = n_images * ((hout * DRQ_PW + 127) / 128);
+    return tiles < sm_budget() ? tiles : sm_budget();
 }
 inline int conv1_wgrad_ctas(int n_images) {
     const int tiles = n_images * 14;
-    return tiles < 148 ? tiles : 148;
+    return tiles < sm_budget() ? tiles : sm_budget();
 }
 constexpr int kWgReduceBlocks = (9248 + 31) / 32;
 constexpr int kC1ReduceBlocks = 32 * 96 / 32;

@@ -470,6 +470,9 @@ class DrQV2Agent:
         self._opt_steps = dict(encoder=0, critic=0, actor=0)   # torch.optim.Adam keeps one step count per optimiser
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self.data_parallel = bool(data_parallel) and _dist.world() > 1
+        # SMs a data-parallel update leaves to NCCL (bf16 mode overlaps its all-reduces with the encoder backward; set
+        # NCCL_MAX_CTAS to the same number before the process group is created)
+        self.dp_reserve_sms = int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8")) if self.mode == "bf16" else 0
         if self.data_parallel:
             a = self._arena
             _dist.broadcast_([a.params, a.target, a.exp_avg, a.exp_avg_sq])
@@ -791,6 +794,9 @@ class DrQV2Agent:
         if fetch is not None and hasattr(replay_iter, "check_ready"):
             replay_iter.check_ready()              # a replayed graph cannot raise: an empty ring is refused here
         state = self._graphs.get(key) if self.use_cuda_graph else None
+        if self.data_parallel and self.dp_reserve_sms:
+            # grids of the persistent kernels are fixed at launch / capture: leave SMs to the NCCL CTAs that run beside them
+            call("drq_set_sm_limit", _lib.lib().drq_device_sm_count() - self.dp_reserve_sms)
         try:
             if not self.use_cuda_graph:
                 self._update_body(ws, fetch, draw=inj is None, ring=ring)
@@ -813,6 +819,9 @@ class DrQV2Agent:
             torch.cuda.synchronize()
             self._scal_cursor.fill_(self._scal_enq)
             raise
+        finally:
+            if self.data_parallel and self.dp_reserve_sms:
+                call("drq_set_sm_limit", 148)
         for net in self._opt_steps:
             self._opt_steps[net] += 1
         self._scalars_enqueued()

@@ -74,6 +74,11 @@ int drq_device_sm_count(void);
  * latency and CTA-local set-up overlap the running kernel's tail; each kernel waits for its predecessors
  * (griddepcontrol.wait) before touching global memory. */
 int drq_set_pdl(int on);
+/* SMs the persistent kernels (convs, GEMMs) size their grids for: 148 (default) or fewer.  A data-parallel update
+ * leaves a few SMs to the NCCL all-reduce that runs beside the encoder backward - a persistent kernel keeps every SM it
+ * got until it ends, so a collective that finds none free would either wait for it or make its late CTAs run their
+ * (statically assigned) tiles after everyone else.  Read at launch time; the per-CTA workspaces are sized for 148. */
+int drq_set_sm_limit(int sms);
 
 /* ------------------------------------------------------------------ replay */
 

@@ -1,4 +1,4 @@
-"""Index-math check of wgrad_tile256_untested.patch (no GPU): every gradient position is covered exactly once, the
+"""Index-math check of wgrad_tile256_no_gain.patch (no GPU): every gradient position is covered exactly once, the
 d rows a tile reads stay in front of the next image's first real row, and no copy leaves the WB buffer."""
 PLB, GUARD, SLACK, PW, HALO, TM = 1776, 88, 128, 41, 84, 256
 for N in (1, 4, 256):
