@@ -682,7 +682,7 @@ def run_ours(args, rank, world):
         torch.cuda.empty_cache()
     out = None
     if rank == 0:
-        if not args.no_subrecords and args.mode == "bf16":
+        if not args.no_subrecords and args.mode == "bf16" and world == 1:   # a one-GPU path: measured in the N=1 run
             extra["act_quadruped"] = sub_act(args)
         gref = gpu_reference(args) if not args.no_gpu_reference else None
         cpu = cpu_baseline(args, steps=5)

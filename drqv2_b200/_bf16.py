@@ -584,6 +584,20 @@ def critic_pass(agent, ws, bw, encoder_grad=True):
 
 
 def actor_pass(agent, ws, bw, soft_update=True, standalone=False):
+    """update_actor; see _actor_pass.  Inside update() this pass runs beside the encoder backward, whose persistent conv
+    kernels keep 148 KB of every SM's shared memory: its GEMMs are launched in their small-footprint variant
+    (drq_set_gemm_small) so that their CTAs fit next to the conv CTAs instead of waiting for a conv kernel to end."""
+    small = agent._encoder_side_stream() is not None and not standalone and agent.small_gemms_beside_encoder
+    if small:
+        call("drq_set_gemm_small", 1)
+    try:
+        _actor_pass(agent, ws, bw, soft_update, standalone)
+    finally:
+        if small:
+            call("drq_set_gemm_small", 0)
+
+
+def _actor_pass(agent, ws, bw, soft_update=True, standalone=False):
     """update_actor (drqv2.py:206-228).  Inside update() the actor's own forward on obs already ran with the critic
     pass (its parameters have not changed since); here: sample, the stepped critic's Q, and the backward.
     standalone=True (stage API): run that forward on the obs rows first.  soft_update=False: leave the target

@@ -48,6 +48,7 @@ SIGNATURES = {
     "drq_gemm_bf16": [P, I, P, I, I, P, L, I, P, P, I, I, I, I, I, I, I, I, P, I, I, P],
     "drq_set_pdl": [I],
     "drq_set_sm_limit": [I],
+    "drq_set_gemm_small": [I],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],

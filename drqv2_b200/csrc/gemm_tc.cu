@@ -52,18 +52,23 @@ static long long* g_stamps = nullptr;
 #define GT_STAMP(i) do { } while (0)
 #endif
 
-template <int MODE, int BN, int EPI>
+// SMALL: a two-stage pipeline (<= 66 KB of shared memory instead of <= 196 KB) for the launches that run BESIDE the
+// encoder backward (the actor pass): the persistent conv kernels keep 148 KB of every SM until they end, and a GEMM
+// CTA that does not fit into the remaining 79 KB waits for the running conv kernel to finish - measured as ~60 us
+// of the update.  These GEMMs are latency-bound, so the shallower pipeline costs them little.
+template <int MODE, int BN, int EPI, int SMALL = 0>
 struct GemmCfg {
     static constexpr int BK = MODE == MODE_MNMN ? RA : 64;                 // contraction extent per stage
     static constexpr int A_BYTES = MODE == MODE_MNMN ? 16 * RA * 16 : 8 * RA * 16;
     static constexpr int B_BYTES = MODE == MODE_KK ? 8 * BN * 16 : (MODE == MODE_KMN ? (BN / 8) * RW * 16 : (BN / 8) * RA * 16);
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    // epilogue scratch: 2 bias rows + per epilogue warp one fp32 transpose tile (32 x 33, or the whole 32 x BN
-    // tile for the trunk weight gradient's re-ordering store)
-    static constexpr int XP_FLOATS = EPI == DRQ_TEPI_TRUNK_WGRAD ? 32 * (BN + 1) : 32 * 33;
+    // epilogue scratch: 2 bias rows + (fp32 outputs only) per epilogue warp one fp32 transpose tile (32 x 33, or the
+    // whole 32 x BN tile for the trunk weight gradient's re-ordering store)
+    static constexpr bool XPOSE = EPI == DRQ_TEPI_F32 || EPI == DRQ_TEPI_TRUNK_WGRAD;
+    static constexpr int XP_FLOATS = EPI == DRQ_TEPI_TRUNK_WGRAD ? 32 * (BN + 1) : (XPOSE ? 32 * 33 : 0);
     static constexpr int EPI_BYTES = 2 * BN * 4 + 4 * XP_FLOATS * 4;
     static constexpr int BUDGET = 196 * 1024 - EPI_BYTES;
-    static constexpr int STAGES = BUDGET / STAGE > 6 ? 6 : BUDGET / STAGE;
+    static constexpr int STAGES = SMALL ? 2 : (BUDGET / STAGE > 6 ? 6 : BUDGET / STAGE);
     static constexpr int ACC = 2;                                          // TMEM accumulator stages
     static constexpr int B_COPIES = (MODE == MODE_KK && BN == 128) ? 2 : 1;   // K-major weight tiles are 64-row blocks
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + EPI_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
@@ -108,9 +113,9 @@ __device__ __forceinline__ TileInfo tile_info(const GemmTcArgs& g, int t, int nt
 // Persistent over output tiles: CTA b works on tiles b, b + gridDim.x, ...; the operand pipeline runs across
 // tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of one tile overlaps
 // the loads and UMMAs of the next (the skinny GEMMs of the trunk backward have 300-600 tiles).
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, int SMALL = 0>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs g) {
-    using Cfg = GemmCfg<MODE, BN, EPI>;
+    using Cfg = GemmCfg<MODE, BN, EPI, SMALL>;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int STAGES = Cfg::STAGES, STAGE = Cfg::STAGE, A_BYTES = Cfg::A_BYTES, BK = Cfg::BK, ACC = Cfg::ACC;
     float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE);      // [2][BN]
@@ -405,16 +410,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     if (tid == 0) GT_STAMP(8);
 }
 
-template <int MODE, int BN, int EPI>
+static int g_gemm_small = 0;
+
+template <int MODE, int BN, int EPI, int SMALL = 0>
 static int launch_gemm_tc(GemmTcArgs& g, int batch, cudaStream_t s) {
-    using Cfg = GemmCfg<MODE, BN, EPI>;
-    if (int rc = ensure_smem((const void*)gemm_tc_kernel<MODE, BN, EPI>, Cfg::SMEM, "gemm_bf16")) return rc;
+    using Cfg = GemmCfg<MODE, BN, EPI, SMALL>;
+    if (int rc = ensure_smem((const void*)gemm_tc_kernel<MODE, BN, EPI, SMALL>, Cfg::SMEM, "gemm_bf16")) return rc;
     g.nz = g.splitk * batch;
     const int nt = (g.N + BN - 1) / BN, mt = (g.M + GT_BM - 1) / GT_BM;
     const int tiles = nt * mt * g.nz;
     const int sms = drq_device_sm_count();
     g.grid3d = tiles <= sms ? 1 : 0;
-    launch_k(gemm_tc_kernel<MODE, BN, EPI>, g.grid3d ? dim3(nt, mt, g.nz) : dim3(sms), GT_THREADS, Cfg::SMEM, s, g);
+    launch_k(gemm_tc_kernel<MODE, BN, EPI, SMALL>, g.grid3d ? dim3(nt, mt, g.nz) : dim3(sms), GT_THREADS, Cfg::SMEM, s, g);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -496,6 +503,12 @@ int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b
     cudaStream_t s = as_stream(stream);
 #define GT_CASE(MODE_, BN_, EPI_) \
     if (mode == MODE_ && bn == BN_ && epilogue == EPI_) return launch_gemm_tc<MODE_, BN_, EPI_>(g, batch, s);
+#define GT_SMALL(MODE_, BN_, EPI_) \
+    if (g_gemm_small && mode == MODE_ && bn == BN_ && epilogue == EPI_) return launch_gemm_tc<MODE_, BN_, EPI_, 1>(g, batch, s);
+    GT_SMALL(MODE_KK, 64, DRQ_TEPI_F32)
+    GT_SMALL(MODE_KK, 64, DRQ_TEPI_RELU_BF16)
+    GT_SMALL(MODE_KMN, 64, DRQ_TEPI_F32)
+    GT_SMALL(MODE_KMN, 64, DRQ_TEPI_MASK_BF16)
     GT_CASE(MODE_KK, 64, DRQ_TEPI_F32)
     GT_CASE(MODE_KK, 64, DRQ_TEPI_RELU_BF16)
     GT_CASE(MODE_KK, 128, DRQ_TEPI_F32)
@@ -508,9 +521,12 @@ int drq_gemm_bf16(const uint16_t* A, int units_a, const uint16_t* B, int units_b
     GT_CASE(MODE_MNMN, 128, DRQ_TEPI_F32)
     GT_CASE(MODE_MNMN, 128, DRQ_TEPI_TRUNK_WGRAD)
 #undef GT_CASE
+#undef GT_SMALL
     set_error("gemm_bf16: no kernel for mode %d, bn %d, epilogue %d", mode, bn, epilogue);
     return DRQ_ERR_INVALID;
 }
+
+int drq_set_gemm_small(int on) { g_gemm_small = on ? 1 : 0; return DRQ_OK; }
 
 int drq_debug_gemm_stamps(int64_t* buf) { g_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
 

@@ -79,6 +79,10 @@ int drq_set_pdl(int on);
  * got until it ends, so a collective that finds none free would either wait for it or make its late CTAs run their
  * (statically assigned) tiles after everyone else.  Read at launch time; the per-CTA workspaces are sized for 148. */
 int drq_set_sm_limit(int sms);
+/* on: drq_gemm_bf16 launches of the K-major / K-MN modes with 64-wide tiles use a two-stage pipeline (<= 66 KB of shared
+ * memory) so that their CTAs fit on an SM BESIDE two resident CTAs of the persistent conv kernels (148 KB) - set by the
+ * host around the launches of the actor pass, which runs beside the encoder backward.  Read at launch time. */
+int drq_set_gemm_small(int on);
 
 /* ------------------------------------------------------------------ replay */
 
