@@ -24,7 +24,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // mode 0: K-major no swizzle ([unit][rows][16B]); 1: K-major 128B swizzle ([rows][128B], K=64 per row);
 // 2: MN-major no swizzle for both; 3: A from TMEM (columns 128.. of the allocation), B K-major no swizzle
-__global__ void __launch_bounds__(128, 2) mma_kernel(int M, int N, int mode, int iters, int distinct, long long* out) {
+template <int mode, int distinct>
+__global__ void __launch_bounds__(128, 2) mma_kernel(int M, int N, int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
@@ -65,7 +66,6 @@ __global__ void __launch_bounds__(128, 2) mma_kernel(int M, int N, int mode, int
 
 int main() {
     long long* out; cudaMalloc(&out, 148 * 8);
-    cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     printf("M N mode | cycles/MMA (grid 148)  -> MAC/clk/SM\n");
     for (int ctas : {1, 2}) {
     printf("---- %d CTA(s) per SM\n", ctas);
@@ -77,7 +77,13 @@ int main() {
               for (int distinct : {9, 8}) {
                 if (distinct == 8 && mode == 1) continue;
                 if (mode == 3 && (ctas == 2 || distinct == 9 || N == 256)) continue;   // A in TMEM: one CTA per SM owns all 512 columns
-                mma_kernel<<<148 * ctas, 128, 100 * 1024>>>(M, N, mode, iters, distinct, out);
+                auto launch = [&](auto kern) {
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                    kern<<<148 * ctas, 128, 100 * 1024>>>(M, N, iters, out);
+                };
+                if (mode == 0 && distinct == 9) launch(mma_kernel<0, 9>);
+                else if (mode == 0) launch(mma_kernel<0, 8>);
+                else launch(mma_kernel<3, 8>);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("M=%d N=%d mode=%d: %s\n", M, N, mode, cudaGetErrorString(e)); return 1; }
                 long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
