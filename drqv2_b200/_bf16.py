@@ -131,6 +131,13 @@ class ColsumJob(C.Structure):
                 ("tb", C.c_int32), ("reserved", C.c_int32), ("Y", C.c_void_p)]
 
 
+class PolicySample(C.Structure):
+    """drq_policy_sample: one TruncatedNormal sample job of drq_policy_head_fwd_bf16"""
+    _fields_ = [("row0", C.c_int32), ("rows", C.c_int32), ("eps", C.c_void_p), ("action_out", C.c_void_p),
+                ("ld_a", C.c_int64), ("mu_out", C.c_void_p), ("metrics", C.c_void_p), ("a_bf16", C.c_void_p),
+                ("units_a", C.c_int64), ("feat_off", C.c_int32), ("reserved", C.c_int32)]
+
+
 def colsum_multi(jobs):
     arr = (ColsumJob * len(jobs))(*jobs)
     call("drq_colsum_multi", arr, len(jobs), _stream())
@@ -411,17 +418,20 @@ def twin_q_fwd(agent, bw, x, nets, B):
     twin_q_heads(agent, bw, nets, B)
 
 
-def actor_mlp_fwd(agent, hA, p1, p2, mu_pre, M):
-    """policy MLP (drqv2.py:77-81) on the first M rows of hA."""
+def actor_mlp_fwd(agent, hA, p1, p2, mu_pre, M, samples=(), clip=0.0):
+    """policy MLP (drqv2.py:77-81) on the first M rows of hA; the Linear(hidden, A) head and the TruncatedNormal
+    samples of the row ranges in `samples` (PolicySample jobs, utils.py:112-126) are one launch."""
     st = agent._bf16
     A, Fd, H = agent.action_dim, agent.feature_dim, agent.hidden_dim
     pa = lambda k: agent._p("actor", k)
-    w0, w2, w4 = st.p0, st.p2, st.p4
+    w0, w2 = st.p0, st.p2
     gemm(hA.ptr(), hA.units, w0.ptr(), w0.units, GEMM_KK, p1.ptr(), p1.units, M, H, Fd, TEPI_RELU_BF16,
          bias=pa("policy.0.bias"))
     gemm(p1.ptr(), p1.units, w2.ptr(), w2.units, GEMM_KK, p2.ptr(), p2.units, M, H, H, TEPI_RELU_BF16,
          bias=pa("policy.2.bias"))
-    gemm(p2.ptr(), p2.units, w4.ptr(), w4.units, GEMM_KK, mu_pre, A, M, A, H, TEPI_F32, bias=pa("policy.4.bias"))
+    jobs = (PolicySample * max(1, len(samples)))(*samples)
+    call("drq_policy_head_fwd_bf16", p2.ptr(), p2.units, pa("policy.4.weight"), pa("policy.4.bias"), mu_pre, M, H, A,
+         jobs, len(samples), agent._sc("stddev"), float(clip), agent._policy_ticket.data_ptr(), _stream())
 
 
 class _Beside:
@@ -486,10 +496,14 @@ def critic_pass(agent, ws, bw, encoder_grad=True):
         with beside:
             twin_q_layers(agent, bw, bw.x, 0, 1, B)
     # ---- actor MLP on [obs | next] rows at once (drqv2.py:182 and :210 use the same actor parameters)
-    actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), RB + B)
-    # next action: clipped sample (drqv2.py:183) -> xT's action columns
-    call("drq_actor_sample", bw.mu_pre.data_ptr() + F32 * RB * A, ws.eps_c.data_ptr(), std_ptr, float(agent.stddev_clip),
-         ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, bw.x.ptr(1), bw.x.units, Fd, B, A, s)
+    # ... with, in the policy head's launch, the next action - clipped sample (drqv2.py:183) -> xT's action columns - and
+    # already the actor pass' own sample on the obs rows (drqv2.py:210-212: same actor, same stddev, its own noise) ->
+    # xA's action columns, mu, log-prob / entropy metrics
+    xA = bw.xA
+    actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), RB + B, clip=agent.stddev_clip, samples=[
+        PolicySample(RB, B, ws.eps_c.data_ptr(), ws.xT.data_ptr() + F32 * Fd, Fd + A, None, None, bw.x.ptr(1), bw.x.units, Fd, 0),
+        PolicySample(0, B, ws.eps_a.data_ptr(), ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(),
+                     ws.metrics.data_ptr() + F32 * 6, xA.ptr(), xA.units, Fd, 0)])
     # ---- target Q on (next, next action) and online Q on (obs, action)
     if split_q:
         twin_q_layers(agent, bw, bw.x, 1, 1, B)
@@ -617,15 +631,16 @@ def _actor_pass(agent, ws, bw, soft_update=True, standalone=False):
         ln_tanh_multi([LnJob(bw.partial.data_ptr(), FP, B * FP, bw.S1, pa("trunk.0.bias"), pa("trunk.1.weight"),
                              pa("trunk.1.bias"), ws.hA.data_ptr(), Fd, ws.xhatA.data_ptr(), ws.rstdA.data_ptr(),
                              bw.hA.buf.data_ptr(), bw.hA.units, 0)], B, Fd)
-        actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), B)
+        actor_mlp_fwd(agent, bw.hA, bw.p1, bw.p2, bw.mu_pre.data_ptr(), B, clip=agent.stddev_clip, samples=[
+            PolicySample(0, B, ws.eps_a.data_ptr(), ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(),
+                         ws.metrics.data_ptr() + F32 * 6, xA.ptr(), xA.units, Fd, 0)])
     if beside.side is not None and soft_update:
         # the soft target update depends on the stepped critic only (drqv2.py:259-260 runs it after update_actor, on the
         # same critic parameters) and nothing in this pass reads the target: beside the whole pass
         with beside:
             st.step_target()
-    call("drq_actor_sample", bw.mu_pre.data_ptr(), ws.eps_a.data_ptr(), std_ptr, float(agent.stddev_clip),
-         ws.xA.data_ptr() + F32 * Fd, Fd + A, ws.mu.data_ptr(), ws.metrics.data_ptr() + F32 * 6,
-         xA.ptr(), xA.units, Fd, B, A, s)
+    # (the sample a = clamp(mu + clip(eps * std)) of drqv2.py:210-211 was drawn with the actor's forward - the policy head's
+    # launch in the critic pass, or just above in the stage API)
     # the just-updated critic on (features, action) (drqv2.py:213-216)
     S = bw.S1
     part = bw.partial.data_ptr()
@@ -714,6 +729,5 @@ def act_body(agent, w, n, sample):
          splitk=S, strides=_strides(split=n * FP))
     ln_tanh_multi([LnJob(part, FP, n * FP, S, pa("trunk.0.bias"), pa("trunk.1.weight"), pa("trunk.1.bias"),
                          w["h"].data_ptr(), Fd, None, None, w["h_b"].ptr(), w["h_b"].units, 0)], n, Fd)
-    actor_mlp_fwd(agent, w["h_b"], w["p1_b"], w["p2_b"], w["mu_pre"].data_ptr(), n)
-    call("drq_actor_sample", w["mu_pre"].data_ptr(), w["eps"].data_ptr() if sample else None,
-         agent._sc("stddev"), 0.0, w["out"].data_ptr(), A, None, None, None, 0, 0, n, A, s)
+    actor_mlp_fwd(agent, w["h_b"], w["p1_b"], w["p2_b"], w["mu_pre"].data_ptr(), n, samples=[
+        PolicySample(0, n, w["eps"].data_ptr() if sample else None, w["out"].data_ptr(), A, None, None, None, 0, 0, 0)])

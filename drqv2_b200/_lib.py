@@ -65,6 +65,7 @@ SIGNATURES = {
     "drq_ln_tanh_fwd_multi": [P, I, I, I, F, P],
     "drq_ln_tanh_bwd": [P, L, P, L, P, P, P, P, P, P, P, L, I, I, I, L, P],
     "drq_actor_sample": [P, P, P, F, P, L, P, P, P, L, I, I, I, P],
+    "drq_policy_head_fwd_bf16": [P, L, P, P, P, I, I, I, P, I, P, F, P, P],
     "drq_actor_sample_bwd": [P, L, P, P, P, L, I, I, I, L, P],
     "drq_q_head_fwd_bf16": [P, L, L, P, P, P, I, I, I, L, I, L, P],
     "drq_q_head_bwd_loss_bf16": [I, P, P, P, P, P, P, P, L, L, P, P, P, P, I, I, L, P],

@@ -17,12 +17,17 @@ STRUCTS = {   # header struct -> (ctypes mirror, fields)
     "drq_wgrad_reduce_job": ("WgReduceJob", ["partial", "dw", "db", "n_images", "hout", "cin", "reserved"]),
     "drq_ln_job": ("LnJob", ["partial", "ld_partial", "split_stride", "S", "bias", "gamma", "beta", "h_out", "ld_h", "xhat",
                              "rstd", "h_bf16", "units_bf16", "row0_bf16", "tail", "ld_tail", "n_tail"]),
+    "drq_policy_sample": ("PolicySample", ["row0", "rows", "eps", "action_out", "ld_a", "mu_out", "metrics", "a_bf16",
+                                           "units_a", "feat_off", "reserved"]),
+    "drq_ring_src": ("replay_buffer.RingSrc", ["frames", "action", "reward", "discount", "capacity", "frame_c", "stack", "A",
+                                               "nstep", "gamma", "reserved", "ep_table", "n_episodes", "seed", "counter",
+                                               "ep_start", "idx"]),
 }
 
 
 @pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
 def test_ctypes_structs_match_the_header(tmp_path):
-    from drqv2_b200 import _bf16
+    from drqv2_b200 import _bf16, replay_buffer
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{ROOT / "include" / "drqv2_b200.h"}"', "int main(void) {"]
     for cname, (_, fields) in STRUCTS.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
@@ -36,7 +41,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
     got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
     for cname, (pyname, fields) in STRUCTS.items():
-        cls = getattr(_bf16, pyname)
+        cls = getattr(replay_buffer, pyname.split(".")[1]) if "." in pyname else getattr(_bf16, pyname)
         assert C.sizeof(cls) == got[(cname, "size")], cname
         assert [f for f, _ in cls._fields_] == fields, cname
         for f in fields:
