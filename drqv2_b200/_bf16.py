@@ -429,6 +429,13 @@ def actor_mlp_fwd(agent, hA, p1, p2, mu_pre, M, samples=(), clip=0.0):
          bias=pa("policy.0.bias"))
     gemm(p1.ptr(), p1.units, w2.ptr(), w2.units, GEMM_KK, p2.ptr(), p2.units, M, H, H, TEPI_RELU_BF16,
          bias=pa("policy.2.bias"))
+    if not agent.fused_policy_head:     # DRQV2_B200_POLICY_HEAD=0: the tensor-core tile + one sampling launch per row range
+        w4 = st.p4
+        gemm(p2.ptr(), p2.units, w4.ptr(), w4.units, GEMM_KK, mu_pre, A, M, A, H, TEPI_F32, bias=pa("policy.4.bias"))
+        for j in samples:
+            call("drq_actor_sample", mu_pre + F32 * j.row0 * A, j.eps, agent._sc("stddev"), float(clip), j.action_out, j.ld_a,
+                 j.mu_out, j.metrics, j.a_bf16, j.units_a, j.feat_off, j.rows, A, _stream())
+        return
     jobs = (PolicySample * max(1, len(samples)))(*samples)
     call("drq_policy_head_fwd_bf16", p2.ptr(), p2.units, pa("policy.4.weight"), pa("policy.4.bias"), mu_pre, M, H, A,
          jobs, len(samples), agent._sc("stddev"), float(clip), agent._policy_ticket.data_ptr(), _stream())

@@ -440,6 +440,8 @@ class DrQV2Agent:
         # bf16 mode fed from the HBM ring: conv1 reads the frame stacks from the ring by index (DRQV2_B200_RING_DIRECT=0:
         # gather them into a batch buffer first)
         self.ring_direct = os.environ.get("DRQV2_B200_RING_DIRECT", "1") != "0"
+        # Linear(hidden, A) + the TruncatedNormal samples in one CUDA-core launch (0: tensor-core tile + sampling launches)
+        self.fused_policy_head = os.environ.get("DRQV2_B200_POLICY_HEAD", "1") != "0"
         # the actor pass' GEMMs in their 66 KB variant, co-resident with the encoder backward's conv CTAs.  Off: measured
         # 1769 vs 1834 updates/s - the encoder backward is the critical chain after the fork, and GEMM CTAs that share its
         # SMs slow it down more than their own waiting costs
