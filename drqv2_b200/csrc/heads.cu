@@ -273,18 +273,38 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
     __shared__ float part[8][32][9];
     __shared__ float sh[256];
     __shared__ int s_last;
-    for (int k = threadIdx.x; k < A * H; k += 256) w_s[k] = __bfloat162float(__float2bfloat16_rn(w4[k]));
-    __syncthreads();
+    for (int k = threadIdx.x; k < A * H / 4; k += 256) {          // H % 8 == 0: whole float4s
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w4) + k);
+        reinterpret_cast<float4*>(w_s)[k] = make_float4(__bfloat162float(__float2bfloat16_rn(w.x)), __bfloat162float(__float2bfloat16_rn(w.y)),
+                                                        __bfloat162float(__float2bfloat16_rn(w.z)), __bfloat162float(__float2bfloat16_rn(w.w)));
+    }
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int m = blockIdx.x * 32 + lane;
     const __nv_bfloat16* x = p2 + fb_index(0, m < M ? m : 0, units);
+    const int nu = H / 8;
+    // the row's first 8 units of this warp are requested before the weights are needed (hides the staging barrier)
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int u = grp + 8 * k;
+        v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
     for (int a0 = 0; a0 < A; a0 += 8) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (m < M) {
-#pragma unroll 2
-            for (int u = grp; u < H / 8; u += 8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8));
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int u0 = grp; u0 < nu; u0 += 64) {       // 8 units of the row in flight per lane
+            if (u0 != grp || a0 != 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int u = u0 + 8 * k;
+                    v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int u = u0 + 8 * k;
+                if (u >= nu) break;
+                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
                 float xv[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { xv[2 * j] = __uint_as_float(w[j] << 16); xv[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
