@@ -15,6 +15,7 @@ namespace drq { void set_error(const char*, ...) {} int check_launch(const char*
 constexpr int PLB = 1776, GUARD = 88, SLACK = 128, PW = 41;
 constexpr int BX = 21, BY = 7;                       // blocks per box row / block rows per box
 constexpr int BOX_BYTES = 4 * BY * BX * 16;          // 9408
+constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
                 const int s = issued % 8, plane = issued & 3, it = issued >> 2;
                 const int n = (blockIdx.x + it * gridDim.x) % n_images, ty = (it % 3) * 6;
                 mbar_arrive_expect_tx(bar + s, BOX_BYTES);
-                tma_load_5d(smem + s * BOX_BYTES, &map, 0, plane & 1, 2 * ty + (plane >> 1), 0, n, bar + s);
+                tma_load_5d(smem + s * SLOT, &map, 0, plane & 1, 2 * ty + (plane >> 1), 0, n, bar + s);
                 ++issued;
             }
             const int s = waited % 8;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(128, 1) tma_kernel(const __grid_constant__ CUt
         const int total = iters * 4;
         for (int b = 0; b < 4; ++b) {
             const int s = (total - 4 + b) % 8;
-            for (int i = threadIdx.x; i < BOX_BYTES / 2; i += 128) out[b * (BOX_BYTES / 2) + i] = reinterpret_cast<uint16_t*>(smem + s * BOX_BYTES)[i];
+            for (int i = threadIdx.x; i < BOX_BYTES / 2; i += 128) out[b * (BOX_BYTES / 2) + i] = reinterpret_cast<uint16_t*>(smem + s * SLOT)[i];
         }
     }
 }
@@ -79,10 +80,10 @@ int main() {
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return 1; }
     uint16_t* out; cudaMalloc(&out, 4 * BOX_BYTES); long long* cyc; cudaMalloc(&cyc, 148 * 8);
-    cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * BOX_BYTES);
+    cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SLOT);
     for (int inflight : {1, 2, 4, 8}) {
         const int iters = 300;
-        tma_kernel<<<148, 128, 8 * BOX_BYTES>>>(map, N, iters, inflight, out, cyc);
+        tma_kernel<<<148, 128, 8 * SLOT>>>(map, N, iters, inflight, out, cyc);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
         long long hc[148]; cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
