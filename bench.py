@@ -270,6 +270,18 @@ def profile_update_launches(agent, it, B, reps=5):
     finally:
         D.call = R.call = BF.call = orig
         agent.use_cuda_graph, agent.overlap_encoder_backward = was_graph, was_overlap
+    # what the bracket itself costs: a one-thread kernel timed in exactly the same way (flush, event, launch, event)
+    scratch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    floor = []
+    for _ in range(9):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig("drq_counter_advance", scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        e1.record()
+        torch.cuda.synchronize()
+        floor.append(e0.elapsed_time(e1) * 1e3)
+    profile_update_launches.event_floor_us = statistics.median(floor)
     launches = []
     for i, (name, a, _) in enumerate(records[0]):
         ms = statistics.median(rec[i][2] for rec in records)
@@ -290,7 +302,10 @@ def roofline_record(launches, value, world, flops_update, mode):
         return sel, us
 
     roof = {"peak_source": src, "timing": "every launch of one eager single-stream update timed alone with CUDA events on "
-            "its launch stream, a 256 MB buffer written in front of each (cold L2); median of 5 updates"}
+            "its launch stream, a 256 MB buffer written in front of each (cold L2); median of 5 updates",
+            "event_bracket_floor_us": getattr(profile_update_launches, "event_floor_us", None),
+            "event_bracket_floor_note": "a one-thread kernel timed in the same bracket: every `us` below includes about this much "
+                                        "launch / event overhead that ncu's gpu__time_duration (profiles/) does not"}
     tensor = [l for l in launches if l["class"] in ("conv", "gemm") and l["flop"]]
     if tensor:
         dom = max(tensor, key=lambda l: l["us"])

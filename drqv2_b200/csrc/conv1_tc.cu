@@ -368,6 +368,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
         const int q = warp & 3;
         if (!WGRAD) {
             int acc = 0; uint32_t acc_phase = 0;
+            float bias_r[32];                       // registers: shared-memory reads per tile were bank-conflict wavefronts
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bias_r[i] = bias_s[i];
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int n = t / TILES_PER_IMG, p0 = (t - n * TILES_PER_IMG) * kC1Tile;
                 mbar_wait(tfull + acc, acc_phase);
@@ -384,8 +387,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
                 uint32_t packed[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    packed[i] = pack_bf16x2(fmaxf(fmaf(v[2 * i], kC1Scale, bias_s[2 * i]), 0.f),
-                                            fmaxf(fmaf(v[2 * i + 1], kC1Scale, bias_s[2 * i + 1]), 0.f));
+                    packed[i] = pack_bf16x2(fmaxf(fmaf(v[2 * i], kC1Scale, bias_r[2 * i]), 0.f),
+                                            fmaxf(fmaf(v[2 * i + 1], kC1Scale, bias_r[2 * i + 1]), 0.f));
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<uint4*>(a.out + (c * a.cs_out + row) * 8) =
