@@ -851,7 +851,8 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"              # rank 0's stdout carries exactly one JSON line
         # the data-parallel sub-record overlaps its all-reduces with persistent kernels that leave 8 SMs free
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8"))
+        if int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8")) > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8"))
         local = int(os.environ.get("LOCAL_RANK", 0))
         torch.cuda.set_device(local)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
