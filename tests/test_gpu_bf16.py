@@ -478,3 +478,52 @@ def test_fused_optimiser_step_equals_adam_then_pack(dev, A, Fd, H):
         assert torch.equal(x, y), (name, int((x != y).sum()))
     for i, (x, y) in enumerate(zip(ref_p, new_p)):
         assert torch.equal(x.view(torch.int16), y.view(torch.int16)), (i, int((x.view(torch.int16) != y.view(torch.int16)).sum()))
+
+
+@pytest.mark.parametrize("M,A,H", [(512, 6, 1024), (70, 21, 256), (1, 12, 1024)])
+def test_policy_head_matches_linear_tanh_sample(dev, M, A, H):
+    """drq_policy_head_fwd_bf16: Linear(hidden, A) on bf16 operands (drqv2.py:81), tanh (:89) and the clipped
+    TruncatedNormal samples of two row ranges (utils.py:117-126) in one launch, against the oracle's functions."""
+    import ctypes as C
+    from drqv2_b200 import _lib
+    from drqv2_b200._bf16 import TB, PolicySample
+    from oracle import drq_oracle as O
+    g = torch.Generator().manual_seed(M + A)
+    p2 = (torch.rand(M, H, generator=g) - 0.3).clamp_min(0).to(dev)
+    w4 = ((torch.rand(A, H, generator=g) - 0.5) * 0.1).to(dev)
+    b4 = ((torch.rand(A, generator=g) - 0.5) * 0.1).to(dev)
+    p2b = TB(M, H, dev)
+    p2b.load(p2)
+    mu_pre = torch.zeros(M, A, device=dev)
+    std = torch.tensor([0.4], device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    n0 = M // 2
+    rows = [(0, n0), (n0, M - n0)] if n0 else [(0, M)]
+    eps = [torch.randn(r, A, generator=g).to(dev) for _, r in rows]
+    act = [torch.zeros(r, A + 3, device=dev) for _, r in rows]          # written at a column offset (ld_a = A + 3)
+    mu_out = torch.zeros(rows[-1][1], A, device=dev)
+    metrics = torch.zeros(2, device=dev)
+    xb = TB(rows[-1][1], 16 + A, dev)
+    jobs = [PolicySample(r0, r, eps[i].data_ptr(), act[i].data_ptr() + 4 * 3, A + 3, None, None, None, 0, 0, 0) for i, (r0, r) in enumerate(rows)]
+    jobs[-1] = PolicySample(rows[-1][0], rows[-1][1], eps[-1].data_ptr(), act[-1].data_ptr() + 4 * 3, A + 3, mu_out.data_ptr(),
+                            metrics.data_ptr(), xb.ptr(), xb.units, 16, 0)
+    arr = (PolicySample * len(jobs))(*jobs)
+    for rep in range(2):                                 # twice: the block-ticket counter resets itself
+        _lib.call("drq_policy_head_fwd_bf16", p2b.ptr(), p2b.units, w4.data_ptr(), b4.data_ptr(), mu_pre.data_ptr(), M, H, A,
+                  arr, len(jobs), std.data_ptr(), 0.3, ticket.data_ptr(), _stream())
+        torch.cuda.synchronize()
+        assert int(ticket) == 0
+    want_pre = _bf(p2).double() @ _bf(w4).double().T + b4.double()
+    assert (mu_pre.double() - want_pre).abs().max().item() <= 2e-5 * max(1.0, want_pre.abs().max().item())
+    for i, (r0, r) in enumerate(rows):
+        mu = torch.tanh(mu_pre[r0:r0 + r].cpu())
+        want = O.truncated_normal_sample(mu, 0.4, eps[i].cpu(), 0.3)
+        assert (act[i][:, 3:].cpu() - want).abs().max().item() <= 1e-6
+    r0, r = rows[-1]
+    mu = torch.tanh(mu_pre[r0:r0 + r].cpu())
+    assert (mu_out.cpu() - mu).abs().max().item() <= 1e-6
+    assert torch.equal(xb.dense()[:, 16:16 + A].cpu(), act[-1][:, 3:].cpu().to(torch.bfloat16).float())
+    a = act[-1][:, 3:].cpu().double()
+    lp = (-((a - mu.double()) ** 2) / (2 * 0.4 ** 2) - np.log(0.4) - np.log(np.sqrt(2 * np.pi))).sum(-1).mean().item()
+    assert abs(float(metrics[0]) - lp) <= 1e-4 * abs(lp) + 1e-5
+    assert abs(float(metrics[1]) - A * (0.5 + 0.5 * np.log(2 * np.pi) + np.log(0.4))) <= 1e-5
