@@ -850,9 +850,8 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"              # rank 0's stdout carries exactly one JSON line
-        # the data-parallel sub-record overlaps its all-reduces with persistent kernels that leave 8 SMs free
-        if int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8")) > 0:
-            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8"))
+        if int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "0")) > 0:   # opt-in: cap NCCL to the SMs the persistent kernels leave
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRQV2_B200_DP_RESERVE_SMS"])
         local = int(os.environ.get("LOCAL_RANK", 0))
         torch.cuda.set_device(local)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -476,9 +476,10 @@ class DrQV2Agent:
         self._opt_steps = dict(encoder=0, critic=0, actor=0)   # torch.optim.Adam keeps one step count per optimiser
         self._seed = int(seed) if seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self.data_parallel = bool(data_parallel) and _dist.world() > 1
-        # SMs a data-parallel update leaves to NCCL (bf16 mode overlaps its all-reduces with the encoder backward; set
-        # NCCL_MAX_CTAS to the same number before the process group is created)
-        self.dp_reserve_sms = int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "8")) if self.mode == "bf16" else 0
+        # SMs a data-parallel update leaves to NCCL (bf16 mode overlaps its all-reduces with the encoder backward).  Off:
+        # with NCCL_MAX_CTAS=8 to match, the 25 MB all-reduce takes 305 us instead of 110 and the 8-GPU step 1.57 ms
+        # instead of 1.25 (profiles/r2_dp_8gpu_*.json); without a cap NCCL's CTA count is not ours to plan for
+        self.dp_reserve_sms = int(os.environ.get("DRQV2_B200_DP_RESERVE_SMS", "0")) if self.mode == "bf16" else 0
         if self.data_parallel:
             a = self._arena
             _dist.broadcast_([a.params, a.target, a.exp_avg, a.exp_avg_sq])
