@@ -11,7 +11,10 @@ from drqv2_b200._bf16 import TB, PolicySample, gemm  # noqa: E402
 from drqv2_b200._lib import GEMM_KK, TEPI_F32  # noqa: E402
 
 dev = torch.device("cuda")
-s = torch.cuda.current_stream().cuda_stream
+def cur():
+    return torch.cuda.current_stream().cuda_stream          # the capture stream inside torch.cuda.graph
+
+
 M, A, H, B = 512, 6, 1024, 256
 g = torch.Generator(device="cuda").manual_seed(0)
 p2 = TB(M, H, dev); p2.buf.copy_((torch.rand(p2.buf.numel(), device=dev, generator=g) - 0.3).clamp_min(0).to(torch.bfloat16))
@@ -31,13 +34,13 @@ jobs = (PolicySample * 2)(PolicySample(256, B, eps.data_ptr(), out1.data_ptr(), 
 
 def fused(nj):
     _lib.call("drq_policy_head_fwd_bf16", p2.ptr(), p2.units, w4.data_ptr(), b4.data_ptr(), mu_pre.data_ptr(), M, H, A, jobs, nj,
-              std.data_ptr(), 0.3, ticket.data_ptr(), s)
+              std.data_ptr(), 0.3, ticket.data_ptr(), cur())
 
 
 def unfused():
     gemm(p2.ptr(), p2.units, w4b.ptr(), w4b.units, GEMM_KK, mu_pre.data_ptr(), A, M, A, H, TEPI_F32, bias=b4.data_ptr())
-    _lib.call("drq_actor_sample", mu_pre.data_ptr() + 4 * 256 * A, eps.data_ptr(), std.data_ptr(), 0.3, out1.data_ptr(), A, None, None, None, 0, 0, B, A, s)
-    _lib.call("drq_actor_sample", mu_pre.data_ptr(), eps.data_ptr(), std.data_ptr(), 0.3, out2.data_ptr(), A, mu.data_ptr(), metrics.data_ptr(), None, 0, 0, B, A, s)
+    _lib.call("drq_actor_sample", mu_pre.data_ptr() + 4 * 256 * A, eps.data_ptr(), std.data_ptr(), 0.3, out1.data_ptr(), A, None, None, None, 0, 0, B, A, cur())
+    _lib.call("drq_actor_sample", mu_pre.data_ptr(), eps.data_ptr(), std.data_ptr(), 0.3, out2.data_ptr(), A, mu.data_ptr(), metrics.data_ptr(), None, 0, 0, B, A, cur())
 
 
 def timeit(fn, n=200):
