@@ -219,54 +219,19 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
     }
 }
 
-// The clipped TruncatedNormal sample of rows [0, B) (utils.py:112-126) - shared by actor_sample_kernel and the last
-// block of policy_head_fwd_kernel.  One block of 256 threads; thread t handles rows t, t + 256, ...
-__device__ __forceinline__ void sample_rows(const float* __restrict__ mu_pre, const float* __restrict__ eps, float std, float clip,
-                                            float* __restrict__ action_out, long long ld_a, float* __restrict__ mu_out,
-                                            float* __restrict__ metrics, __nv_bfloat16* __restrict__ a_bf, long long rpad_ab,
-                                            int feat_off, int B, int A, float* sh) {
-    const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;  // utils.py:113 (python: -1.0 + 1e-6 -> fp32)
-    const float log_std = logf(std);
-    float lp_sum = 0.f;
-    for (int b = threadIdx.x; b < B; b += 256) {
-        float lp = 0.f;
-        for (int j = 0; j < A; ++j) {
-            const float mu = tanhf(__ldcg(mu_pre + (long long)b * A + j));   // drqv2.py:89
-            float a = mu;
-            if (eps) {
-                float e = __fmul_rn(eps[(long long)b * A + j], std);      // utils.py:120
-                if (clip > 0.f) e = fminf(fmaxf(e, -clip), clip);         // utils.py:121-122
-                const float x = __fadd_rn(mu, e);                          // utils.py:123
-                a = fminf(fmaxf(x, lo), hi);                               // utils.py:113-116 (value)
-                const float d = a - mu;
-                lp += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
-            }
-            action_out[(long long)b * ld_a + j] = a;
-            if (a_bf) a_bf[fb_index(feat_off + j, b, rpad_ab)] = __float2bfloat16_rn(a);
-            if (mu_out) mu_out[(long long)b * A + j] = mu;
-        }
-        lp_sum += lp;
-    }
-    if (metrics) {
-        const float t = block_sum_256(lp_sum, sh);
-        if (threadIdx.x == 0) {
-            metrics[0] = t / (float)B;                                         // actor_logprob
-            metrics[1] = (float)A * (0.5f + 0.9189385332046727f + log_std);    // actor_ent
-        }
-    }
-}
-
 // Policy head (drqv2.py:81,88-92): mu_pre[m][:] = p2[m][:] . bf16(W4)^T + b4 for all M rows of a TB activation - the
 // Linear(hidden, A) as dot products on the CUDA cores (A <= 32 outputs: a tensor-core tile would be > 75 % padding and
-// run on M / 128 CTAs) - and, in the block that finishes last, the TruncatedNormal samples of up to
-// DRQ_POLICY_MAX_JOBS row ranges.  Block = 32 rows x 8 unit groups, as q_head_fwd_kernel.  The weights are rounded to
-// bf16 when they are staged, i.e. the arithmetic is that of the bf16 GEMM this replaces (bf16 x bf16 products, fp32 sums).
-struct PolicyJobs { drq_policy_sample j[DRQ_POLICY_MAX_JOBS]; int n; };
+// run on M / 128 CTAs) - and, by the thread that holds each mu_pre value, the TruncatedNormal samples of up to
+// DRQ_POLICY_MAX_JOBS row ranges (utils.py:112-126).  Block = 32 rows x 8 unit groups, as q_head_fwd_kernel.  The
+// weights are rounded to bf16 when they are staged, i.e. the arithmetic is that of the bf16 GEMM this replaces (bf16 x
+// bf16 products, fp32 sums).  A job with metrics needs the batch mean of the log-probabilities: every block leaves its
+// partial sum in scratch[1 + block], the block that finishes last (ticket in scratch[0]) adds them in block order.
+struct PolicyJobs { drq_policy_sample j[DRQ_POLICY_MAX_JOBS]; int n; int metrics_job; };
 
 __global__ void __launch_bounds__(256)
 policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, const float* __restrict__ w4,
                        const float* __restrict__ b4, float* __restrict__ mu_pre, int M, int H, int A, const PolicyJobs jobs,
-                       const float* __restrict__ std_dev, float clip, unsigned int* __restrict__ ticket) {
+                       const float* __restrict__ std_dev, float clip, unsigned int* __restrict__ scratch) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float w_s[];                       // [A][H]
@@ -289,6 +254,10 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
         const int u = grp + 8 * k;
         v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
     }
+    const float std = std_dev ? *std_dev : 0.f;
+    const float log_std = jobs.n ? logf(std) : 0.f;
+    const float lo = -1.0f + 1e-6f, hi = 1.0f - 1e-6f;  // utils.py:113 (python: -1.0 + 1e-6 -> fp32)
+    float lp_acc = 0.f;                                  // this thread's log-prob terms of the metrics job
     __syncthreads();
     for (int a0 = 0; a0 < A; a0 += 8) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -324,33 +293,56 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
 #pragma unroll
         for (int a = 0; a < 8; ++a) part[grp][lane][a] = acc[a];
         __syncthreads();
-        {   // 32 rows x 8 outputs: thread (row = tid / 8, a = tid % 8) sums the 8 unit groups in fixed order
-            const int r = threadIdx.x >> 3, a = threadIdx.x & 7, mr = blockIdx.x * 32 + r;
-            if (mr < M && a0 + a < A) {
+        {   // 32 rows x 8 outputs: thread (row = tid / 8, a = tid % 8) sums the 8 unit groups in fixed order, then samples
+            const int r = threadIdx.x >> 3, a = threadIdx.x & 7, mr = blockIdx.x * 32 + r, j = a0 + a;
+            if (mr < M && j < A) {
                 float t = 0.f;
 #pragma unroll
                 for (int g2 = 0; g2 < 8; ++g2) t += part[g2][r][a];
-                mu_pre[(long long)mr * A + a0 + a] = t + b4[a0 + a];
+                const float pre = t + b4[j];
+                mu_pre[(long long)mr * A + j] = pre;
+                for (int i = 0; i < jobs.n; ++i) {
+                    const drq_policy_sample& jb = jobs.j[i];
+                    const int b = mr - jb.row0;
+                    if (b < 0 || b >= jb.rows) continue;
+                    const float mu = tanhf(pre);                                   // drqv2.py:89
+                    float av = mu;
+                    if (jb.eps) {
+                        float e = __fmul_rn(jb.eps[(long long)b * A + j], std);    // utils.py:120
+                        if (clip > 0.f) e = fminf(fmaxf(e, -clip), clip);          // utils.py:121-122
+                        av = fminf(fmaxf(__fadd_rn(mu, e), lo), hi);               // utils.py:123, 113-116 (value)
+                        if (i == jobs.metrics_job) {
+                            const float d = av - mu;                                // Normal.log_prob(a)
+                            lp_acc += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
+                        }
+                    }
+                    jb.action_out[(long long)b * jb.ld_a + j] = av;
+                    if (jb.a_bf16) reinterpret_cast<__nv_bfloat16*>(jb.a_bf16)[fb_index(jb.feat_off + j, b, jb.units_a)] = __float2bfloat16_rn(av);
+                    if (jb.mu_out) jb.mu_out[(long long)b * A + j] = mu;
+                }
             }
         }
         __syncthreads();
     }
-    if (jobs.n == 0) return;
-    // the block that finishes last draws the samples (one block: the log-prob mean is a fixed-order sum)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (jobs.metrics_job < 0) return;
+    // batch mean of the log-probabilities: block partials, combined in block order by the block that finishes last
+    const float bsum = block_sum_256(lp_acc, sh);
+    if (threadIdx.x == 0) {
+        reinterpret_cast<float*>(scratch)[1 + blockIdx.x] = bsum;
+        __threadfence();
+        s_last = atomicAdd(scratch, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    const float std = std_dev ? *std_dev : 0.f;
-    for (int i = 0; i < jobs.n; ++i) {
-        const drq_policy_sample& jb = jobs.j[i];
-        sample_rows(mu_pre + (long long)jb.row0 * A, jb.eps, std, clip, jb.action_out, jb.ld_a, jb.mu_out, jb.metrics,
-                    reinterpret_cast<__nv_bfloat16*>(jb.a_bf16), jb.units_a, jb.feat_off, jb.rows, A, sh);
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        float tot = 0.f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(reinterpret_cast<const float*>(scratch) + 1 + b);
+        const drq_policy_sample& jb = jobs.j[jobs.metrics_job];
+        jb.metrics[0] = tot / (float)jb.rows;                                       // actor_logprob
+        jb.metrics[1] = (float)A * (0.5f + 0.9189385332046727f + log_std);          // actor_ent
+        *scratch = 0u;                                                              // ready for the next launch
     }
-    if (threadIdx.x == 0) *ticket = 0u;                  // ready for the next launch
 }
 
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ da, long long ld_da,
@@ -653,14 +645,19 @@ int drq_policy_head_fwd_bf16(const uint16_t* p2, int64_t units, const float* w4,
                              uint32_t* ticket, void* stream) {
     DRQ_REQUIRE(p2 && w4 && b4 && mu_pre, "policy_head_fwd: null pointer");
     DRQ_REQUIRE(M > 0 && H > 0 && H % 8 == 0 && units * 8 >= H && A > 0 && A <= 32, "policy_head_fwd: bad dims (A <= 32, H % 8 == 0)");
-    DRQ_REQUIRE(njobs >= 0 && njobs <= DRQ_POLICY_MAX_JOBS && (njobs == 0 || (jobs && ticket)), "policy_head_fwd: 0..%d sample jobs (with a ticket counter)", DRQ_POLICY_MAX_JOBS);
+    DRQ_REQUIRE(njobs >= 0 && njobs <= DRQ_POLICY_MAX_JOBS && (njobs == 0 || jobs), "policy_head_fwd: 0..%d sample jobs", DRQ_POLICY_MAX_JOBS);
     PolicyJobs pj{};
     pj.n = njobs;
+    pj.metrics_job = -1;
     for (int i = 0; i < njobs; ++i) {
         pj.j[i] = jobs[i];
         DRQ_REQUIRE(jobs[i].rows > 0 && jobs[i].row0 >= 0 && jobs[i].row0 + jobs[i].rows <= M && jobs[i].action_out,
                     "policy_head_fwd: bad sample job %d", i);
         DRQ_REQUIRE(!(jobs[i].eps && !std_dev), "policy_head_fwd: eps without std");
+        if (jobs[i].metrics) {
+            DRQ_REQUIRE(pj.metrics_job < 0 && jobs[i].eps && ticket, "policy_head_fwd: one job may carry metrics (it needs eps and the scratch words)");
+            pj.metrics_job = i;
+        }
     }
     const size_t smem = (size_t)A * H * sizeof(float);
     if (int rc = ensure_smem((const void*)policy_head_fwd_kernel, smem, "policy_head_fwd")) return rc;

@@ -423,16 +423,17 @@ int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev
                      uint16_t* action_bf16, int64_t rpad_ab, int feat_off, int B, int A, void* stream);
 
 /* Policy head of the tensor-core mode in one launch (drqv2.py:81,88-92 + utils.py:112-126): mu_pre[m][a] =
- * p2[m][:] . bf16(w4[a][:]) + b4[a] for the M rows of the TB activation p2 (units per row), then - in the block that
- * finishes last - drq_actor_sample on up to DRQ_POLICY_MAX_JOBS row ranges of mu_pre.  `ticket` is a zero-initialised
- * device counter the kernel resets.  Replaces a 128 x 64 tensor-core tile that was > 75 % padding (A <= 32 outputs)
- * followed by one or two sampling launches. */
+ * p2[m][:] . bf16(w4[a][:]) + b4[a] for the M rows of the TB activation p2 (units per row), and - by the thread that
+ * holds each value - drq_actor_sample's arithmetic on up to DRQ_POLICY_MAX_JOBS row ranges.  At most one job carries
+ * metrics (it needs eps); `scratch` then is 1 + ceil(M / 32) zero-initialised 32-bit words (block ticket + per-block
+ * log-prob sums) that the kernel leaves zeroed.  Replaces a 128 x 64 tensor-core tile that was > 75 % padding
+ * (A <= 32 outputs) followed by one or two sampling launches. */
 #define DRQ_POLICY_MAX_JOBS 2
 typedef struct { int32_t row0; int32_t rows; const float* eps; float* action_out; int64_t ld_a; float* mu_out;
                  float* metrics; uint16_t* a_bf16; int64_t units_a; int32_t feat_off; int32_t reserved; } drq_policy_sample;
 int drq_policy_head_fwd_bf16(const uint16_t* p2, int64_t units, const float* w4, const float* b4, float* mu_pre, int M,
                              int H, int A, const drq_policy_sample* jobs, int njobs, const float* std_dev, float clip,
-                             uint32_t* ticket, void* stream);
+                             uint32_t* scratch, void* stream);
 
 /* d(mu_pre) = d(action) * (1 - mu^2)   (straight-through clamp, utils.py:113-116) */
 int drq_actor_sample_bwd(const float* daction, int64_t ld_da, const float* mu, float* dmu_pre,

@@ -496,7 +496,7 @@ def test_policy_head_matches_linear_tanh_sample(dev, M, A, H):
     p2b.load(p2)
     mu_pre = torch.zeros(M, A, device=dev)
     std = torch.tensor([0.4], device=dev)
-    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    ticket = torch.zeros(1 + (M + 31) // 32, dtype=torch.int32, device=dev)     # block ticket + per-block log-prob sums
     n0 = M // 2
     rows = [(0, n0), (n0, M - n0)] if n0 else [(0, M)]
     eps = [torch.randn(r, A, generator=g).to(dev) for _, r in rows]
@@ -512,7 +512,7 @@ def test_policy_head_matches_linear_tanh_sample(dev, M, A, H):
         _lib.call("drq_policy_head_fwd_bf16", p2b.ptr(), p2b.units, w4.data_ptr(), b4.data_ptr(), mu_pre.data_ptr(), M, H, A,
                   arr, len(jobs), std.data_ptr(), 0.3, ticket.data_ptr(), _stream())
         torch.cuda.synchronize()
-        assert int(ticket) == 0
+        assert int(ticket[0]) == 0
     want_pre = _bf(p2).double() @ _bf(w4).double().T + b4.double()
     assert (mu_pre.double() - want_pre).abs().max().item() <= 2e-5 * max(1.0, want_pre.abs().max().item())
     for i, (r0, r) in enumerate(rows):
