@@ -45,6 +45,15 @@ struct ConvTcArgs {
 };
 
 static long long* g_conv_stamps = nullptr;
+
+// conv2x2_tc.cu: the 2x2-output-block formulation.  0 = off, 1 = for launches that fill the machine (default),
+// 2 = always (tests)
+int conv2x2_launch(bool dgrad, const __nv_bfloat16* in, long long cs_in, const __nv_bfloat16* w, const float* bias,
+                   const __nv_bfloat16* mask, long long cs_mask, __nv_bfloat16* out, long long cs_out, int N, int h_layer_out,
+                   int out_mode, long long feat_rpad, int feat_half, int feat_half_row, cudaStream_t stream);
+static int g_conv2x2 = 1;
+constexpr int kConv2x2MinImages = 48;      // ~148 tiles of 128 blocks: below that the one-pixel-per-row kernel's 18 KB set-up wins
+static bool use_conv2x2(int N) { return g_conv2x2 == 2 || (g_conv2x2 == 1 && N >= kConv2x2MinImages); }
 #ifdef DRQ_STAMPS
 #define CV_T() (a.stamps ? clock64() : 0ll)
 #define CV_STAMPS(x) x
@@ -419,6 +428,12 @@ extern "C" {
 
 int drq_debug_conv_stamps(int64_t* buf) { g_conv_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
 
+int drq_set_conv2x2(int mode) {
+    const int prev = g_conv2x2;
+    if (mode >= 0 && mode <= 2) g_conv2x2 = mode;
+    return prev;
+}
+
 int64_t drq_wb_elems(int n_images) { return 4ll * ((long long)n_images * kPLB + kSlack) * 8; }
 
 int drq_pack_conv_w_bf16(const float* w, uint16_t* w_fwd, uint16_t* w_dgrad, void* stream) {
@@ -450,6 +465,9 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
+    if (use_conv2x2(N))
+        return conv2x2_launch(false, a.in, a.cs_in, a.w, bias, nullptr, 0, a.out, a.cs_out, N, hout, nhwc_out, feat_rpad, a.feat_half,
+                              feat_half_row, as_stream(stream));
     launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<fwd>");
 }
@@ -474,6 +492,8 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.w_valid = hin;
     a.nhwc_out = 0;
     a.stamps = g_conv_stamps;
+    if (use_conv2x2(N))
+        return conv2x2_launch(true, a.in, a.cs_in, a.w, nullptr, a.mask, a.cs_mask, a.out, a.cs_out, N, hout, 0, 0, 0, 0, as_stream(stream));
     launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
 }

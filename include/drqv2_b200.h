@@ -83,6 +83,12 @@ int drq_set_sm_limit(int sms);
  * memory) so that their CTAs fit on an SM BESIDE two resident CTAs of the persistent conv kernels (148 KB) - set by the
  * host around the launches of the actor pass, which runs beside the encoder backward.  Read at launch time. */
 int drq_set_gemm_small(int on);
+/* which kernel drq_conv3x3_fwd_bf16 / drq_conv3x3_dgrad_bf16 launch: 0 = one output pixel per accumulator row (N = 32
+ * UMMAs, csrc/conv_tc.cu), 1 (default) = a 2x2 block of output pixels per row (N = 128 / 64 / 32 UMMAs over the 4x4
+ * input window, csrc/conv2x2_tc.cu) for launches of >= 48 images and the former below, 2 = the latter always.  Same
+ * arguments, layouts and results (to fp32 accumulation order).  Returns the previous mode; a value outside 0..2 only
+ * queries. */
+int drq_set_conv2x2(int mode);
 
 /* ------------------------------------------------------------------ replay */
 

@@ -33,8 +33,18 @@ def _pack_w(w, dev):
     return wf, wd
 
 
+@pytest.fixture(params=[0, 2], ids=["pixel_rows", "block_rows"])
+def conv_mode(request):
+    """both conv3x3 forward / data-gradient kernels at every size: 0 = one pixel per accumulator row (conv_tc.cu),
+    2 = a 2x2 block of pixels per row (conv2x2_tc.cu; the default mode 1 picks it from 48 images up)"""
+    from drqv2_b200 import _lib
+    prev = _lib.lib().drq_set_conv2x2(request.param)
+    yield request.param
+    _lib.lib().drq_set_conv2x2(prev)
+
+
 @pytest.mark.parametrize("hout,N", [(39, 3), (37, 5), (35, 2)])
-def test_conv3x3_fwd_bf16(dev, hout, N):
+def test_conv3x3_fwd_bf16(dev, hout, N, conv_mode):
     from drqv2_b200 import _lib
     g = torch.Generator().manual_seed(hout)
     hin = hout + 2
@@ -70,7 +80,7 @@ def test_conv3x3_fwd_bf16(dev, hout, N):
 
 
 @pytest.mark.parametrize("hout,N", [(39, 2), (35, 3)])
-def test_conv3x3_dgrad_bf16(dev, hout, N):
+def test_conv3x3_dgrad_bf16(dev, hout, N, conv_mode):
     from drqv2_b200 import _lib
     g = torch.Generator().manual_seed(100 + hout)
     hin = hout + 2
