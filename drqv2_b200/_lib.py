@@ -49,10 +49,11 @@ SIGNATURES = {
     "drq_set_pdl": [I],
     "drq_set_sm_limit": [I],
     "drq_set_gemm_small": [I],
-    "drq_set_conv2x2": [I],
+    "drq_set_conv4x1": [I],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],
+    "drq_debug_conv4x1_stamps": [P],
     "drq_debug_conv1_stamps": [P],
     "drq_pack_multi": [P, I, P],
     "drq_conv_wgrad_reduce_multi": [P, I, P],
@@ -127,8 +128,8 @@ def lib():
         h.drq_set_pdl(0 if os.environ.get("DRQV2_B200_PDL", "0") == "0" else 1)
         if os.environ.get("DRQV2_B200_OPT_MINB"):       # tuning: register target of the fused optimiser kernel
             h.drq_debug_opt_min_blocks(int(os.environ["DRQV2_B200_OPT_MINB"]))
-        if os.environ.get("DRQV2_B200_CONV2X2"):        # A/B: 0 = one-pixel-per-row conv kernels, 1 = default, 2 = 2x2-block kernels always
-            h.drq_set_conv2x2(int(os.environ["DRQV2_B200_CONV2X2"]))
+        if os.environ.get("DRQV2_B200_CONV4X1"):        # A/B: 0 = one-pixel-per-row conv kernels, 1 = default, 2 = four-pixel-column kernels always
+            h.drq_set_conv4x1(int(os.environ["DRQV2_B200_CONV4X1"]))
         _lib = h
     return _lib
 

@@ -46,14 +46,14 @@ struct ConvTcArgs {
 
 static long long* g_conv_stamps = nullptr;
 
-// conv2x2_tc.cu: the 2x2-output-block formulation.  0 = off, 1 = for launches that fill the machine (default),
-// 2 = always (tests)
-int conv2x2_launch(bool dgrad, const __nv_bfloat16* in, long long cs_in, const __nv_bfloat16* w, const float* bias,
+// conv4x1_tc.cu: four output pixels (a column) per accumulator row.  0 = off, 1 = for launches that fill the machine
+// (default), 2 = always (tests)
+int conv4x1_launch(bool dgrad, const __nv_bfloat16* in, long long cs_in, const __nv_bfloat16* w, const float* bias,
                    const __nv_bfloat16* mask, long long cs_mask, __nv_bfloat16* out, long long cs_out, int N, int h_layer_out,
                    int out_mode, long long feat_rpad, int feat_half, int feat_half_row, cudaStream_t stream);
-static int g_conv2x2 = 1;
-constexpr int kConv2x2MinImages = 48;      // ~148 tiles of 128 blocks: below that the one-pixel-per-row kernel's 18 KB set-up wins
-static bool use_conv2x2(int N) { return g_conv2x2 == 2 || (g_conv2x2 == 1 && N >= kConv2x2MinImages); }
+static int g_conv4x1 = 1;
+constexpr int kConv4x1MinImages = 48;      // ~148 tiles: below that the one-pixel-per-row kernel's 18 KB set-up wins
+static bool use_conv4x1(int N) { return g_conv4x1 == 2 || (g_conv4x1 == 1 && N >= kConv4x1MinImages); }
 #ifdef DRQ_STAMPS
 #define CV_T() (a.stamps ? clock64() : 0ll)
 #define CV_STAMPS(x) x
@@ -428,9 +428,9 @@ extern "C" {
 
 int drq_debug_conv_stamps(int64_t* buf) { g_conv_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
 
-int drq_set_conv2x2(int mode) {
-    const int prev = g_conv2x2;
-    if (mode >= 0 && mode <= 2) g_conv2x2 = mode;
+int drq_set_conv4x1(int mode) {
+    const int prev = g_conv4x1;
+    if (mode >= 0 && mode <= 2) g_conv4x1 = mode;
     return prev;
 }
 
@@ -465,8 +465,8 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
-    if (use_conv2x2(N))
-        return conv2x2_launch(false, a.in, a.cs_in, a.w, bias, nullptr, 0, a.out, a.cs_out, N, hout, nhwc_out, feat_rpad, a.feat_half,
+    if (use_conv4x1(N))
+        return conv4x1_launch(false, a.in, a.cs_in, a.w, bias, nullptr, 0, a.out, a.cs_out, N, hout, nhwc_out, feat_rpad, a.feat_half,
                               feat_half_row, as_stream(stream));
     launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<fwd>");
@@ -492,8 +492,8 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.w_valid = hin;
     a.nhwc_out = 0;
     a.stamps = g_conv_stamps;
-    if (use_conv2x2(N))
-        return conv2x2_launch(true, a.in, a.cs_in, a.w, nullptr, a.mask, a.cs_mask, a.out, a.cs_out, N, hout, 0, 0, 0, 0, as_stream(stream));
+    if (use_conv4x1(N))
+        return conv4x1_launch(true, a.in, a.cs_in, a.w, nullptr, a.mask, a.cs_mask, a.out, a.cs_out, N, hout, 0, 0, 0, 0, as_stream(stream));
     launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<dgrad>");
 }

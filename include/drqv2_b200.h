@@ -84,11 +84,11 @@ int drq_set_sm_limit(int sms);
  * host around the launches of the actor pass, which runs beside the encoder backward.  Read at launch time. */
 int drq_set_gemm_small(int on);
 /* which kernel drq_conv3x3_fwd_bf16 / drq_conv3x3_dgrad_bf16 launch: 0 = one output pixel per accumulator row (N = 32
- * UMMAs, csrc/conv_tc.cu), 1 (default) = a 2x2 block of output pixels per row (N = 128 / 64 / 32 UMMAs over the 4x4
- * input window, csrc/conv2x2_tc.cu) for launches of >= 48 images and the former below, 2 = the latter always.  Same
- * arguments, layouts and results (to fp32 accumulation order).  Returns the previous mode; a value outside 0..2 only
- * queries. */
-int drq_set_conv2x2(int mode);
+ * UMMAs, csrc/conv_tc.cu), 1 (default) = a column of four output pixels per row (N = 32 / 64 / 96 UMMAs over the 6x3
+ * input window, tensor-map TMA loads; csrc/conv4x1_tc.cu) for launches of >= 48 images and the former below, 2 = the
+ * latter always.  Same arguments, layouts and results (to fp32 accumulation order).  Returns the previous mode; a value
+ * outside 0..2 only queries. */
+int drq_set_conv4x1(int mode);
 
 /* ------------------------------------------------------------------ replay */
 
@@ -321,6 +321,10 @@ int drq_debug_gemm_stamps(int64_t* buf);
 /* the same for drq_conv3x3_{fwd,dgrad}_bf16: [0] producer wait-for-empty, [1] producer total, [2] issuer
  * wait-for-accumulator, [3] issuer wait-for-data, [4] issuer total, [5] epilogue wait-for-accumulator (cycles). */
 int drq_debug_conv_stamps(int64_t* buf);
+/* 12 clock64 totals of block 0 of the four-pixel-column conv kernels (device buffer, or null = off): producer {wait
+ * stage, -, -, total}, UMMA warp {wait accumulator, wait stage, issue, total}, first epilogue warp {wait accumulator,
+ * TMEM load, math + stores, total} */
+int drq_debug_conv4x1_stamps(int64_t* buf);
 /* drq_conv1_fwd_bf16 builders (threads 0 / 128 of block 0 at [0..4] / [8..12]): wait-for-rows, re-pitch,
  * barrier, wait-for-free-tile, build (cycles). */
 int drq_debug_conv1_stamps(int64_t* buf);

@@ -33,14 +33,14 @@ def _pack_w(w, dev):
     return wf, wd
 
 
-@pytest.fixture(params=[0, 2], ids=["pixel_rows", "block_rows"])
+@pytest.fixture(params=[0, 2], ids=["pixel_rows", "column_rows"])
 def conv_mode(request):
     """both conv3x3 forward / data-gradient kernels at every size: 0 = one pixel per accumulator row (conv_tc.cu),
-    2 = a 2x2 block of pixels per row (conv2x2_tc.cu; the default mode 1 picks it from 48 images up)"""
+    2 = a column of four pixels per row (conv4x1_tc.cu; the default mode 1 picks it from 48 images up)"""
     from drqv2_b200 import _lib
-    prev = _lib.lib().drq_set_conv2x2(request.param)
+    prev = _lib.lib().drq_set_conv4x1(request.param)
     yield request.param
-    _lib.lib().drq_set_conv2x2(prev)
+    _lib.lib().drq_set_conv4x1(prev)
 
 
 @pytest.mark.parametrize("hout,N", [(39, 3), (37, 5), (35, 2)])

@@ -1,4 +1,4 @@
-"""conv3x3 forward (N=512) / data gradient (N=256): the one-pixel-per-row kernel against the 2x2-block kernel.
+"""conv3x3 forward (N=512) / data gradient (N=256): the one-pixel-per-row kernel against the four-pixel-column kernel.
 CUDA events around single launches, a 256 MB buffer written in front of each (cold L2), and 10 back-to-back (warm);
 max |difference| of the outputs."""
 import os, sys
@@ -30,7 +30,7 @@ from drqv2_b200._bf16 import TB
 for hout in (39, 37, 35):
     outs = {}
     for mode in (0, 2):
-        L.drq_set_conv2x2(mode)
+        L.drq_set_conv4x1(mode)
         a2 = torch.zeros(L.drq_wb_elems(2 * Bt), dtype=torch.bfloat16, device=dev)
         d2 = torch.zeros(L.drq_wb_elems(Bt), dtype=torch.bfloat16, device=dev)
         f = lambda: _lib.call("drq_conv3x3_fwd_bf16", a1.data_ptr(), wf.data_ptr(), b1.data_ptr(), a2.data_ptr(), 2 * Bt, hout, 0, 0, 0, 0, s)
@@ -47,4 +47,17 @@ for hout in (39, 37, 35):
         outs[mode] = (nchw_from_wb(a2.view(4, -1, 8), 2 * Bt, hout, hout), nchw_from_wb(d2.view(4, -1, 8), Bt, hout + 2, hout + 2))
     print(f"   max |fwd diff| {(outs[0][0] - outs[2][0]).abs().max().item():.3e} of {outs[0][0].abs().max().item():.3e}; "
           f"max |dgrad diff| {(outs[0][1] - outs[2][1]).abs().max().item():.3e} of {outs[0][1].abs().max().item():.3e}", flush=True)
-L.drq_set_conv2x2(1)
+L.drq_set_conv4x1(2)
+st = torch.zeros(16, dtype=torch.int64, device=dev)
+L.drq_debug_conv4x1_stamps(st.data_ptr())
+a2 = torch.zeros(L.drq_wb_elems(2 * Bt), dtype=torch.bfloat16, device=dev)
+d2 = torch.zeros(L.drq_wb_elems(Bt), dtype=torch.bfloat16, device=dev)
+for nm, fn in (("fwd", lambda: _lib.call("drq_conv3x3_fwd_bf16", a1.data_ptr(), wf.data_ptr(), b1.data_ptr(), a2.data_ptr(), 2 * Bt, 39, 0, 0, 0, 0, s)),
+               ("dgrad", lambda: _lib.call("drq_conv3x3_dgrad_bf16", d1.data_ptr(), wf.data_ptr(), a1.data_ptr(), 2 * Bt, d2.data_ptr(), Bt, 39, s))):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    v = st.tolist()
+    print(f"{nm} block 0 clock64 totals: producer wait-stage {v[0]} total {v[3]} | umma wait-acc {v[4]} wait-stage {v[5]} issue {v[6]} total {v[7]} | "
+          f"epilogue wait-acc {v[8]} ld {v[9]} rest {v[10]} total {v[11]}")
+L.drq_debug_conv4x1_stamps(None)
+L.drq_set_conv4x1(1)
