@@ -46,14 +46,23 @@ struct ConvTcArgs {
 
 static long long* g_conv_stamps = nullptr;
 
-// conv4x1_tc.cu: four output pixels (a column) per accumulator row.  0 = off, 1 = for launches that fill the machine
-// (default), 2 = always (tests)
+// conv4x1_tc.cu: four output pixels (a column) per accumulator row.  0 = off, 1 = for launches that fill the machine,
+// 2 = always (tests), 3 (default) = as 1 for the forward only, 4 = as 1 for the data gradient only.  Measured on the
+// B = 256 update (gpurun_out/ab_conv4x1_*): alone the new kernels are faster (graph nodes, warm: forward 27.6 vs 28.9 us,
+// data gradient 16.7 vs 20.1 us; one-stream update 1719 vs 1672 updates/s), but in the three-stream schedule the data
+// gradient runs on the encoder stream beside the critic's optimiser step and the actor pass, and its one 200 KB /
+// 54 K-register CTA per SM leaves no room for their blocks (the old kernel's two 74 KB CTAs do): 1798 updates/s with it,
+// 1858 without, 1868 with the forward alone.
 int conv4x1_launch(bool dgrad, const __nv_bfloat16* in, long long cs_in, const __nv_bfloat16* w, const float* bias,
                    const __nv_bfloat16* mask, long long cs_mask, __nv_bfloat16* out, long long cs_out, int N, int h_layer_out,
                    int out_mode, long long feat_rpad, int feat_half, int feat_half_row, cudaStream_t stream);
-static int g_conv4x1 = 1;
+static int g_conv4x1 = 3;
 constexpr int kConv4x1MinImages = 48;      // ~148 tiles: below that the one-pixel-per-row kernel's 18 KB set-up wins
-static bool use_conv4x1(int N) { return g_conv4x1 == 2 || (g_conv4x1 == 1 && N >= kConv4x1MinImages); }
+static bool use_conv4x1(int N, bool dgrad) {
+    if (g_conv4x1 == 3 && dgrad) return false;      // 3 / 4: forward only / data gradient only (A/B measurements)
+    if (g_conv4x1 == 4 && !dgrad) return false;
+    return g_conv4x1 == 2 || (g_conv4x1 >= 1 && N >= kConv4x1MinImages);
+}
 #ifdef DRQ_STAMPS
 #define CV_T() (a.stamps ? clock64() : 0ll)
 #define CV_STAMPS(x) x
@@ -430,7 +439,7 @@ int drq_debug_conv_stamps(int64_t* buf) { g_conv_stamps = reinterpret_cast<long 
 
 int drq_set_conv4x1(int mode) {
     const int prev = g_conv4x1;
-    if (mode >= 0 && mode <= 2) g_conv4x1 = mode;
+    if (mode >= 0 && mode <= 4) g_conv4x1 = mode;
     return prev;
 }
 
@@ -465,7 +474,7 @@ int drq_conv3x3_fwd_bf16(const uint16_t* in, const uint16_t* w_fwd, const float*
     a.feat_half = feat_half > 0 ? feat_half : N;
     a.feat_half_row = feat_half_row;
     DRQ_REQUIRE(nhwc_out != 2 || feat_rpad == (int64_t)hout * hout * 4, "conv3x3_fwd_bf16: TB feature units must be hout*hout*4");
-    if (use_conv4x1(N))
+    if (use_conv4x1(N, false))
         return conv4x1_launch(false, a.in, a.cs_in, a.w, bias, nullptr, 0, a.out, a.cs_out, N, hout, nhwc_out, feat_rpad, a.feat_half,
                               feat_half_row, as_stream(stream));
     launch_k(conv3x3_tc_kernel<false>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
@@ -492,7 +501,7 @@ int drq_conv3x3_dgrad_bf16(const uint16_t* dout, const uint16_t* w_dgrad, const 
     a.w_valid = hin;
     a.nhwc_out = 0;
     a.stamps = g_conv_stamps;
-    if (use_conv4x1(N))
+    if (use_conv4x1(N, true))
         return conv4x1_launch(true, a.in, a.cs_in, a.w, nullptr, a.mask, a.cs_mask, a.out, a.cs_out, N, hout, 0, 0, 0, 0, as_stream(stream));
     launch_k(conv3x3_tc_kernel<true>, conv_tc_grid(N * a.ntiles, 2), kThreadsTC, kConvTcSmem, as_stream(stream), a);
     return check_launch("conv3x3_tc_kernel<dgrad>");

@@ -84,10 +84,11 @@ int drq_set_sm_limit(int sms);
  * host around the launches of the actor pass, which runs beside the encoder backward.  Read at launch time. */
 int drq_set_gemm_small(int on);
 /* which kernel drq_conv3x3_fwd_bf16 / drq_conv3x3_dgrad_bf16 launch: 0 = one output pixel per accumulator row (N = 32
- * UMMAs, csrc/conv_tc.cu), 1 (default) = a column of four output pixels per row (N = 32 / 64 / 96 UMMAs over the 6x3
- * input window, tensor-map TMA loads; csrc/conv4x1_tc.cu) for launches of >= 48 images and the former below, 2 = the
- * latter always.  Same arguments, layouts and results (to fp32 accumulation order).  Returns the previous mode; a value
- * outside 0..2 only queries. */
+ * UMMAs, csrc/conv_tc.cu); 1 = a column of four output pixels per row (N = 32 / 64 / 96 UMMAs over the 6x3 input window,
+ * tensor-map TMA loads; csrc/conv4x1_tc.cu) for launches of >= 48 images and the former below; 2 = the latter always;
+ * 3 (default) = as 1 for the forward, the former for the data gradient (which runs beside other streams' kernels and
+ * must leave them room on the SM); 4 = as 1 for the data gradient only.  Same arguments, layouts and results (to fp32
+ * accumulation order).  Returns the previous mode; a value outside 0..4 only queries. */
 int drq_set_conv4x1(int mode);
 
 /* ------------------------------------------------------------------ replay */
