@@ -50,6 +50,7 @@ SIGNATURES = {
     "drq_set_sm_limit": [I],
     "drq_set_gemm_small": [I],
     "drq_set_conv4x1": [I],
+    "drq_set_conv1_planes": [I],
     "drq_debug_gemm_stamps": [P],
     "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],
@@ -130,6 +131,8 @@ def lib():
             h.drq_debug_opt_min_blocks(int(os.environ["DRQV2_B200_OPT_MINB"]))
         if os.environ.get("DRQV2_B200_CONV4X1"):        # A/B: 0 = one-pixel-per-row conv kernels, 1 = default, 2 = four-pixel-column kernels always
             h.drq_set_conv4x1(int(os.environ["DRQV2_B200_CONV4X1"]))
+        if os.environ.get("DRQV2_B200_CONV1_PLANES"):   # A/B: 0 = im2col conv1 forward, 1 = parity-plane forward (default)
+            h.drq_set_conv1_planes(int(os.environ["DRQV2_B200_CONV1_PLANES"]))
         _lib = h
     return _lib
 

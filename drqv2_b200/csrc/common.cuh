@@ -19,6 +19,10 @@ int ensure_smem(const void* kernel, size_t bytes, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda), or null; cast to the driver's signature by
+// the callers that include <cuda.h> (conv4x1_tc.cu, conv1_tc.cu)
+void* tensor_map_encoder();
+
 // Programmatic dependent launch (drq_set_pdl): every kernel waits for its predecessors (griddepcontrol.wait =
 // all prior grids complete and flushed) before it touches global memory, so its launch latency, barrier / TMEM
 // set-up and first instruction fetches may overlap the tail of the running kernel.  The long tensor-core

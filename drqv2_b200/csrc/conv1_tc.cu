@@ -25,6 +25,9 @@
 // Warp roles (704 threads): warps 0..15 re-pitch the rows + build im2col tiles (4 threads per output
 // position), warp 16 issues UMMAs (and bulk-loads the gradient tile in wgrad), warps 17..20 run the
 // epilogue, warp 21 bulk-copies the source rows of the next tiles (4 stages ahead).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "pack.cuh"
 #include "wgrad_reduce.cuh"
 
@@ -435,6 +438,327 @@ conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin, flo
     conv1_reduce_block(partial, G, cin, dw, db, blockIdx.x, red, redb);
 }
 
+// ---------------------------------------------------------------- forward, second formulation: parity planes
+// The im2col tile above costs 96 built entries per output position (9 taps x 9 channels, padded), and building them is
+// what the kernel spends its time on.  The stride-2 conv is a stride-1 conv over the four row/column parity planes of
+// the augmented image V (plane (py, px)[i][j] = V[2i+py][2j+px]): tap (ky, kx) of output (y, x) is plane (ky&1, kx&1)
+// at [y + ky/2][x + kx/2].  So the builders convert every pixel of the tile's 7 V rows ONCE, pixel-major - K unit 0 =
+// channels 0..7, K unit 1 = channels 8.. (zero padded) - into [K unit][py][px][4 plane rows][42 columns][16 B], and tap
+// (ky, kx) of 126 consecutive (row, column) positions is the K-major operand at the constant offset
+// (ky/2)*42 + kx/2 of its plane: 9 UMMAs of M128 N32 K16 per tile of 3 output rows, 10 converted values per input
+// pixel instead of 96 per output pixel.  A builder thread owns one plane column of one V row (two pixels): consecutive
+// lanes write consecutive 16-byte slots (no bank conflicts) and read the bulk-copied source rows directly - the shift
+// and the replicate padding are a clamped byte address and a byte selector, there is no re-pitch pass.  Same
+// exact-integer entries, same epilogue (scale 1/255, fused bias), same results up to fp32 summation order.
+#ifndef P1_HINT
+#define P1_HINT 1000000u        // suspend-time hint of the kernel's mbarrier waits (measured: no effect between 0 and 1 ms)
+#endif
+constexpr int kP1Pitch = 42;                      // plane columns j = 0..41 (V columns 2j + px)
+constexpr int kP1Rows = 3;                        // output rows per tile
+constexpr int kP1TilesPerImg = (kPW + kP1Rows - 1) / kP1Rows;     // 14
+constexpr int kP1Live = kP1Rows * kP1Pitch;       // 126 accumulator rows carry positions (column 41 is a dummy)
+constexpr int kP1Region = 4 * kP1Pitch * 16;      // one (K unit, py, px): 4 plane rows
+constexpr int kP1StageBytes = 8 * kP1Region;      // 21,504
+constexpr int kP1Stages = 6;
+constexpr int kP1VRows = 2 * kP1Rows + 1;         // V rows per tile
+constexpr int kP1WBytes = 9 * 2 * 32 * 16;        // [tap][2 K units][32 co][16 B]
+constexpr int kP1Units = kP1VRows * (kImg / 4);   // builder work units: (V row, 4 columns) = 147
+constexpr int kP1Group = 160;                     // builder threads per group
+constexpr int kP1Groups = 3;                      // groups take tiles round robin
+constexpr int kP1Acc = 8;                         // accumulator ring: 8 x 32 TMEM columns
+constexpr int kP1Threads = kP1Groups * kP1Group + 10 * 32; // + UMMA warp, 8 epilogue warps (two per TMEM lane quarter), row producer warp
+constexpr int kP1RawSlot = 640;                   // raw rows of one channel: 7 * 84 bytes + the word a funnel shift may touch, 128-byte granular
+constexpr int kP1BoxWords = kP1RawSlot / 4;       // TMA box: 160 words of a channel plane from the tile's first source row
+constexpr int kP1RawBytes = 10 * kP1RawSlot;
+constexpr int kP1RawStages = 8;
+
+struct P1Geom { int n, y0, rlo, nrows; };
+__device__ __forceinline__ P1Geom p1_geom(int t, int sy, int pad) {
+    P1Geom g;
+    g.n = t / kP1TilesPerImg;
+    g.y0 = (t - g.n * kP1TilesPerImg) * kP1Rows;
+    g.rlo = clampi(2 * g.y0 + sy - pad, 0, kImg - 1);
+    const int rhi = clampi(2 * g.y0 + kP1VRows - 1 + sy - pad, 0, kImg - 1);
+    g.nrows = rhi - g.rlo + 1;
+    return g;
+}
+
+// fp16 pairs (x_A - 128, x_B - 128) of two pixels at once: `ab` = [A px0, B px0, A px1, B px1] bytes (one PRMT from the
+// two channel words); 0x6400 | x is the fp16 1024 + x, one packed subtract centres both halves exactly.  (The im2col
+// kernel feeds bf16 because its weight-gradient twin multiplies the same tile with a bf16 gradient and kind::f16 wants
+// one format for both operands; the forward alone is free to use fp16 pixels x fp16 copies of the bf16-rounded weights,
+// which is 1.25 instructions per entry instead of 2.5.)
+__device__ __forceinline__ uint32_t centred_h2(uint32_t ab, uint32_t sel) {
+    const uint32_t h = __byte_perm(ab, 0x64646464u, sel);
+    const __half2 c = __hsub2(*reinterpret_cast<const __half2*>(&h), __half2half2(__ushort_as_half((unsigned short)0x6480)));   // 1024 + 128
+    return *reinterpret_cast<const uint32_t*>(&c);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// `map`: the source as (1764 words of a channel plane) x (channel planes): the gathered stacks [N * cin planes], or the
+// ring's frames [capacity * frame_c planes]; box = (kP1BoxWords, cin) resp. (kP1BoxWords, frame_c)
+template <int CIN>                                // compile-time channel count, 0 = use a.cin (<= 10)
+__global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __grid_constant__ CUtensorMap map, Conv1TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w_s = smem;                                    // [tap][2][32][16 B]
+    float* bias_s = reinterpret_cast<float*>(smem + kP1WBytes);
+    uint8_t* raw_s = smem + kP1WBytes + 128;                // kP1RawStages x raw rows (bulk-copy destinations)
+    uint8_t* st_s = raw_s + kP1RawStages * kP1RawBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + kP1Stages * kP1StageBytes + 128);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kP1Stages;
+    uint64_t* tfull = bars + 2 * kP1Stages;
+    uint64_t* tempty = bars + 2 * kP1Stages + kP1Acc;
+    uint64_t* rfull = bars + 2 * kP1Stages + 2 * kP1Acc;
+    uint64_t* rempty = rfull + kP1RawStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + kP1RawStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kBuildWarps = kP1Groups * kP1Group / 32;  // warps 0..14 build, 15 issues UMMAs, 16..23 epilogue, 24 copies rows
+    const int cin = CIN ? CIN : a.cin;
+    const int total_tiles = a.n_images * kP1TilesPerImg;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kP1Stages; ++i) { mbar_init(full + i, kP1Group); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kP1Acc; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        for (int i = 0; i < kP1RawStages; ++i) { mbar_init(rfull + i, a.ring_frames ? a.ring_stack : 1); mbar_init(rempty + i, kP1Group); }
+        fence_barrier_init();
+    }
+    if (warp == kBuildWarps) {
+        tmem_alloc(tmem_slot, kP1Acc * 32);
+        tmem_relinquish();
+    }
+    // plane stages start as zeros: the never written fourth row of the odd-row planes must read as finite values
+    for (int i = threadIdx.x; i < kP1Stages * kP1StageBytes / 16; i += kP1Threads) reinterpret_cast<uint4*>(st_s)[i] = make_uint4(0, 0, 0, 0);
+    pdl_wait();                 // CTA-local set-up above overlaps the previous kernel's tail
+    {
+        // B operands from the packed im2col weights [k / 8][co][k % 8], k = 9 * c + tap: [tap][c / 8][co][c % 8].  The packed
+        // block is staged in the (not yet used) raw-row buffer with 16-byte loads and re-ordered from there: 2-byte gathers
+        // straight from global memory were a chain of L2 round trips per thread.
+        const uint4* src = reinterpret_cast<const uint4*>(a.w);
+        uint4* tmp = reinterpret_cast<uint4*>(raw_s);
+        for (int i = threadIdx.x; i < (kC1WBytes + 128) / 16; i += kP1Threads) tmp[i] = __ldg(src + i);
+        __syncthreads();
+        // (fp16 copies of the bf16 weights: exact but for magnitudes below 2^-14, which lose bits to fp16 subnormals)
+        const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(raw_s);
+        __half* dst = reinterpret_cast<__half*>(w_s);
+        for (int i = threadIdx.x; i < 9 * 2 * 32 * 8; i += kP1Threads) {
+            const int e = i & 7, co = (i >> 3) & 31, u = (i >> 8) & 1, tap = i >> 9;
+            const int c = u * 8 + e, k = 9 * c + tap;
+            dst[i] = __float2half_rn(c < cin ? __bfloat162float(wp[((k >> 3) * 32 + co) * 8 + (k & 7)]) : 0.f);
+        }
+        if (threadIdx.x < 32) bias_s[threadIdx.x] = reinterpret_cast<const float*>(wp + kC1Units * 32 * 8)[threadIdx.x];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();            // also: the staged weights are read before the row producer overwrites the raw buffer
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kBuildWarps) {
+        // ------------------------------------------------ plane builders; three groups of 5 warps take tiles round robin
+        const int group = threadIdx.x / kP1Group, gb = threadIdx.x - group * kP1Group;
+        const int k = gb / (kImg / 4), g = gb - k * (kImg / 4);          // work unit: V row k of the tile, V columns 4g..4g+3
+        const bool worker = gb < kP1Units;
+        long long s_raw = 0, s_empty = 0, s_build = 0, s_fence = 0;
+        const long long s_begin = clock64();
+        // the shifts of a tile's image are fetched one tile ahead: a dependent global load per tile was most of the loop
+        int2 sh_next = make_int2(a.pad, a.pad);
+        {
+            const int t0 = blockIdx.x + group * (int)gridDim.x;
+            if (a.shift && t0 < total_tiles) sh_next = *reinterpret_cast<const int2*>(a.shift + 2 * (t0 / kP1TilesPerImg));
+        }
+        for (int ord = group; blockIdx.x + ord * (int)gridDim.x < total_tiles; ord += kP1Groups) {
+            const long long c0 = clock64();
+            const int t = blockIdx.x + ord * gridDim.x;
+            const int stage = ord % kP1Stages; const uint32_t phase = (ord / kP1Stages) & 1;
+            const int rs = ord % kP1RawStages; const uint32_t rphase = (ord / kP1RawStages) & 1;
+            const int sx = sh_next.x, sy = sh_next.y;
+            {
+                const int tn = t + kP1Groups * (int)gridDim.x;
+                if (a.shift && tn < total_tiles) sh_next = *reinterpret_cast<const int2*>(a.shift + 2 * (tn / kP1TilesPerImg));
+            }
+            const P1Geom cur = p1_geom(t, sy, a.pad);
+            mbar_wait<P1_HINT>(rfull + rs, rphase);
+            const long long c1 = clock64();
+            mbar_wait<P1_HINT>(empty + stage, phase ^ 1);
+            const long long c2 = clock64();
+            if (worker) {
+                // V row 2*y0 + k = source row clamp(. + sy - pad) (a V row past the image only feeds output rows past it);
+                // V columns 4g + i = source columns s_i = clamp(. + sx - pad): the bytes s_0 + b_i of the row, b_i = s_i - s_0
+                // (consecutive, or repeated at an edge).  (Two plane columns 21 apart per thread instead - consecutive lanes on
+                // consecutive 16-byte slots, no two-pass stores - measured slower: twice the loads.)
+                const int sr = clampi(min(2 * cur.y0 + k, kImg - 1) + sy - a.pad, 0, kImg - 1) - cur.rlo;
+                const int x0 = 4 * g + sx - a.pad;
+                const int s0 = clampi(x0, 0, kImg - 1);
+                const uint32_t b1 = (uint32_t)(clampi(x0 + 1, 0, kImg - 1) - s0), b2 = (uint32_t)(clampi(x0 + 2, 0, kImg - 1) - s0),
+                               b3 = (uint32_t)(clampi(x0 + 3, 0, kImg - 1) - s0);
+                const int ab = ((cur.rlo * kImg) & 15) + sr * kImg + s0;
+                const int sh = (ab & 3) * 8;
+                // pixel pairs (0, 2) -> plane column 2g and (1, 3) -> 2g + 1 of the even / odd column planes:
+                // [A b_i, B b_i, A b_j, B b_j] from the two channel words A, B
+                const uint32_t sel02 = 0u | (4u << 4) | (b2 << 8) | ((4u + b2) << 12);
+                const uint32_t sel13 = b1 | ((4u + b1) << 4) | (b3 << 8) | ((4u + b3) << 12);
+                const uint8_t* base = raw_s + rs * kP1RawBytes + (ab & ~3);
+                uint32_t v[10];
+#pragma unroll
+                for (int c = 0; c < 10; ++c) {
+                    v[c] = 0x80808080u;                                   // pixel 128 = entry 0 (its weights are zero anyway)
+                    if (c < cin) {
+                        const uint32_t* p = reinterpret_cast<const uint32_t*>(base + c * kP1RawSlot);
+                        v[c] = __funnelshift_r(p[0], p[1], sh);
+                    }
+                }
+                // h[px][pair][q]: channel pair q of the pixel at plane column 2g + pair of column plane px
+                uint32_t h[2][2][5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const uint32_t e = __byte_perm(v[2 * q], v[2 * q + 1], sel02), o = __byte_perm(v[2 * q], v[2 * q + 1], sel13);
+                    h[0][0][q] = centred_h2(e, 0x4140u); h[0][1][q] = centred_h2(e, 0x4342u);
+                    h[1][0][q] = centred_h2(o, 0x4140u); h[1][1][q] = centred_h2(o, 0x4342u);
+                }
+                uint8_t* dst = st_s + stage * kP1StageBytes + (k & 1) * (2 * kP1Region) + ((k >> 1) * kP1Pitch + 2 * g) * 16;
+#pragma unroll
+                for (int px = 0; px < 2; ++px)
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        uint8_t* d = dst + px * kP1Region + pr * 16;
+                        *reinterpret_cast<uint4*>(d) = make_uint4(h[px][pr][0], h[px][pr][1], h[px][pr][2], h[px][pr][3]);
+                        *reinterpret_cast<uint4*>(d + 4 * kP1Region) = make_uint4(h[px][pr][4], 0, 0, 0);
+                    }
+            }
+            mbar_arrive(rempty + rs);
+            const long long c3 = clock64();
+            fence_proxy_async();
+            mbar_arrive(full + stage);
+            const long long c4 = clock64();
+            s_raw += c1 - c0; s_empty += c2 - c1; s_build += c3 - c2; s_fence += c4 - c3;
+        }
+        if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.stamps[0] = s_raw; a.stamps[1] = 0; a.stamps[2] = s_empty; a.stamps[3] = s_build; a.stamps[4] = s_fence;
+            a.stamps[5] = clock64() - s_begin;
+        }
+    } else if (warp == kBuildWarps) {
+        // ------------------------------------------------ UMMA issuer: tap (ky, kx) = plane (ky&1, kx&1) at row offset (ky/2)*42 + kx/2
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        const uint64_t da0 = make_smem_desc(smem_u32(st_s), 4 * kP1Region, 128);
+        const uint64_t db0 = make_smem_desc(smem_u32(w_s), 512, 128);
+        constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false) & ~((1u << 7) | (1u << 10));     // A, B format fp16 (0)
+        long long s_tempty = 0, s_full = 0;
+        const long long s_begin = clock64();
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const long long c0 = clock64();
+            mbar_wait<P1_HINT>(tempty + acc, acc_phase ^ 1);
+            const long long c1 = clock64();
+            mbar_wait<P1_HINT>(full + stage, phase);
+            s_tempty += c1 - c0; s_full += clock64() - c1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = da0 + (uint64_t)(stage * (kP1StageBytes >> 4));
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    umma_bf16(tmem_base + acc * 32,
+                              da + (uint64_t)(((ky & 1) * 2 + (kx & 1)) * (kP1Region >> 4) + (ky >> 1) * kP1Pitch + (kx >> 1)),
+                              db0 + (uint64_t)(tap * 64), idesc, tap ? 1u : 0u);
+                }
+                umma_commit(empty + stage);
+                umma_commit(tfull + acc);
+            }
+            __syncwarp();
+            if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
+            if (++acc == kP1Acc) { acc = 0; acc_phase ^= 1; }
+        }
+        if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[6] = s_tempty; a.stamps[7] = s_full; a.stamps[8] = clock64() - s_begin; }
+    } else if (warp == kBuildWarps + 9) {
+        // ------------------------------------------------ row producer: one tensor-map copy per tile (gathered stacks) or
+        // one per ring frame - every channel's 7 source rows (588 contiguous bytes of its plane) in one box.  (One
+        // 1-d bulk copy per channel, as the im2col kernel does, was the bottleneck here: ~85 ns per copy issued by a warp.)
+        const int n_src = a.ring_frames ? a.ring_stack : 1;
+        if (lane < n_src) {
+            int rs = 0; uint32_t rphase = 0;
+            const int planes_per_src = a.ring_frames ? a.ring_frame_c : a.cin;
+            const uint32_t nbytes = (uint32_t)(planes_per_src * kP1RawSlot);
+            // geometry and plane index (shift, ring index, episode start: dependent global loads) one tile ahead
+            auto locate = [&](int t, int& word0, int& plane0) {
+                if (t >= total_tiles) return;
+                const int n = t / kP1TilesPerImg;
+                const P1Geom g = p1_geom(t, a.shift ? a.shift[2 * n + 1] : a.pad, a.pad);
+                word0 = (g.rlo * (kImg / 4)) & ~3;              // boxes start on 16-byte boundaries; the builders add (rlo * 84) % 16
+                if (!a.ring_frames) { plane0 = n * a.cin; return; }
+                // frame `lane` of image n's stack (channel_plane)
+                const bool is_next = n >= a.ring_B;
+                const int b = is_next ? n - a.ring_B : n;
+                const int tt = is_next ? a.ring_idx[b] + a.ring_nstep - 1 : a.ring_idx[b] - 1;
+                int r = tt - (a.ring_stack - 1 - lane);
+                r = r < 0 ? 0 : r;
+                plane0 = (int)(((long long)a.ring_ep_start[b] + r) % a.ring_capacity) * a.ring_frame_c;
+            };
+            long long p_wait = 0; const long long p_begin = clock64();
+            int w_next = 0, p_next = 0;
+            locate(blockIdx.x, w_next, p_next);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int word0 = w_next, plane0 = p_next;
+                locate(t + gridDim.x, w_next, p_next);
+                const long long p0 = clock64();
+                mbar_wait<P1_HINT>(rempty + rs, rphase ^ 1);
+                p_wait += clock64() - p0;
+                mbar_arrive_expect_tx(rfull + rs, nbytes);
+                tma_load_2d(smem_u32(raw_s + rs * kP1RawBytes + lane * planes_per_src * kP1RawSlot), &map, word0, plane0, rfull + rs);
+                if (++rs == kP1RawStages) { rs = 0; rphase ^= 1; }
+            }
+            if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[9] = p_wait; a.stamps[10] = clock64() - p_begin; }
+        }
+        pdl_release();
+    } else {
+        // ------------------------------------------------ epilogue warps 16..23: lane quarter warp % 4, two warps per quarter on
+        // alternate tiles (one warp per quarter needs ~1000 cycles per tile between the TMEM load, 80 arithmetic
+        // instructions and its share of the issue slots; the UMMAs of a tile take 400)
+        const int q = warp & 3, par = (warp - kBuildWarps - 1) >> 2;
+        const int m = q * 32 + lane;
+        const int r = m / kP1Pitch, x = m - r * kP1Pitch;
+        float bias_r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias_r[i] = bias_s[i];
+        int ord = par;
+        for (int t = blockIdx.x + par * (int)gridDim.x; t < total_tiles; t += 2 * gridDim.x, ord += 2) {
+            const int acc = ord % kP1Acc; const uint32_t acc_phase = (ord / kP1Acc) & 1;
+            const int n = t / kP1TilesPerImg, y = (t - n * kP1TilesPerImg) * kP1Rows + r;
+            mbar_wait<P1_HINT>(tfull + acc, acc_phase);
+            tc_fence_after();
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+            if (m >= kP1Live || x >= kPW || y >= kPW) continue;
+            const long long row = (long long)n * DRQ_PLB + DRQ_GUARD + y * kPW + x;
+            uint32_t packed[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                packed[i] = pack_bf16x2(fmaxf(fmaf(v[2 * i], kC1Scale, bias_r[2 * i]), 0.f),
+                                        fmaxf(fmaf(v[2 * i + 1], kC1Scale, bias_r[2 * i + 1]), 0.f));
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(a.out + (c * a.cs_out + row) * 8) =
+                    make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kBuildWarps) tmem_dealloc(tmem_base, kP1Acc * 32);
+}
+
+constexpr size_t kConv1PlanesSmem = kP1WBytes + 128 + kP1RawStages * kP1RawBytes + kP1Stages * kP1StageBytes + 128 +
+                                    (2 * kP1Stages + 2 * kP1Acc + 2 * kP1RawStages) * 8 + 16;
+static_assert(kC1WBytes + 128 <= kP1RawStages * kP1RawBytes, "the packed weights are staged in the raw-row buffer");
+static int g_conv1_planes = 1;
+
 constexpr size_t kConv1FwdSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * kC1ABytes +
                                  (3 * kC1Stages + 2 * kC1Acc + 1 + 2 * kC1RawStages) * 8 + 16;
 // wgrad: + one extra d-tile worth of tail padding (rows 32..63 of the M=64 operand read 4 blocks past the tile)
@@ -448,6 +772,12 @@ using namespace drq;
 extern "C" {
 
 int drq_debug_conv1_stamps(int64_t* buf) { g_c1_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
+
+int drq_set_conv1_planes(int on) {
+    const int prev = g_conv1_planes;
+    if (on == 0 || on == 1) g_conv1_planes = on;
+    return prev;
+}
 
 int64_t drq_conv1_w_packed_elems(void) { return kC1Units * 32 * 8 + 64; }
 
@@ -510,6 +840,35 @@ static int conv1_fwd_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t
     a.cs_out = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
     a.n_images = N;
     a.stamps = g_c1_stamps;
+    if (g_conv1_planes) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        EncodeFn encode = reinterpret_cast<EncodeFn>(tensor_map_encoder());
+        DRQ_REQUIRE(encode, "conv1_fwd_bf16: cuTensorMapEncodeTiled is not available");
+        // the source as (words of a channel plane) x (channel planes); a box = the tile's source rows of the planes of one
+        // stack (gathered) or of one ring frame
+        const bool ring = a.ring_frames != nullptr;
+        const void* base = ring ? (const void*)a.ring_frames : (const void*)a.obs;
+        const long long planes = ring ? a.ring_capacity * a.ring_frame_c : (long long)N * cin;
+        const int box_planes = ring ? a.ring_frame_c : cin;
+        DRQ_REQUIRE(((uintptr_t)base % 16) == 0 && planes < (1ll << 31) && box_planes * a.ring_stack * (ring ? 1 : 0) <= 10 && box_planes <= 10,
+                    "conv1_fwd_bf16: source must be 16-byte aligned, <= 10 channels");
+        CUtensorMap map;
+        const cuuint64_t gdim[2] = {(cuuint64_t)(kImg * kImg / 4), (cuuint64_t)planes};
+        const cuuint64_t gstr[1] = {(cuuint64_t)(kImg * kImg)};
+        const cuuint32_t box[2] = {(cuuint32_t)kP1BoxWords, (cuuint32_t)box_planes};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DRQ_REQUIRE(r == CUDA_SUCCESS, "conv1_fwd_bf16: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        if (int rc = ensure_smem((const void*)conv1_planes_kernel<9>, kConv1PlanesSmem, "conv1_fwd_bf16")) return rc;
+        if (int rc = ensure_smem((const void*)conv1_planes_kernel<0>, kConv1PlanesSmem, "conv1_fwd_bf16")) return rc;
+        const int ptiles = N * kP1TilesPerImg;
+        const int G = ptiles < sm_budget() ? ptiles : sm_budget();
+        if (cin == 9) launch_k(conv1_planes_kernel<9>, G, kP1Threads, kConv1PlanesSmem, stream, map, a);
+        else launch_k(conv1_planes_kernel<0>, G, kP1Threads, kConv1PlanesSmem, stream, map, a);
+        return check_launch("conv1_planes_kernel");
+    }
     const int tiles = N * 14;
     const int G = tiles < sm_budget() ? tiles : sm_budget();
     if (cin == 9) launch_k(conv1_tc_kernel<false, 9>, G, kC1Threads, kConv1FwdSmem, stream, a);

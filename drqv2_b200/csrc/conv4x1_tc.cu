@@ -339,16 +339,7 @@ long long* g_stamps = nullptr;
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeFn encode_fn() {
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        cudaDriverEntryPointQueryResult q;
-        void* p = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(p);
-    }
-    return fn;
-}
+static EncodeFn encode_fn() { return reinterpret_cast<EncodeFn>(tensor_map_encoder()); }
 
 }  // namespace c4
 

@@ -18,6 +18,16 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+void* tensor_map_encoder() {
+    static void* fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = p;
+    }
+    return fn;
+}
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -36,17 +36,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  try_wait suspends the
 // thread in hardware for up to the time hint, so waiting warps do not burn issue slots polling.  Kept
 // tiny: the wait is inlined at every use and cold instruction fetch dominates the short kernels.
+template <uint32_t HINT_NS = 1000000u>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 20); ++it) {
+    for (uint32_t it = 0; it < (HINT_NS >= 1000000u ? (1u << 20) : (1u << 28)); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(1000000u)
+            : "r"(addr), "r"(parity), "r"(HINT_NS)
             : "memory");
         if (done) return;
     }

@@ -90,6 +90,11 @@ int drq_set_gemm_small(int on);
  * must leave them room on the SM); 4 = as 1 for the data gradient only.  Same arguments, layouts and results (to fp32
  * accumulation order).  Returns the previous mode; a value outside 0..4 only queries. */
 int drq_set_conv4x1(int mode);
+/* which kernel drq_conv1_fwd_bf16[_ring] launch: 1 (default) = the input pixels are converted once into parity planes and
+ * the nine taps are descriptor offsets into them (9 UMMAs of K = 16 per tile of three output rows), 0 = an im2col tile of
+ * 96 entries per output position is built in shared memory (csrc/conv1_tc.cu, both).  Same arguments, layouts and
+ * results (to fp32 accumulation order).  Returns the previous value; a value outside 0..1 only queries. */
+int drq_set_conv1_planes(int on);
 
 /* ------------------------------------------------------------------ replay */
 

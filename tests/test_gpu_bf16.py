@@ -272,8 +272,17 @@ def test_trunk_weight_pack_and_epilogues(dev):
     assert (got - want_d).abs().max().item() <= 2 ** -8 * want_d.abs().max().item()
 
 
-@pytest.mark.parametrize("N,cin", [(3, 9), (40, 9), (5, 3)])
-def test_conv1_bf16_fwd_and_wgrad(dev, N, cin):
+@pytest.fixture(params=[0, 1], ids=["im2col", "planes"])
+def conv1_mode(request):
+    """both conv1 forward kernels: 0 = im2col tile per output position, 1 = parity planes + tap offsets (default)"""
+    from drqv2_b200 import _lib
+    prev = _lib.lib().drq_set_conv1_planes(request.param)
+    yield request.param
+    _lib.lib().drq_set_conv1_planes(prev)
+
+
+@pytest.mark.parametrize("N,cin", [(3, 9), (40, 9), (5, 3), (2, 10)])
+def test_conv1_bf16_fwd_and_wgrad(dev, N, cin, conv1_mode):
     """conv1 with fused integer-shift augmentation + normalisation, tensor-core path.  The kernel feeds
     the exact pixels (x - 128 in bf16) and bf16 weights, so the reference is fp64 math on exact inputs,
     bf16-rounded weights and (wgrad) the bf16-rounded gradient."""
