@@ -450,6 +450,9 @@ conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int G, int cin, flo
 // lanes write consecutive 16-byte slots (no bank conflicts) and read the bulk-copied source rows directly - the shift
 // and the replicate padding are a clamped byte address and a byte selector, there is no re-pitch pass.  Same
 // exact-integer entries, same epilogue (scale 1/255, fused bias), same results up to fp32 summation order.
+#ifndef P1_RELAXED_WAIT
+#define P1_RELAXED_WAIT mbar_wait_relaxed<128u>
+#endif
 #ifndef P1_HINT
 #define P1_HINT 1000000u        // suspend-time hint of the kernel's mbarrier waits (measured: no effect between 0 and 1 ms)
 #endif
@@ -584,9 +587,9 @@ __global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __gri
                 if (a.shift && tn < total_tiles) sh_next = *reinterpret_cast<const int2*>(a.shift + 2 * (tn / kP1TilesPerImg));
             }
             const P1Geom cur = p1_geom(t, sy, a.pad);
-            mbar_wait<P1_HINT>(rfull + rs, rphase);
+            P1_RELAXED_WAIT(rfull + rs, rphase);
             const long long c1 = clock64();
-            mbar_wait<P1_HINT>(empty + stage, phase ^ 1);
+            P1_RELAXED_WAIT(empty + stage, phase ^ 1);
             const long long c2 = clock64();
             if (worker) {
                 // V row 2*y0 + k = source row clamp(. + sy - pad) (a V row past the image only feeds output rows past it);
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __gri
                 const int word0 = w_next, plane0 = p_next;
                 locate(t + gridDim.x, w_next, p_next);
                 const long long p0 = clock64();
-                mbar_wait<P1_HINT>(rempty + rs, rphase ^ 1);
+                P1_RELAXED_WAIT(rempty + rs, rphase ^ 1);
                 p_wait += clock64() - p0;
                 mbar_arrive_expect_tx(rfull + rs, nbytes);
                 tma_load_2d(smem_u32(raw_s + rs * kP1RawBytes + lane * planes_per_src * kP1RawSlot), &map, word0, plane0, rfull + rs);
