@@ -33,6 +33,8 @@
 
 namespace drq {
 
+DRQ_TRAP_NOTE_HOOK(trap_note_conv1)
+
 using namespace tc;
 
 constexpr int kC1K = 96, kC1Units = kC1K / 8;
@@ -468,7 +470,7 @@ constexpr int kP1WBytes = 9 * 2 * 32 * 16;        // [tap][2 K units][32 co][16 
 constexpr int kP1Units = kP1VRows * (kImg / 4);   // builder work units: (V row, 4 columns) = 147
 constexpr int kP1Group = 160;                     // builder threads per group
 constexpr int kP1Groups = 3;                      // groups take tiles round robin
-constexpr int kP1Acc = 8;                         // accumulator ring: 8 x 32 TMEM columns
+constexpr int kP1Acc = 4;                         // accumulator ring: 4 x 32 TMEM columns
 constexpr int kP1Threads = kP1Groups * kP1Group + 10 * 32; // + UMMA warp, 8 epilogue warps (two per TMEM lane quarter), row producer warp
 constexpr int kP1RawSlot = 640;                   // raw rows of one channel: 7 * 84 bytes + the word a funnel shift may touch, 128-byte granular
 constexpr int kP1BoxWords = kP1RawSlot / 4;       // TMA box: 160 words of a channel plane from the tile's first source row
@@ -760,7 +762,10 @@ __global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __gri
 constexpr size_t kConv1PlanesSmem = kP1WBytes + 128 + kP1RawStages * kP1RawBytes + kP1Stages * kP1StageBytes + 128 +
                                     (2 * kP1Stages + 2 * kP1Acc + 2 * kP1RawStages) * 8 + 16;
 static_assert(kC1WBytes + 128 <= kP1RawStages * kP1RawBytes, "the packed weights are staged in the raw-row buffer");
+// 0 = im2col kernel, 1 (default) = parity planes for launches that fill the machine (>= 48 images, the same rule and the
+// same kernel family as the conv3x3 forward that follows it: csrc/conv_tc.cu), 2 = parity planes always (tests)
 static int g_conv1_planes = 1;
+constexpr int kP1MinImages = 48;
 
 constexpr size_t kConv1FwdSmem = kC1WBytes + 128 + 4 * kC1InBytes + kC1RawStages * kC1RawBytes + kC1Stages * kC1ABytes +
                                  (3 * kC1Stages + 2 * kC1Acc + 1 + 2 * kC1RawStages) * 8 + 16;
@@ -778,7 +783,7 @@ int drq_debug_conv1_stamps(int64_t* buf) { g_c1_stamps = reinterpret_cast<long l
 
 int drq_set_conv1_planes(int on) {
     const int prev = g_conv1_planes;
-    if (on == 0 || on == 1) g_conv1_planes = on;
+    if (on >= 0 && on <= 2) g_conv1_planes = on;
     return prev;
 }
 
@@ -843,7 +848,7 @@ static int conv1_fwd_launch(Conv1TcArgs& a, const int32_t* shift, const uint16_t
     a.cs_out = (long long)N * DRQ_PLB + DRQ_WB_SLACK;
     a.n_images = N;
     a.stamps = g_c1_stamps;
-    if (g_conv1_planes) {
+    if (g_conv1_planes == 2 || (g_conv1_planes == 1 && N >= kP1MinImages)) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
         EncodeFn encode = reinterpret_cast<EncodeFn>(tensor_map_encoder());

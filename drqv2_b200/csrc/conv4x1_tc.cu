@@ -32,6 +32,8 @@
 
 namespace drq {
 
+DRQ_TRAP_NOTE_HOOK(trap_note_conv4x1)
+
 using namespace tc;
 
 namespace c4 {
@@ -108,7 +110,7 @@ __device__ __forceinline__ void expand_weights(const __nv_bfloat16* __restrict__
 static_assert(kWUnits % kExpanders == 0, "expansion loop has no tail");
 
 template <bool DGRAD>
-__global__ void __launch_bounds__(kThreads, 1) conv4x1_tc_kernel(const __grid_constant__ CUtensorMap map, const Args a) {
+__global__ void __maxnreg__(128) conv4x1_tc_kernel(const __grid_constant__ CUtensorMap map, const Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* w_s = smem;
     uint8_t* a_s = smem + kWBytes;

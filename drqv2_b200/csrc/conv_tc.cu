@@ -18,6 +18,8 @@
 
 namespace drq {
 
+DRQ_TRAP_NOTE_HOOK(trap_note_conv)
+
 constexpr int kPLB = DRQ_PLB;        // pixel rows per image in WB buffers
 constexpr int kGuard = DRQ_GUARD;    // zero rows in front of every image
 constexpr int kSlack = DRQ_WB_SLACK; // rows after the last image of each block

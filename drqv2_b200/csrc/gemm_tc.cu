@@ -24,6 +24,8 @@
 
 namespace drq {
 
+DRQ_TRAP_NOTE_HOOK(trap_note_gemm)
+
 using namespace tc;
 
 constexpr int GT_BM = 128, GT_THREADS = 192;

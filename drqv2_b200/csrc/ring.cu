@@ -468,3 +468,15 @@ int drq_random_shift_f32(const float* in, const int32_t* shift, float* out, int 
 }
 
 }  // extern "C"
+
+namespace drq {
+int trap_note_conv(unsigned int*); int trap_note_conv1(unsigned int*); int trap_note_conv4x1(unsigned int*); int trap_note_gemm(unsigned int*);
+}
+extern "C" int drq_debug_trap_note(uint32_t* mapped_host_words) {
+    unsigned int* p = mapped_host_words;
+    if (drq::trap_note_conv(p) | drq::trap_note_conv1(p) | drq::trap_note_conv4x1(p) | drq::trap_note_gemm(p)) {
+        drq::set_error("drq_debug_trap_note: cudaMemcpyToSymbol failed");
+        return DRQ_ERR_CUDA;
+    }
+    return DRQ_OK;
+}

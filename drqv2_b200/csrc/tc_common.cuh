@@ -13,6 +13,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// drq_debug_trap_note: mapped host memory (6 words) that a timed-out mbarrier wait fills in before it traps, or null.
+// One copy per translation unit (no relocatable device code in this build): DRQ_TRAP_NOTE_HOOK(name) defines the
+// unit's setter, ring.cu calls them all.
+static __device__ unsigned int* volatile g_trap_note = nullptr;
+#define DRQ_TRAP_NOTE_HOOK(name)                                                                               \
+    int name(unsigned int* p) { return cudaMemcpyToSymbol(drq::tc::g_trap_note, &p, sizeof(p)) == cudaSuccess ? 0 : 1; }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -51,6 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) return;
     }
+    if (g_trap_note) {      // which wait gave up: (block size, thread, barrier address, parity) in mapped host memory
+        g_trap_note[1] = blockDim.x; g_trap_note[2] = threadIdx.x; g_trap_note[3] = addr; g_trap_note[4] = parity; g_trap_note[5] = blockIdx.x;
+        __threadfence_system();
+        g_trap_note[0] = 1u;
+        __threadfence_system();
+    }
     __trap();
 }
 
@@ -72,6 +85,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "memory");
         if (done) return;
         __nanosleep(SLEEP_NS);
+    }
+    if (g_trap_note) {
+        g_trap_note[1] = blockDim.x; g_trap_note[2] = threadIdx.x; g_trap_note[3] = addr; g_trap_note[4] = parity; g_trap_note[5] = blockIdx.x;
+        __threadfence_system();
+        g_trap_note[0] = 2u;
+        __threadfence_system();
     }
     __trap();
 }

@@ -90,10 +90,11 @@ int drq_set_gemm_small(int on);
  * must leave them room on the SM); 4 = as 1 for the data gradient only.  Same arguments, layouts and results (to fp32
  * accumulation order).  Returns the previous mode; a value outside 0..4 only queries. */
 int drq_set_conv4x1(int mode);
-/* which kernel drq_conv1_fwd_bf16[_ring] launch: 1 (default) = the input pixels are converted once into parity planes and
- * the nine taps are descriptor offsets into them (9 UMMAs of K = 16 per tile of three output rows), 0 = an im2col tile of
- * 96 entries per output position is built in shared memory (csrc/conv1_tc.cu, both).  Same arguments, layouts and
- * results (to fp32 accumulation order).  Returns the previous value; a value outside 0..1 only queries. */
+/* which kernel drq_conv1_fwd_bf16[_ring] launch: 0 = an im2col tile of 96 entries per output position is built in shared
+ * memory; 1 (default) = for launches of >= 48 images the input pixels are converted once into parity planes and the nine
+ * taps are descriptor offsets into them (9 UMMAs of K = 16 per tile of three output rows; csrc/conv1_tc.cu, both), the
+ * former below; 2 = the latter always.  Same arguments, layouts and results (to fp32 accumulation order).  Returns the
+ * previous value; a value outside 0..2 only queries. */
 int drq_set_conv1_planes(int on);
 
 /* ------------------------------------------------------------------ replay */
@@ -327,6 +328,10 @@ int drq_debug_gemm_stamps(int64_t* buf);
 /* the same for drq_conv3x3_{fwd,dgrad}_bf16: [0] producer wait-for-empty, [1] producer total, [2] issuer
  * wait-for-accumulator, [3] issuer wait-for-data, [4] issuer total, [5] epilogue wait-for-accumulator (cycles). */
 int drq_debug_conv_stamps(int64_t* buf);
+/* 6 words of MAPPED HOST memory (cudaHostAlloc / torch pin_memory; readable after the context died), or null: a bounded
+ * mbarrier wait that gives up writes {1 = plain / 2 = sleeping wait, block size, thread, barrier shared-memory address,
+ * parity, block} there before it traps - tells which role of which kernel stopped making progress */
+int drq_debug_trap_note(uint32_t* mapped_host_words);
 /* 12 clock64 totals of block 0 of the four-pixel-column conv kernels (device buffer, or null = off): producer {wait
  * stage, -, -, total}, UMMA warp {wait accumulator, wait stage, issue, total}, first epilogue warp {wait accumulator,
  * TMEM load, math + stores, total} */

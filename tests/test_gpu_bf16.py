@@ -272,9 +272,10 @@ def test_trunk_weight_pack_and_epilogues(dev):
     assert (got - want_d).abs().max().item() <= 2 ** -8 * want_d.abs().max().item()
 
 
-@pytest.fixture(params=[0, 1], ids=["im2col", "planes"])
+@pytest.fixture(params=[0, 2], ids=["im2col", "planes"])
 def conv1_mode(request):
-    """both conv1 forward kernels: 0 = im2col tile per output position, 1 = parity planes + tap offsets (default)"""
+    """both conv1 forward kernels at every size: 0 = im2col tile per output position, 2 = parity planes + tap offsets
+    (the default mode 1 picks it from 48 images up)"""
     from drqv2_b200 import _lib
     prev = _lib.lib().drq_set_conv1_planes(request.param)
     yield request.param

@@ -28,7 +28,7 @@ b = (torch.rand(32, device=dev) - 0.5) * 0.1
 wp = torch.zeros(L.drq_conv1_w_packed_elems(), dtype=torch.bfloat16, device=dev)
 _lib.call("drq_pack_conv1_w_bf16", w.data_ptr(), b.data_ptr(), wp.data_ptr(), 9, s)
 outs = {}
-for mode in (0, 1):
+for mode in (0, 2):
     L.drq_set_conv1_planes(mode)
     out = torch.zeros(L.drq_wb_elems(N), dtype=torch.bfloat16, device=dev)
     f = lambda: _lib.call("drq_conv1_fwd_bf16", obs.data_ptr(), shift.data_ptr(), wp.data_ptr(), out.data_ptr(), N, 9, 4, s)
