@@ -55,6 +55,7 @@ SIGNATURES = {
     "drq_debug_opt_min_blocks": [I],
     "drq_debug_conv_stamps": [P],
     "drq_debug_trap_note": [P],
+    "drq_debug_force_timeout": [P],
     "drq_debug_conv4x1_stamps": [P],
     "drq_debug_conv1_stamps": [P],
     "drq_pack_multi": [P, I, P],

@@ -439,6 +439,18 @@ extern "C" {
 
 int drq_debug_conv_stamps(int64_t* buf) { g_conv_stamps = reinterpret_cast<long long*>(buf); return DRQ_OK; }
 
+// self-test of drq_debug_trap_note: one thread waits on a barrier nobody arrives on (bounded: ~2^20 polls), then traps
+__global__ void debug_force_timeout_kernel() {
+    __shared__ uint64_t bar;
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_wait(&bar, 0);
+}
+int drq_debug_force_timeout(void* stream) {
+    launch_k(debug_force_timeout_kernel, 1, 1, 0, as_stream(stream));
+    return check_launch("debug_force_timeout_kernel");
+}
+
 int drq_set_conv4x1(int mode) {
     const int prev = g_conv4x1;
     if (mode >= 0 && mode <= 4) g_conv4x1 = mode;

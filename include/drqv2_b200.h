@@ -332,6 +332,9 @@ int drq_debug_conv_stamps(int64_t* buf);
  * mbarrier wait that gives up writes {1 = plain / 2 = sleeping wait, block size, thread, barrier shared-memory address,
  * parity, block} there before it traps - tells which role of which kernel stopped making progress */
 int drq_debug_trap_note(uint32_t* mapped_host_words);
+/* self-test of the above: launches one thread that waits on a barrier nobody arrives on; the context dies with a launch
+ * failure after the wait's bound (how long that takes is the bound of every wait in the library) */
+int drq_debug_force_timeout(void* stream);
 /* 12 clock64 totals of block 0 of the four-pixel-column conv kernels (device buffer, or null = off): producer {wait
  * stage, -, -, total}, UMMA warp {wait accumulator, wait stage, issue, total}, first epilogue warp {wait accumulator,
  * TMEM load, math + stores, total} */
