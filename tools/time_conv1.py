@@ -34,7 +34,7 @@ for mode in (0, 2):
     f = lambda: _lib.call("drq_conv1_fwd_bf16", obs.data_ptr(), shift.data_ptr(), wp.data_ptr(), out.data_ptr(), N, 9, 4, s)
     print(f"conv1 fwd mode {mode}: cold {cold(f):6.1f} us  warm {warm(f):6.1f} us", flush=True)
     outs[mode] = out.float()
-print("max |diff|", (outs[0] - outs[1]).abs().max().item(), "of", outs[0].abs().max().item())
+print("max |diff|", (outs[0] - outs[2]).abs().max().item(), "of", outs[0].abs().max().item())
 L.drq_set_conv1_planes(1)
 st = torch.zeros(16, dtype=torch.int64, device=dev)
 L.drq_debug_conv1_stamps(st.data_ptr())
