@@ -222,11 +222,13 @@ actor_sample_kernel(const float* __restrict__ mu_pre, const float* __restrict__ 
 // Policy head (drqv2.py:81,88-92): mu_pre[m][:] = p2[m][:] . bf16(W4)^T + b4 for all M rows of a TB activation - the
 // Linear(hidden, A) as dot products on the CUDA cores (A <= 32 outputs: a tensor-core tile would be > 75 % padding and
 // run on M / 128 CTAs) - and, by the thread that holds each mu_pre value, the TruncatedNormal samples of up to
-// DRQ_POLICY_MAX_JOBS row ranges (utils.py:112-126).  Block = 32 rows x 8 unit groups, as q_head_fwd_kernel.  The
-// weights are rounded to bf16 when they are staged, i.e. the arithmetic is that of the bf16 GEMM this replaces (bf16 x
-// bf16 products, fp32 sums).  A job with metrics needs the batch mean of the log-probabilities: every block leaves its
-// partial sum in scratch[1 + block], the block that finishes last (ticket in scratch[0]) adds them in block order.
+// DRQ_POLICY_MAX_JOBS row ranges (utils.py:112-126).  Block = 8 rows, one warp per row, lanes split the row's 16-byte
+// units (32 rows per block left the launch on M / 32 = 16 SMs: 12.6 us as a graph node).  The weights are rounded to
+// bf16 when they are staged, i.e. the arithmetic is that of the bf16 GEMM this replaces (bf16 x bf16 products, fp32
+// sums).  A job with metrics needs the batch mean of the log-probabilities: every block leaves its partial sum in
+// scratch[1 + block], the block that finishes last (ticket in scratch[0]) adds them in block order.
 struct PolicyJobs { drq_policy_sample j[DRQ_POLICY_MAX_JOBS]; int n; int metrics_job; };
+constexpr int kPolicyRows = 8;
 
 __global__ void __launch_bounds__(256)
 policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, const float* __restrict__ w4,
@@ -235,24 +237,23 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
     pdl_trigger();
     pdl_wait();
     extern __shared__ float w_s[];                       // [A][H]
-    __shared__ float part[8][32][9];
     __shared__ float sh[256];
     __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * kPolicyRows + warp;
+    const int nu = H / 8;
+    const __nv_bfloat16* x = p2 + fb_index(0, m < M ? m : 0, units);
+    // the lane's first units of the row are requested before the weights are staged (hides the staging barrier)
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = lane + 32 * k;
+        v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
+    }
     for (int k = threadIdx.x; k < A * H / 4; k += 256) {          // H % 8 == 0: whole float4s
         const float4 w = __ldg(reinterpret_cast<const float4*>(w4) + k);
         reinterpret_cast<float4*>(w_s)[k] = make_float4(__bfloat162float(__float2bfloat16_rn(w.x)), __bfloat162float(__float2bfloat16_rn(w.y)),
                                                         __bfloat162float(__float2bfloat16_rn(w.z)), __bfloat162float(__float2bfloat16_rn(w.w)));
-    }
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int m = blockIdx.x * 32 + lane;
-    const __nv_bfloat16* x = p2 + fb_index(0, m < M ? m : 0, units);
-    const int nu = H / 8;
-    // the row's first 8 units of this warp are requested before the weights are needed (hides the staging barrier)
-    uint4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int u = grp + 8 * k;
-        v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
     }
     const float std = std_dev ? *std_dev : 0.f;
     const float log_std = jobs.n ? logf(std) : 0.f;
@@ -261,17 +262,17 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
     __syncthreads();
     for (int a0 = 0; a0 < A; a0 += 8) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int u0 = grp; u0 < nu; u0 += 64) {       // 8 units of the row in flight per lane
-            if (u0 != grp || a0 != 0) {
+        for (int u0 = lane; u0 < nu; u0 += 128) {     // 4 units of the row in flight per lane
+            if (u0 != lane || a0 != 0) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int u = u0 + 8 * k;
+                for (int k = 0; k < 4; ++k) {
+                    const int u = u0 + 32 * k;
                     v[k] = (m < M && u < nu) ? __ldg(reinterpret_cast<const uint4*>(x + (long long)u * DRQ_TB_ACT * 8)) : make_uint4(0, 0, 0, 0);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int u = u0 + 8 * k;
+            for (int k = 0; k < 4; ++k) {
+                const int u = u0 + 32 * k;
                 if (u >= nu) break;
                 const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
                 float xv[8];
@@ -290,39 +291,37 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
                 }
             }
         }
+        // the row's dot products: butterfly over the lanes (fixed order), lane a keeps output a0 + a and samples it
+        float mine = 0.f;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) part[grp][lane][a] = acc[a];
-        __syncthreads();
-        {   // 32 rows x 8 outputs: thread (row = tid / 8, a = tid % 8) sums the 8 unit groups in fixed order, then samples
-            const int r = threadIdx.x >> 3, a = threadIdx.x & 7, mr = blockIdx.x * 32 + r, j = a0 + a;
-            if (mr < M && j < A) {
-                float t = 0.f;
-#pragma unroll
-                for (int g2 = 0; g2 < 8; ++g2) t += part[g2][r][a];
-                const float pre = t + b4[j];
-                mu_pre[(long long)mr * A + j] = pre;
-                for (int i = 0; i < jobs.n; ++i) {
-                    const drq_policy_sample& jb = jobs.j[i];
-                    const int b = mr - jb.row0;
-                    if (b < 0 || b >= jb.rows) continue;
-                    const float mu = tanhf(pre);                                   // drqv2.py:89
-                    float av = mu;
-                    if (jb.eps) {
-                        float e = __fmul_rn(jb.eps[(long long)b * A + j], std);    // utils.py:120
-                        if (clip > 0.f) e = fminf(fmaxf(e, -clip), clip);          // utils.py:121-122
-                        av = fminf(fmaxf(__fadd_rn(mu, e), lo), hi);               // utils.py:123, 113-116 (value)
-                        if (i == jobs.metrics_job) {
-                            const float d = av - mu;                                // Normal.log_prob(a)
-                            lp_acc += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
-                        }
+        for (int a = 0; a < 8; ++a) {
+            const float t = warp_sum(acc[a]);
+            if (lane == a) mine = t;
+        }
+        const int j = a0 + lane;
+        if (lane < 8 && m < M && j < A) {
+            const float pre = mine + b4[j];
+            mu_pre[(long long)m * A + j] = pre;
+            for (int i = 0; i < jobs.n; ++i) {
+                const drq_policy_sample& jb = jobs.j[i];
+                const int b = m - jb.row0;
+                if (b < 0 || b >= jb.rows) continue;
+                const float mu = tanhf(pre);                                   // drqv2.py:89
+                float av = mu;
+                if (jb.eps) {
+                    float e = __fmul_rn(jb.eps[(long long)b * A + j], std);    // utils.py:120
+                    if (clip > 0.f) e = fminf(fmaxf(e, -clip), clip);          // utils.py:121-122
+                    av = fminf(fmaxf(__fadd_rn(mu, e), lo), hi);               // utils.py:123, 113-116 (value)
+                    if (i == jobs.metrics_job) {
+                        const float d = av - mu;                                // Normal.log_prob(a)
+                        lp_acc += -(d * d) / (2.0f * std * std) - log_std - 0.9189385332046727f;
                     }
-                    jb.action_out[(long long)b * jb.ld_a + j] = av;
-                    if (jb.a_bf16) reinterpret_cast<__nv_bfloat16*>(jb.a_bf16)[fb_index(jb.feat_off + j, b, jb.units_a)] = __float2bfloat16_rn(av);
-                    if (jb.mu_out) jb.mu_out[(long long)b * A + j] = mu;
                 }
+                jb.action_out[(long long)b * jb.ld_a + j] = av;
+                if (jb.a_bf16) reinterpret_cast<__nv_bfloat16*>(jb.a_bf16)[fb_index(jb.feat_off + j, b, jb.units_a)] = __float2bfloat16_rn(av);
+                if (jb.mu_out) jb.mu_out[(long long)b * A + j] = mu;
             }
         }
-        __syncthreads();
     }
     if (jobs.metrics_job < 0) return;
     // batch mean of the log-probabilities: block partials, combined in block order by the block that finishes last
@@ -334,10 +333,12 @@ policy_head_fwd_kernel(const __nv_bfloat16* __restrict__ p2, long long units, co
     }
     __syncthreads();
     if (!s_last) return;
+    // the last block adds the partials: thread t takes blocks t, t + 256, ... in order, then the block-wide sum (a fixed tree)
+    __threadfence();
+    float mine = 0.f;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 256) mine += __ldcg(reinterpret_cast<const float*>(scratch) + 1 + b);
+    const float tot = block_sum_256(mine, sh);
     if (threadIdx.x == 0) {
-        __threadfence();
-        float tot = 0.f;
-        for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(reinterpret_cast<const float*>(scratch) + 1 + b);
         const drq_policy_sample& jb = jobs.j[jobs.metrics_job];
         jb.metrics[0] = tot / (float)jb.rows;                                       // actor_logprob
         jb.metrics[1] = (float)A * (0.5f + 0.9189385332046727f + log_std);          // actor_ent
@@ -659,9 +660,10 @@ int drq_policy_head_fwd_bf16(const uint16_t* p2, int64_t units, const float* w4,
             pj.metrics_job = i;
         }
     }
+    DRQ_REQUIRE(pj.metrics_job < 0 || (M + kPolicyRows - 1) / kPolicyRows <= 4096, "policy_head_fwd: the metrics scratch holds 4096 block partials (M <= 32768)");
     const size_t smem = (size_t)A * H * sizeof(float);
     if (int rc = ensure_smem((const void*)policy_head_fwd_kernel, smem, "policy_head_fwd")) return rc;
-    launch_k(policy_head_fwd_kernel, (M + 31) / 32, 256, smem, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(p2),
+    launch_k(policy_head_fwd_kernel, (M + kPolicyRows - 1) / kPolicyRows, 256, smem, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(p2),
              (long long)units, w4, b4, mu_pre, M, H, A, pj, std_dev, clip, ticket);
     return check_launch("policy_head_fwd_kernel");
 }

@@ -501,7 +501,7 @@ class DrQV2Agent:
         self._scal_dev = torch.zeros(SCAL_SLOT, device=dev)   # layout: SCAL_OFF
         self._init_scalar_ring()
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._policy_ticket = torch.zeros(1 + 1024, dtype=torch.int32, device=dev)   # drq_policy_head_fwd_bf16's scratch words
+        self._policy_ticket = torch.zeros(1 + 4096, dtype=torch.int32, device=dev)   # drq_policy_head_fwd_bf16's scratch words
         self._metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._injected = None
         self._bf16 = _bf16.Bf16State(self) if self.mode == "bf16" else None

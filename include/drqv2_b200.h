@@ -449,7 +449,7 @@ int drq_actor_sample(const float* mu_pre, const float* eps, const float* std_dev
 /* Policy head of the tensor-core mode in one launch (drqv2.py:81,88-92 + utils.py:112-126): mu_pre[m][a] =
  * p2[m][:] . bf16(w4[a][:]) + b4[a] for the M rows of the TB activation p2 (units per row), and - by the thread that
  * holds each value - drq_actor_sample's arithmetic on up to DRQ_POLICY_MAX_JOBS row ranges.  At most one job carries
- * metrics (it needs eps); `scratch` then is 1 + ceil(M / 32) zero-initialised 32-bit words (block ticket + per-block
+ * metrics (it needs eps); `scratch` then is 1 + ceil(M / 8) (at most 4097) zero-initialised 32-bit words (block ticket + per-block
  * log-prob sums) that the kernel leaves zeroed.  Replaces a 128 x 64 tensor-core tile that was > 75 % padding
  * (A <= 32 outputs) followed by one or two sampling launches. */
 #define DRQ_POLICY_MAX_JOBS 2

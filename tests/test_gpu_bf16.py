@@ -516,7 +516,7 @@ def test_policy_head_matches_linear_tanh_sample(dev, M, A, H):
     p2b.load(p2)
     mu_pre = torch.zeros(M, A, device=dev)
     std = torch.tensor([0.4], device=dev)
-    ticket = torch.zeros(1 + (M + 31) // 32, dtype=torch.int32, device=dev)     # block ticket + per-block log-prob sums
+    ticket = torch.zeros(1 + (M + 7) // 8, dtype=torch.int32, device=dev)       # block ticket + per-block log-prob sums
     n0 = M // 2
     rows = [(0, n0), (n0, M - n0)] if n0 else [(0, M)]
     eps = [torch.randn(r, A, generator=g).to(dev) for _, r in rows]

@@ -23,7 +23,7 @@ b4 = torch.zeros(A, device=dev)
 w4b = TB(A, H, dev, rblk=64); w4b.load(w4)
 mu_pre = torch.zeros(M, A, device=dev)
 std = torch.tensor([0.4], device=dev)
-ticket = torch.zeros(1 + 64, dtype=torch.int32, device=dev)
+ticket = torch.zeros(1 + 4096, dtype=torch.int32, device=dev)
 eps = torch.randn(B, A, device=dev, generator=g)
 out1, out2, mu = torch.zeros(B, A), torch.zeros(B, A), torch.zeros(B, A)
 out1, out2, mu = out1.to(dev), out2.to(dev), mu.to(dev)
