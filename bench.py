@@ -310,15 +310,24 @@ def roofline_record(launches, value, world, flops_update, mode):
     if tensor:
         # the dominant kernel = the kernel (entry point) with the largest share of the update's time; its achieved rate is
         # its algorithmic FLOP over its summed cold-cache launch time.  The slowest single launch is reported beside it.
+        def kernel_of(label):          # one family per kernel function: gemm_tc_kernel<MODE, BN, EPI> instantiations are different kernels
+            name = label.split("(")[0]
+            if name != "gemm":
+                return name
+            kv = dict(p.split("=") for p in label[label.index("(") + 1:-1].split(","))
+            return f"gemm<mode={kv['mode']},bn={kv['bn']},epi={kv['epi']}>"
         fam = {}
         for l in tensor:
-            f = fam.setdefault(l["kernel"].split("(")[0], {"us": 0.0, "flop": 0, "launches": []})
+            f = fam.setdefault(kernel_of(l["kernel"]), {"us": 0.0, "flop": 0, "launches": []})
             f["us"] += l["us"]; f["flop"] += l["flop"]; f["launches"].append(l["kernel"])
         name, dom = max(fam.items(), key=lambda kv: kv[1]["us"])
         ach = dom["flop"] / (dom["us"] * 1e-6) / 1e12
         tr = (traffic.get("kernels", {}).get(name) or {})
+        floor = roof["event_bracket_floor_us"] or 0.0
+        net_us = dom["us"] - floor * len(dom["launches"])
         roof.update({"bound": "tensor", "kernel": name, "kernel_launches": dom["launches"], "achieved": ach, "peak": tf_burst,
                      "unit": "TFLOP/s", "frac": ach / tf_burst, "kernel_us": dom["us"] / len(dom["launches"]),
+                     "frac_net_of_event_bracket": (dom["flop"] / (net_us * 1e-6) / 1e12 / tf_burst) if net_us > 0 else None,
                      "traffic": tr.get("dram_bytes"), "traffic_launch": tr.get("launch"), "traffic_source": traffic.get("source")})
         slow = max(tensor, key=lambda l: l["us"])
         sach = slow["flop"] / (slow["us"] * 1e-6) / 1e12
