@@ -685,6 +685,16 @@ __global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __gri
             if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
             if (++acc == kP1Acc) { acc = 0; acc_phase ^= 1; }
         }
+        // drain: the commits' arrivals on the last stages' `empty` barriers are asynchronous and nobody else waits for them;
+        // the CTA must not exit (and hand its shared memory to the next CTA) while one is still in flight
+        for (int j = 0; j < kP1Stages; ++j) {
+            int s2 = stage - 1 - j; uint32_t ph = phase;
+            if (s2 < 0) { s2 += kP1Stages; ph ^= 1; }
+            // slot s2 was last committed in "wrap" ph (never used at all if the CTA had fewer tiles: its phase 0 never
+            // completes - skip those)
+            const int used = (int)((total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x) + 1;     // tiles of this CTA
+            if (j < used) mbar_wait<P1_HINT>(empty + s2, ph);
+        }
         if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[6] = s_tempty; a.stamps[7] = s_full; a.stamps[8] = clock64() - s_begin; }
     } else if (warp == kBuildWarps + 9) {
         // ------------------------------------------------ row producer: one tensor-map copy per tile (gathered stacks) or

@@ -173,6 +173,15 @@ __global__ void __launch_bounds__(kThreadsTC, 2) conv3x3_tc_kernel(ConvTcArgs a)
             if (++stage == kStagesTC) { stage = 0; phase ^= 1; }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        // drain the last stages' `empty` arrivals (asynchronous, waited for by nobody else) before the CTA may exit
+        {
+            const int used = blockIdx.x < (unsigned)total_tiles ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            for (int j = 0; j < kStagesTC && j < used; ++j) {
+                int s2 = stage - 1 - j; uint32_t ph = phase;
+                if (s2 < 0) { s2 += kStagesTC; ph ^= 1; }
+                mbar_wait(empty + s2, ph);
+            }
+        }
         CV_STAMPS(if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[2] = w_tempty; a.stamps[3] = w_full; a.stamps[4] = CV_T() - t_begin; })
     } else {
         // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
