@@ -128,7 +128,7 @@ def lib():
         if h.drq_abi_version() != 1:
             raise ImportError("libdrqv2_b200.so ABI version mismatch")
         # programmatic dependent launch between the library's kernels (opt-in with DRQV2_B200_PDL=1: measured neutral without early trigger, -25 % with it)
-        h.drq_set_pdl(0 if os.environ.get("DRQV2_B200_PDL", "0") == "0" else 1)
+        h.drq_set_pdl(int(os.environ.get("DRQV2_B200_PDL", "0")))
         if os.environ.get("DRQV2_B200_OPT_MINB"):       # tuning: register target of the fused optimiser kernel
             h.drq_debug_opt_min_blocks(int(os.environ["DRQV2_B200_OPT_MINB"]))
         if os.environ.get("DRQV2_B200_CONV4X1"):        # A/B: 0 = one-pixel-per-row conv kernels, 1 = default, 2 = four-pixel-column kernels always

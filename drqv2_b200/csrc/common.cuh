@@ -30,7 +30,8 @@ void* tensor_map_encoder();
 // remaining tail is MMA drain and epilogue; everything else releases implicitly at exit.  Releasing at kernel
 // entry (pdl_trigger, -DDRQ_PDL_ENTRY_TRIGGER) parks the next kernel's CTAs on the SMs for the whole run of a
 // multi-wave kernel and was measured 25 % slower.  Without the launch attribute the instructions are no-ops.
-extern int g_pdl;
+extern int g_pdl;        // 0 off, 1 every launch, 2 only the launches that ask for it (g_pdl_once)
+extern int g_pdl_once;   // set by a launcher right before launch_k: this launch may start before its predecessor has drained
 // SMs the persistent kernels size their grids for (drq_set_sm_limit): all of them, or fewer when a concurrent
 // collective's CTAs need SMs of their own (a persistent kernel never yields an SM once its CTAs are resident).
 extern int g_sm_limit;
@@ -50,7 +51,8 @@ inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, c
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (g_pdl == 1 || (g_pdl == 2 && g_pdl_once)) ? 1 : 0;
+    g_pdl_once = 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 

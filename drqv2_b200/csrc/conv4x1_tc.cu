@@ -133,7 +133,10 @@ __global__ void __maxnreg__(128) conv4x1_tc_kernel(const __grid_constant__ CUten
         tmem_alloc(tmem_slot, kAcc * 128);
         tmem_relinquish();
     }
-    pdl_wait();
+    // Programmatic dependent launch (the forward chain conv1 -> conv2 -> conv3 -> conv4): everything up to here and the
+    // weight expansion below touch nothing the previous kernel writes (parameters are from the previous update), so a CTA
+    // that gets its SM while other SMs still run the previous kernel's last tiles sets itself up meanwhile; the activation
+    // loads, the mask loads and the output stores wait for the previous grid (pdl_wait in every role).
     if (!DGRAD && threadIdx.x < 32) bias_s[threadIdx.x] = a.bias[threadIdx.x];
     tc_fence_before();
     __syncthreads();
@@ -142,6 +145,7 @@ __global__ void __maxnreg__(128) conv4x1_tc_kernel(const __grid_constant__ CUten
 
     if (warp == 1) {
         // ------------------------------------------------ TMA producer: one box per tile
+        pdl_wait();
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             long long st_empty = 0;
@@ -165,6 +169,7 @@ __global__ void __maxnreg__(128) conv4x1_tc_kernel(const __grid_constant__ CUten
         expand_weights<DGRAD>(a.w, w_s, warp == 0 ? lane : threadIdx.x - 32);
         fence_proxy_async();
         asm volatile("bar.sync 1, %0;" ::"n"(kExpanders) : "memory");
+        pdl_wait();
         if (warp == 0) {
             // -------------------------------------------- UMMA issuer
             // A: K-major, 16-byte K units (channel blocks) 4 regions apart; B: K-major, K units 32 * cnt rows apart
@@ -386,6 +391,7 @@ int conv4x1_launch(bool dgrad, const __nv_bfloat16* in, long long cs_in, const _
         return DRQ_ERR_INVALID;
     }
     const int grid = a.total_tiles < sm_budget() ? a.total_tiles : sm_budget();
+    if (!dgrad) g_pdl_once = 1;       // drq_set_pdl(2): the forward chain's launches overlap their set-up with the predecessor's tail
     if (dgrad) {
         if (int rc = ensure_smem((const void*)conv4x1_tc_kernel<true>, kSmem, "conv4x1_dgrad")) return rc;
         launch_k(conv4x1_tc_kernel<true>, grid, kThreads, kSmem, stream, map, a);

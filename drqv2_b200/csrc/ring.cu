@@ -9,6 +9,7 @@ namespace drq {
 
 static thread_local char g_err[512] = "";
 int g_pdl = 0;
+int g_pdl_once = 0;
 int g_sm_limit = 148;
 
 void set_error(const char* fmt, ...) {
@@ -327,7 +328,7 @@ using namespace drq;
 
 extern "C" {
 
-int drq_set_pdl(int on) { g_pdl = on ? 1 : 0; return DRQ_OK; }
+int drq_set_pdl(int on) { g_pdl = on == 2 ? 2 : (on ? 1 : 0); return DRQ_OK; }
 
 int drq_set_sm_limit(int sms) {
     DRQ_REQUIRE(sms >= 1 && sms <= 148, "set_sm_limit: 1..148");

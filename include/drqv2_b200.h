@@ -70,9 +70,10 @@ int drq_abi_version(void);
 const char* drq_last_error(void);
 /* number of SMs of the current device (0 if none) — used to size persistent grids */
 int drq_device_sm_count(void);
-/* programmatic dependent launch for every kernel of the library (default off): the next kernel's launch
- * latency and CTA-local set-up overlap the running kernel's tail; each kernel waits for its predecessors
- * (griddepcontrol.wait) before touching global memory. */
+/* programmatic dependent launch: 0 (default) off; 1 every kernel of the library - the next kernel's launch latency and
+ * CTA-local set-up overlap the running kernel's tail, each kernel waits for its predecessors (griddepcontrol.wait) before
+ * touching global memory; 2 only the conv3x3 forward launches of the four-pixel-column kernel (the encoder's forward
+ * chain: barrier / TMEM set-up and the weight expansion of layer k+1 run on the SMs that have finished layer k). */
 int drq_set_pdl(int on);
 /* SMs the persistent kernels (convs, GEMMs) size their grids for: 148 (default) or fewer.  A data-parallel update
  * leaves a few SMs to the NCCL all-reduce that runs beside the encoder backward - a persistent kernel keeps every SM it
