@@ -261,7 +261,7 @@ class Critic(nn.Module):
 
 # ----------------------------------------------------------------------------- flat arenas
 @contextlib.contextmanager
-def _capture(graph):
+def _capture(graph, stream=None):
     """``torch.cuda.graph`` with the cyclic garbage collector held off.  A collection in the middle of a
     capture may run the destructors of dead CUDA objects (other agents' graphs, pinned buffers, events);
     cudaFree / cudaEventDestroy from the capturing thread are illegal then and abort the process."""
@@ -270,7 +270,8 @@ def _capture(graph):
     gc.disable()
     try:
         # thread_local: NCCL's watchdog thread may touch CUDA while this thread captures
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        kw = {} if stream is None else {"stream": stream}
+        with torch.cuda.graph(graph, capture_error_mode="thread_local", **kw):
             yield
     finally:
         if was:
@@ -448,6 +449,18 @@ class DrQV2Agent:
         self.small_gemms_beside_encoder = os.environ.get("DRQV2_B200_SMALL_GEMMS", "0") != "0"
         self._side_stream = None
         self._side_stream2 = None
+        self._main_stream = None
+        self._aux = None
+        self._ema = None
+        self._ema_own_stream = os.environ.get("DRQV2_B200_EMA_STREAM", "0") != "0"
+        self._critic_rest = None
+        # schedule switches of the captured tensor-core update; every one leaves the results bit-identical
+        self.early_encoder_backward = os.environ.get("DRQV2_B200_EARLY_ENC", "1") != "0"
+        self.split_critic_step = os.environ.get("DRQV2_B200_SPLIT_CRITIC_STEP", "0") != "0"
+        self.split_actor_step = os.environ.get("DRQV2_B200_SPLIT_ACTOR_STEP", "0") != "0"
+        self.encoder_backward_sms = int(os.environ.get("DRQV2_B200_ENC_BWD_SMS", "140"))
+        # priorities of (main, encoder-backward, weight-gradient) streams inside the captured update; 0 = default (lowest)
+        self._prio = tuple(int(x) for x in os.environ.get("DRQV2_B200_PRIO", "-2,-1,-1").split(","))
         self.mode = mode or os.environ.get("DRQV2_B200_MODE", "bf16")
         if self.mode not in ("fp32", "bf16"):
             raise ValueError(f"mode must be 'fp32' or 'bf16', got {self.mode!r}")
@@ -521,6 +534,9 @@ class DrQV2Agent:
         st["_scal_events"] = [None, None]
         st["_side_stream"] = None
         st["_side_stream2"] = None
+        st["_main_stream"] = None
+        st["_aux"] = None
+        st["_ema"] = None
         return st
 
     def __setstate__(self, st):
@@ -817,7 +833,7 @@ class DrQV2Agent:
                 if state == "warm":
                     torch.cuda.synchronize()
                     state = torch.cuda.CUDAGraph()
-                    with _capture(state):
+                    with _capture(state, self._capture_stream()):
                         self._update_body(ws, fetch, draw=inj is None, ring=ring)
                     self._graphs[key] = state
                 state.replay()
@@ -933,7 +949,7 @@ class DrQV2Agent:
         if not self.overlap_encoder_backward or self.mode != "bf16":
             return None
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=self._dev)
+            self._side_stream = torch.cuda.Stream(device=self._dev, priority=self._prio[1])
         return self._side_stream
 
     def _wgrad_side_stream(self):
@@ -941,8 +957,32 @@ class DrQV2Agent:
         if not self.overlap_encoder_backward or self.mode != "bf16":
             return None
         if self._side_stream2 is None:
-            self._side_stream2 = torch.cuda.Stream(device=self._dev)
+            self._side_stream2 = torch.cuda.Stream(device=self._dev, priority=self._prio[2])
         return self._side_stream2
+
+    def _aux_stream(self):
+        """Fourth stream, at the main chain's priority: the half of critic_opt.step() the actor pass needs second."""
+        if self._aux is None:
+            self._aux = torch.cuda.Stream(device=self._dev, priority=self._prio[0])
+        return self._aux
+
+    def _ema_stream(self):
+        """Stream of the soft target update inside the captured update (None: the weight-gradient stream)."""
+        if not self._ema_own_stream:
+            return None
+        if self._ema is None:
+            self._ema = torch.cuda.Stream(device=self._dev, priority=0)
+        return self._ema
+
+    def _capture_stream(self):
+        """Stream the update graph is captured on (None: torch's own capture stream).  Kernel nodes keep the priority of
+        the stream they were captured on, so the three streams of the schedule can be ranked: when CTAs of two ready
+        kernels compete for SMs, the block scheduler takes the higher priority (lower number) first."""
+        if self._prio[0] == 0 or self.mode != "bf16":
+            return None
+        if self._main_stream is None:
+            self._main_stream = torch.cuda.Stream(device=self._dev, priority=self._prio[0])
+        return self._main_stream
 
     def _update_body(self, ws, fetch=None, draw=True, ring=None):
         """Everything of one update that runs on the device, in stream order; no host sync."""
