@@ -873,7 +873,14 @@ def main():
             os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRQV2_B200_DP_RESERVE_SMS"])
         local = int(os.environ.get("LOCAL_RANK", 0))
         torch.cuda.set_device(local)
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+        kw = {}
+        if os.environ.get("DRQV2_B200_NCCL_HIPRIO", "0") != "0":
+            # the collectives captured into the update graph then run at the highest stream priority: their CTAs are
+            # placed before the persistent conv kernels' when both are waiting for SMs
+            opts = torch.distributed.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            kw["pg_options"] = opts
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local), **kw)
     out = run_ours(args, rank, world)
     if out is not None:
         print(json.dumps(out), flush=True)

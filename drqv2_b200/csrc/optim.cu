@@ -292,20 +292,39 @@ __global__ void __launch_bounds__(256, MINB) adam_pack_kernel(const OptArgs a) {
                     *reinterpret_cast<const uint4*>(sh + lr * t.SW + ul * 8);
         }
     } else if (sg.kind == DRQ_OPT_TRUNK) {
-        // block = (weight row r, channel unit cu, pixel fifth xt): warp w walks channel 8*cu + w, 245 pixels
+        // block = (weight row r, channel unit cu, pixel fifth xt): warp w walks channel 8*cu + w, 245 pixels.  The
+        // channel's pixels start at an arbitrary 4-byte offset (1225 is odd): up to 3 leading and 3 trailing values go
+        // through scalar accesses of single lanes, the 60-61 aligned float4 in between two per lane.
         float (*tile)[256] = reinterpret_cast<float(*)[256]>(smraw);
         const int r = b / 20, rem = b - r * 20;
         const int cu = rem / 5, yx0 = (rem - cu * 5) * kTrunkW;
         const int w = tid >> 5, l = tid & 31;
-        int o[8]; bool ok[8]; float val[8];
+        const int e0 = r * DRQ_REPR_DIM + (cu * 8 + w) * 1225 + yx0;      // first element (segment starts are 16-byte aligned)
+        const int lead = (4 - (e0 & 3)) & 3;
+        const int body4 = (kTrunkW - lead) >> 2;
+        const int tail = kTrunkW - lead - 4 * body4;
+        int i4[2]; bool ok4[2]; float4 v4[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            o[k] = r * DRQ_REPR_DIM + (cu * 8 + w) * 1225 + yx0 + l + 32 * k;
-            ok[k] = l + 32 * k < kTrunkW;
+        for (int k = 0; k < 2; ++k) {
+            ok4[k] = l + 32 * k < body4;
+            i4[k] = ((e0 + lead) >> 2) + l + 32 * k;
         }
-        upd_scalar<8, 7>(u, o, ok, val);
+        // one scalar per lane at most: lanes 0..lead-1 the leading values, lanes 8..8+tail-1 the trailing ones
+        int so[1], spix = -1; bool sok[1]; float sv[1];
+        if (l < lead) spix = l;
+        else if (l >= 8 && l - 8 < tail) spix = lead + 4 * body4 + (l - 8);
+        sok[0] = spix >= 0;
+        so[0] = e0 + (spix >= 0 ? spix : 0);
+        upd_vec<2>(u, i4, ok4, v4);
+        upd_scalar<1, 0>(u, so, sok, sv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tile[w][l + 32 * k] = val[k];
+        for (int k = 0; k < 2; ++k) {
+            if (ok4[k]) {
+                float* t4 = &tile[w][lead + 4 * (l + 32 * k)];
+                t4[0] = v4[k].x; t4[1] = v4[k].y; t4[2] = v4[k].z; t4[3] = v4[k].w;
+            }
+        }
+        if (sok[0]) tile[w][spix] = sv[0];
         __syncthreads();
         if (tid < kTrunkW) {
             uint32_t pk[4];

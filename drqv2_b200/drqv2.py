@@ -446,7 +446,7 @@ class DrQV2Agent:
         # the actor pass' GEMMs in their 66 KB variant, co-resident with the encoder backward's conv CTAs.  Off: measured
         # 1769 vs 1834 updates/s - the encoder backward is the critical chain after the fork, and GEMM CTAs that share its
         # SMs slow it down more than their own waiting costs
-        self.small_gemms_beside_encoder = os.environ.get("DRQV2_B200_SMALL_GEMMS", "0") != "0"
+        self.small_gemms_beside_encoder = os.environ.get("DRQV2_B200_SMALL_GEMMS", "1") != "0"
         self._side_stream = None
         self._side_stream2 = None
         self._main_stream = None
