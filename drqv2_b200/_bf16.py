@@ -123,7 +123,7 @@ OPT_PLAIN, OPT_LINEAR, OPT_TRUNK, OPT_CONV, OPT_CONV1 = 0, 1, 2, 3, 4
 
 class WgReduceJob(C.Structure):
     _fields_ = [("partial", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p), ("n_images", C.c_int32),
-                ("hout", C.c_int32), ("cin", C.c_int32), ("reserved", C.c_int32)]
+                ("hout", C.c_int32), ("cin", C.c_int32), ("ctas", C.c_int32)]
 
 
 class ColsumJob(C.Structure):
@@ -593,13 +593,25 @@ def critic_pass(agent, ws, bw, encoder_grad=True):
             call("drq_conv3x3_dgrad_bf16", d[layer], st.conv_wd[layer - 1].data_ptr(), acts[layer - 1], 2 * B,
                  d[layer - 1], B, hout, s2)
         src = getattr(ws, "ring_src", None)
-        if src is not None:
-            call("drq_conv1_wgrad_bf16_ring", C.byref(src), B, ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
-                 B, agent.aug.pad, s2)
-        else:
-            call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
-                 B, agent.obs_shape[0], agent.aug.pad, s2)
-        jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], 0))
+        # conv1's weight gradient leaves no room for any other block on its SMs: its own (smaller) SM limit when it runs
+        # beside the actor pass, and the number of partials that makes handed to the reduction
+        lim1 = agent.conv1_wgrad_sms if agent._encoder_side_stream() is not None else 0
+        g1 = 0
+        if lim1:
+            prev = _lib.lib().drq_device_sm_count()
+            call("drq_set_sm_limit", lim1)
+            g1 = min(14 * B, lim1)
+        try:
+            if src is not None:
+                call("drq_conv1_wgrad_bf16_ring", C.byref(src), B, ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+                     B, agent.aug.pad, s2)
+            else:
+                call("drq_conv1_wgrad_bf16", ws.obs.data_ptr(), ws.shift.data_ptr(), d[0], bw.wg_ws[0].data_ptr(), None, None,
+                     B, agent.obs_shape[0], agent.aug.pad, s2)
+        finally:
+            if lim1:
+                call("drq_set_sm_limit", prev)
+        jobs.append(WgReduceJob(bw.wg_ws[0].data_ptr(), ge("convnet.0.weight"), ge("convnet.0.bias"), B, 0, agent.obs_shape[0], g1))
         arr = (WgReduceJob * len(jobs))(*jobs)
         call("drq_conv_wgrad_reduce_multi", arr, len(jobs), s2)   # all four layers' partials -> dW, db in one launch
 

@@ -160,7 +160,8 @@ int drq_conv_wgrad_reduce_multi(const drq_wgrad_reduce_job* jobs, int njobs, voi
         DRQ_REQUIRE(jb.partial && jb.dw && jb.db && jb.n_images > 0 && jb.cin >= 0 && jb.cin * 9 + 1 <= 96 &&
                     (jb.cin > 0 || (jb.hout > 0 && jb.hout <= DRQ_PW - 2)), "wgrad_reduce_multi: bad job %d", i);
         wj.j[i] = jb;
-        wj.G[i] = jb.cin > 0 ? conv1_wgrad_ctas(jb.n_images) : conv_wgrad_ctas(jb.n_images, jb.hout);
+        // ctas > 0: the layer's weight-gradient kernel was launched under another SM limit than the current one
+        wj.G[i] = jb.ctas > 0 ? jb.ctas : (jb.cin > 0 ? conv1_wgrad_ctas(jb.n_images) : conv_wgrad_ctas(jb.n_images, jb.hout));
     }
     launch_k(wgrad_reduce_multi_kernel, dim3(kWgReduceBlocks, njobs), 256, 0, as_stream(stream), wj);
     return check_launch("wgrad_reduce_multi_kernel");

@@ -458,6 +458,7 @@ class DrQV2Agent:
         self.early_encoder_backward = os.environ.get("DRQV2_B200_EARLY_ENC", "1") != "0"
         self.split_critic_step = os.environ.get("DRQV2_B200_SPLIT_CRITIC_STEP", "0") != "0"
         self.split_actor_step = os.environ.get("DRQV2_B200_SPLIT_ACTOR_STEP", "0") != "0"
+        self.conv1_wgrad_sms = int(os.environ.get("DRQV2_B200_CONV1_WG_SMS", "0"))
         self.encoder_backward_sms = int(os.environ.get("DRQV2_B200_ENC_BWD_SMS", "140"))
         # priorities of (main, encoder-backward, weight-gradient) streams inside the captured update; 0 = default (lowest)
         self._prio = tuple(int(x) for x in os.environ.get("DRQV2_B200_PRIO", "-2,-1,-1").split(","))

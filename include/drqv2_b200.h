@@ -377,7 +377,7 @@ int drq_colsum_multi(const drq_colsum_job* jobs, int njobs, void* stream);
  * drq_conv1_wgrad_bf16 called with dw == db == NULL leave their per-CTA partials in `partial`; this call
  * reduces them (fixed order) into dw / db.  cin > 0: a conv1 job (N images); cin == 0: a conv3x3 job (N, hout). */
 #define DRQ_WGRAD_REDUCE_MAX_JOBS 4
-typedef struct { const float* partial; float* dw; float* db; int32_t n_images; int32_t hout; int32_t cin; int32_t reserved; } drq_wgrad_reduce_job;
+typedef struct { const float* partial; float* dw; float* db; int32_t n_images; int32_t hout; int32_t cin; int32_t ctas; } drq_wgrad_reduce_job;
 int drq_conv_wgrad_reduce_multi(const drq_wgrad_reduce_job* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------ dense, fp32 */
