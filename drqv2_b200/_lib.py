@@ -27,6 +27,7 @@ SIGNATURES = {
     "drq_ring_sample_step": [P, P, I, U, P, P, P, I, P],
     "drq_update_prologue": [P, I, P, P, U, P, I, P, P, P, P, I, I, P],
     "drq_update_prologue_ring": [P, I, P, P, U, P, I, P, P, P, P, I, I, P, P, P, P, P],
+    "drq_update_prologue_ring_part": [P, I, P, P, U, P, I, P, P, P, P, I, I, P, P, P, P, I, P],
     "drq_conv1_fwd_bf16_ring": [P, I, P, P, P, I, I, P],
     "drq_conv1_wgrad_bf16_ring": [P, I, P, P, P, P, P, I, I, P],
     "drq_rng_normal_f32": [U, P, P, I, P],

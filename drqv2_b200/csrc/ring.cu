@@ -161,7 +161,7 @@ __device__ __forceinline__ void update_draws_elem(unsigned long long seed, unsig
                                                   int* __restrict__ shift_next, float* __restrict__ eps_c,
                                                   float* __restrict__ eps_a, int B, int A, int i) {
     const unsigned range = 2 * pad + 1;
-    if (i < B) {
+    if (shift_obs && i < B) {
         uint32_t r[4];
         Philox::gen(seed, (c << 3) | 1ull, (uint64_t)i, r);
         shift_obs[2 * i] = (int)(((uint64_t)r[0] * range) >> 32);
@@ -170,7 +170,7 @@ __device__ __forceinline__ void update_draws_elem(unsigned long long seed, unsig
         shift_next[2 * i + 1] = (int)(((uint64_t)r[3] * range) >> 32);
     }
     // Box-Muller: 4 words -> 2 pairs -> 4 normals; element i uses pair (i>>1) of stream 3/4.
-    if (i < B * A) {
+    if (eps_c && i < B * A) {
         uint32_t r[4];
         Philox::gen(seed, (c << 3) | 3ull, (uint64_t)(i >> 1), r);
         eps_c[i] = box_muller(r[0], r[1], i & 1);
@@ -213,15 +213,20 @@ __global__ void __launch_bounds__(1024) update_prologue_kernel(const float* scal
 // The head of a ring-fed update in one block: update_prologue_kernel, then ring_sample_step_kernel, then the scalar
 // part of ring_gather_kernel (action copy + un-fused fp32 n-step chain) on the indices just drawn.  The frame stacks
 // stay in the ring (conv1_tc_kernel's row producer reads them through ep_start / idx).
+// `part`: 3 = everything; 1 = only what the encoder's first kernel waits for (the two shift draws, the replay sample);
+// 2 = the rest (host scalars, the two noise draws, n-step reward / discount, action copy), launched after part 1 on a side
+// stream (drq_update_prologue_ring_part).  Same values either way: every draw is a function of (seed, counter, element).
 __global__ void __launch_bounds__(1024) update_prologue_ring_kernel(const float* scal_ring, int slots, unsigned long long* cursor,
                                                                     float* scal_out, unsigned long long seed, unsigned long long* counter,
                                                                     int pad, int* __restrict__ shift_obs, int* __restrict__ shift_next,
                                                                     float* __restrict__ eps_c, float* __restrict__ eps_a, int B, int A,
                                                                     const drq_ring_src src, float* __restrict__ action_out,
-                                                                    float* __restrict__ reward_out, float* __restrict__ discount_out) {
+                                                                    float* __restrict__ reward_out, float* __restrict__ discount_out,
+                                                                    int part) {
     pdl_trigger();
     pdl_wait();
-    if (threadIdx.x < DRQ_SCAL_SLOT) {
+    const bool head = part & 1, rest = part & 2;
+    if (rest && threadIdx.x < DRQ_SCAL_SLOT) {
         const unsigned long long cur = *cursor;
         scal_out[threadIdx.x] = *reinterpret_cast<const volatile float*>(scal_ring + (cur % (unsigned long long)slots) * DRQ_SCAL_SLOT + threadIdx.x);
         __syncwarp();
@@ -230,17 +235,23 @@ __global__ void __launch_bounds__(1024) update_prologue_ring_kernel(const float*
     unsigned long long c = 0;
     if (shift_obs) {
         c = *counter;
-        const int n = B * A > B ? B * A : B;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) update_draws_elem(seed, c, pad, shift_obs, shift_next, eps_c, eps_a, B, A, i);
+        // update_draws_elem writes the shifts of element i < B and the noise of element i < B * A
+        const int n = rest ? (B * A > B ? B * A : B) : B;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            update_draws_elem(seed, c, pad, head ? shift_obs : nullptr, shift_next, rest ? eps_c : nullptr, eps_a, B, A, i);
     }
-    const unsigned long long cs = *src.counter;
-    const int E = *src.n_episodes;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) ring_sample_elem(src.ep_table, E, src.nstep, src.seed, cs, src.ep_start, src.idx, b);
+    unsigned long long cs = 0;
+    if (head) {
+        cs = *src.counter;
+        const int E = *src.n_episodes;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) ring_sample_elem(src.ep_table, E, src.nstep, src.seed, cs, src.ep_start, src.idx, b);
+    }
     __syncthreads();                                  // indices visible to the block; every counter read is done
     if (threadIdx.x == 0) {
-        if (shift_obs) *counter = c + 1ull;
-        *src.counter = cs + 1ull;
+        if (shift_obs && rest) *counter = c + 1ull;   // (part 1 reads the counter part 2 advances)
+        if (head) *src.counter = cs + 1ull;
     }
+    if (!rest) return;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const long long start = src.ep_start[b];
         const int row = src.idx[b];
@@ -433,10 +444,11 @@ int drq_update_prologue(const float* scal_ring, int slots, uint64_t* cursor, flo
     return check_launch("update_prologue_kernel");
 }
 
-int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
-                             uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
-                             float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
-                             float* reward_out, float* discount_out, void* stream) {
+int drq_update_prologue_ring_part(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
+                                  uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
+                                  float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
+                                  float* reward_out, float* discount_out, int part, void* stream) {
+    DRQ_REQUIRE(part >= 1 && part <= 3, "update_prologue_ring: part is 1 (shifts + sample), 2 (the rest) or 3 (both)");
     DRQ_REQUIRE(scal_ring && cursor && scal_out && slots > 0, "update_prologue_ring: bad scalar ring");
     DRQ_REQUIRE(!shift_obs || (counter && shift_next && eps_critic && eps_actor && pad >= 0), "update_prologue_ring: bad draw arguments");
     DRQ_REQUIRE(src && src->action && src->reward && src->discount && src->ep_table && src->n_episodes && src->counter &&
@@ -445,8 +457,16 @@ int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor
     DRQ_REQUIRE(action_out && reward_out && discount_out, "update_prologue_ring: null output");
     launch_k(update_prologue_ring_kernel, 1, 1024, 0, as_stream(stream), scal_ring, slots, (unsigned long long*)cursor, scal_out,
              (unsigned long long)seed, (unsigned long long*)counter, pad, shift_obs, shift_next, eps_critic, eps_actor, B, A,
-             *src, action_out, reward_out, discount_out);
+             *src, action_out, reward_out, discount_out, part);
     return check_launch("update_prologue_ring_kernel");
+}
+
+int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
+                             uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
+                             float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
+                             float* reward_out, float* discount_out, void* stream) {
+    return drq_update_prologue_ring_part(scal_ring, slots, cursor, scal_out, seed, counter, pad, shift_obs, shift_next, eps_critic,
+                                         eps_actor, B, A, src, action_out, reward_out, discount_out, 3, stream);
 }
 
 int drq_scalars_fetch(const float* ring, int slots, uint64_t* cursor, float* out, void* stream) {

@@ -459,6 +459,7 @@ class DrQV2Agent:
         self.split_critic_step = os.environ.get("DRQV2_B200_SPLIT_CRITIC_STEP", "0") != "0"
         self.split_actor_step = os.environ.get("DRQV2_B200_SPLIT_ACTOR_STEP", "0") != "0"
         self.conv1_wgrad_sms = int(os.environ.get("DRQV2_B200_CONV1_WG_SMS", "0"))
+        self.split_prologue = os.environ.get("DRQV2_B200_SPLIT_PROLOGUE", "1") != "0"
         self.encoder_backward_sms = int(os.environ.get("DRQV2_B200_ENC_BWD_SMS", "140"))
         # priorities of (main, encoder-backward, weight-gradient) streams inside the captured update; 0 = default (lowest)
         self._prio = tuple(int(x) for x in os.environ.get("DRQV2_B200_PRIO", "-2,-1,-1").split(","))
@@ -1000,8 +1001,18 @@ class DrQV2Agent:
             # ... and in the same launch the replay sample (replay_buffer.py:142-160): indices, action, n-step reward and
             # discount.  The frame stacks stay in the ring; conv1 reads them through (ep_start, idx).
             ws.ring_src = ring.ring_source()
-            call("drq_update_prologue_ring", *head, ctypes.byref(ws.ring_src), ws.action.data_ptr(), ws.reward.data_ptr(),
-                 ws.discount.data_ptr(), s)
+            tail = (ctypes.byref(ws.ring_src), ws.action.data_ptr(), ws.reward.data_ptr(), ws.discount.data_ptr())
+            side = self._wgrad_side_stream() if self.split_prologue else None
+            if side is None:
+                call("drq_update_prologue_ring", *head, *tail, s)
+            else:
+                # conv1 waits for the shifts and the sample only; the scalars (a read of pinned host memory), the noise and
+                # the n-step chain run beside it and are joined in front of the first kernel behind the encoder
+                call("drq_update_prologue_ring_part", *head, *tail, 1, s)
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    call("drq_update_prologue_ring_part", *head, *tail, 2, _stream())
         else:
             call("drq_update_prologue", *head, s)
             if fetch is not None:
@@ -1009,6 +1020,8 @@ class DrQV2Agent:
         if self.mode == "bf16":
             bw = self.bf16_workspace(B)
             _bf16.encode(self, ws, bw)
+            if ring is not None and self.split_prologue and self._wgrad_side_stream() is not None:
+                torch.cuda.current_stream().wait_stream(self._wgrad_side_stream())
             _bf16.critic_pass(self, ws, bw)
             _bf16.actor_pass(self, ws, bw)
             side = self._encoder_side_stream()

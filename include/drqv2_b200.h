@@ -175,6 +175,14 @@ int drq_update_prologue_ring(const float* scal_ring, int slots, uint64_t* cursor
                              float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
                              float* reward_out, float* discount_out, void* stream);
 
+/* The same in two launches: part 1 = what the encoder's first kernel waits for (the two shift draws and the replay
+ * sample (ep_start, idx)); part 2 = the rest (host scalars, the two noise draws, action copy, n-step reward / discount),
+ * launched after part 1 - on a side stream it runs beside conv1.  part 3 = drq_update_prologue_ring.  Bit-identical. */
+int drq_update_prologue_ring_part(const float* scal_ring, int slots, uint64_t* cursor, float* scal_out, uint64_t seed,
+                                  uint64_t* counter, int pad, int32_t* shift_obs, int32_t* shift_next, float* eps_critic,
+                                  float* eps_actor, int B, int A, const drq_ring_src* src, float* action_out,
+                                  float* reward_out, float* discount_out, int part, void* stream);
+
 /* drq_ring_sample followed by *counter += 1 in one launch (one block). */
 int drq_ring_sample_step(const int32_t* ep_table, const int32_t* n_episodes, int nstep, uint64_t seed, uint64_t* counter,
                          int32_t* ep_start_out, int32_t* idx_out, int B, void* stream);
