@@ -356,15 +356,56 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(Conv1TcArgs a) 
         // ------------------------------------------------ row producer: lane c copies channel c's rows of the tile
         if (lane < a.cin) {
             int rs = 0; uint32_t rphase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileGeom g = tile_geom(t, a.shift, a.pad);
-                const uint8_t* src = channel_plane(a, g.n, lane) + g.rlo * kImg;
-                const int off0 = (g.rlo * kImg) & 15;            // every channel plane starts 16-byte aligned
-                const uint32_t nbytes = (uint32_t)((off0 + g.nrows * kImg + 15) & ~15);
-                mbar_wait(rempty + rs, rphase ^ 1);
-                mbar_arrive_expect_tx(rfull + rs, nbytes);
-                bulk_g2s(raw_s + rs * kC1RawBytes + lane * kC1RawSlot, src - off0, nbytes, rfull + rs);
-                if (++rs == kC1RawStages) { rs = 0; rphase ^= 1; }
+            // As in conv1_planes_kernel's producer: the image's shift, ring index and episode start are requested
+            // kAhead tiles ahead (their round trip to L2, and a 64-bit modulo per tile, were on this warp's serial path:
+            // ~1.3 us per tile), the ring slot is a compare-and-subtract, the lane's frame / channel are loop constants.
+            constexpr int kAhead = 4;
+            constexpr int TPI = (kPW * kPW + kC1Tile - 1) / kC1Tile;
+            const bool ring = a.ring_frames != nullptr;
+            const int fj = ring ? lane / a.ring_frame_c : 0, fcc = ring ? lane - fj * a.ring_frame_c : 0;
+            const int cap = (int)a.ring_capacity;
+            int q_sy[kAhead], q_idx[kAhead], q_ep[kAhead];
+            auto fetch = [&](int t, int& sy, int& idx, int& ep) {
+                sy = a.pad; idx = 0; ep = 0;
+                if (t >= total_tiles) return;
+                const int n = t / TPI;
+                if (a.shift) sy = a.shift[2 * n + 1];
+                if (ring) {
+                    const int b = n >= a.ring_B ? n - a.ring_B : n;
+                    idx = a.ring_idx[b];
+                    ep = a.ring_ep_start[b];
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < kAhead; ++d) fetch(blockIdx.x + d * gridDim.x, q_sy[d], q_idx[d], q_ep[d]);
+            for (int t0 = blockIdx.x; t0 < total_tiles; t0 += kAhead * gridDim.x) {
+#pragma unroll
+                for (int d = 0; d < kAhead; ++d) {
+                    const int t = t0 + d * gridDim.x;
+                    if (t >= total_tiles) break;
+                    const int sy1[2] = {0, q_sy[d]};                 // tile_geom reads shift[2 * n + 1]: hand it element 1 of a pair
+                    const TileGeom g0 = tile_geom(t - (t / TPI) * TPI, sy1, a.pad);   // image 0's tile of the same index: same rows
+                    const int n = t / TPI;
+                    const uint8_t* plane;
+                    if (!ring) {
+                        plane = a.obs + ((long long)n * a.cin + lane) * (kImg * kImg);
+                    } else {
+                        const int tt = n >= a.ring_B ? q_idx[d] + a.ring_nstep - 1 : q_idx[d] - 1;
+                        int r = tt - (a.ring_stack - 1 - fj);
+                        r = r < 0 ? 0 : r;
+                        int slot = q_ep[d] + r;
+                        while (slot >= cap) slot -= cap;
+                        plane = a.ring_frames + ((long long)slot * a.ring_frame_c + fcc) * (long long)(kImg * kImg);
+                    }
+                    fetch(t + kAhead * gridDim.x, q_sy[d], q_idx[d], q_ep[d]);
+                    const uint8_t* src = plane + g0.rlo * kImg;
+                    const int off0 = (g0.rlo * kImg) & 15;           // every channel plane starts 16-byte aligned
+                    const uint32_t nbytes = (uint32_t)((off0 + g0.nrows * kImg + 15) & ~15);
+                    mbar_wait(rempty + rs, rphase ^ 1);
+                    mbar_arrive_expect_tx(rfull + rs, nbytes);
+                    bulk_g2s(raw_s + rs * kC1RawBytes + lane * kC1RawSlot, src - off0, nbytes, rfull + rs);
+                    if (++rs == kC1RawStages) { rs = 0; rphase ^= 1; }
+                }
             }
         }
         pdl_release();                          // last rows are on their way: the next kernel may set itself up
@@ -705,33 +746,53 @@ __global__ void __launch_bounds__(kP1Threads, 1) conv1_planes_kernel(const __gri
             int rs = 0; uint32_t rphase = 0;
             const int planes_per_src = a.ring_frames ? a.ring_frame_c : a.cin;
             const uint32_t nbytes = (uint32_t)(planes_per_src * kP1RawSlot);
-            // geometry and plane index (shift, ring index, episode start: dependent global loads) one tile ahead
-            auto locate = [&](int t, int& word0, int& plane0) {
+            // The tile's geometry needs the image's shift, its ring index and episode start: global loads whose latency
+            // (and, before, a 64-bit modulo per tile) sat on this lane's serial path - one tile of this loop could not be
+            // shorter than a round trip to L2.  The raw values are requested kP1Ahead tiles ahead and only used - clamps,
+            // ring slot by compare-and-subtract (ep_start < capacity, row < capacity) - when their tile comes up.
+            constexpr int kP1Ahead = 4;
+            int q_sy[kP1Ahead], q_idx[kP1Ahead], q_ep[kP1Ahead];
+            auto fetch = [&](int t, int& sy, int& idx, int& ep) {
+                sy = a.pad; idx = 0; ep = 0;
                 if (t >= total_tiles) return;
                 const int n = t / kP1TilesPerImg;
-                const P1Geom g = p1_geom(t, a.shift ? a.shift[2 * n + 1] : a.pad, a.pad);
-                word0 = (g.rlo * (kImg / 4)) & ~3;              // boxes start on 16-byte boundaries; the builders add (rlo * 84) % 16
-                if (!a.ring_frames) { plane0 = n * a.cin; return; }
-                // frame `lane` of image n's stack (channel_plane)
-                const bool is_next = n >= a.ring_B;
-                const int b = is_next ? n - a.ring_B : n;
-                const int tt = is_next ? a.ring_idx[b] + a.ring_nstep - 1 : a.ring_idx[b] - 1;
-                int r = tt - (a.ring_stack - 1 - lane);
-                r = r < 0 ? 0 : r;
-                plane0 = (int)(((long long)a.ring_ep_start[b] + r) % a.ring_capacity) * a.ring_frame_c;
+                if (a.shift) sy = a.shift[2 * n + 1];
+                if (a.ring_frames) {
+                    const int b = n >= a.ring_B ? n - a.ring_B : n;
+                    idx = a.ring_idx[b];
+                    ep = a.ring_ep_start[b];
+                }
             };
+#pragma unroll
+            for (int d = 0; d < kP1Ahead; ++d) fetch(blockIdx.x + d * gridDim.x, q_sy[d], q_idx[d], q_ep[d]);
+            const int cap = (int)a.ring_capacity;
             long long p_wait = 0; const long long p_begin = clock64();
-            int w_next = 0, p_next = 0;
-            locate(blockIdx.x, w_next, p_next);
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int word0 = w_next, plane0 = p_next;
-                locate(t + gridDim.x, w_next, p_next);
-                const long long p0 = clock64();
-                P1_RELAXED_WAIT(rempty + rs, rphase ^ 1);
-                p_wait += clock64() - p0;
-                mbar_arrive_expect_tx(rfull + rs, nbytes);
-                tma_load_2d(smem_u32(raw_s + rs * kP1RawBytes + lane * planes_per_src * kP1RawSlot), &map, word0, plane0, rfull + rs);
-                if (++rs == kP1RawStages) { rs = 0; rphase ^= 1; }
+            for (int t0 = blockIdx.x; t0 < total_tiles; t0 += kP1Ahead * gridDim.x) {
+#pragma unroll
+                for (int d = 0; d < kP1Ahead; ++d) {
+                    const int t = t0 + d * gridDim.x;
+                    if (t >= total_tiles) break;
+                    const int n = t / kP1TilesPerImg;
+                    const P1Geom g = p1_geom(t, q_sy[d], a.pad);
+                    const int word0 = (g.rlo * (kImg / 4)) & ~3;    // boxes start on 16-byte boundaries; the builders add (rlo * 84) % 16
+                    int plane0 = n * a.cin;
+                    if (a.ring_frames) {
+                        // frame `lane` of image n's stack (channel_plane)
+                        const int tt = n >= a.ring_B ? q_idx[d] + a.ring_nstep - 1 : q_idx[d] - 1;
+                        int r = tt - (a.ring_stack - 1 - lane);
+                        r = r < 0 ? 0 : r;
+                        int slot = q_ep[d] + r;
+                        while (slot >= cap) slot -= cap;
+                        plane0 = slot * a.ring_frame_c;
+                    }
+                    fetch(t + kP1Ahead * gridDim.x, q_sy[d], q_idx[d], q_ep[d]);
+                    const long long p0 = clock64();
+                    P1_RELAXED_WAIT(rempty + rs, rphase ^ 1);
+                    p_wait += clock64() - p0;
+                    mbar_arrive_expect_tx(rfull + rs, nbytes);
+                    tma_load_2d(smem_u32(raw_s + rs * kP1RawBytes + lane * planes_per_src * kP1RawSlot), &map, word0, plane0, rfull + rs);
+                    if (++rs == kP1RawStages) { rs = 0; rphase ^= 1; }
+                }
             }
             if (a.stamps && blockIdx.x == 0 && lane == 0) { a.stamps[9] = p_wait; a.stamps[10] = clock64() - p_begin; }
         }
