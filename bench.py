@@ -324,7 +324,7 @@ def profile_update_launches(agent, it, B, reps=5):
 
 def roofline_record(launches, value, world, flops_update, mode):
     hbm, tf_burst, tf_sust, src = peaks()
-    traffic_file = os.path.join(ROOT, "profiles", "r2b_dram_traffic.json")
+    traffic_file = os.path.join(ROOT, "profiles", "r2c_dram_traffic.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
 
     def cls(c):
