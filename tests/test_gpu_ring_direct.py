@@ -63,8 +63,13 @@ def test_prologue_ring_and_conv1_from_ring_bitwise(dev, nstep):
                 out["shift_o"].data_ptr(), out["shift_n"].data_ptr(), out["eps_c"].data_ptr(), out["eps_a"].data_ptr(), B, A)
         if direct:
             src = it.ring_source()
-            _lib.call("drq_update_prologue_ring", *args, C.byref(src), out["action"].data_ptr(), out["reward"].data_ptr(),
-                      out["discount"].data_ptr(), _stream())
+            tail = (C.byref(src), out["action"].data_ptr(), out["reward"].data_ptr(), out["discount"].data_ptr())
+            if direct == "parts":       # the two launches of the update's schedule: shifts + sample, then the rest
+                _lib.call("drq_update_prologue_ring_part", *args, *tail, 1, _stream())
+                assert int(cursor) == 2 and int(counter) == 11, "part 1 leaves the scalar cursor and the draw counter alone"
+                _lib.call("drq_update_prologue_ring_part", *args, *tail, 2, _stream())
+            else:
+                _lib.call("drq_update_prologue_ring", *args, *tail, _stream())
             out["src"] = src
         else:
             _lib.call("drq_update_prologue", *args, _stream())
@@ -74,10 +79,11 @@ def test_prologue_ring_and_conv1_from_ring_bitwise(dev, nstep):
                    lcounter=loader._counter.clone())
         return out
 
-    a, b = head(False), head(True)
+    a, b, c = head(False), head(True), head("parts")
     for k in ("scal", "shift_o", "shift_n", "eps_c", "eps_a", "action", "reward", "discount", "ep_start", "idx", "cursor",
               "counter", "lcounter"):
         assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k], c[k]), ("parts", k)
     assert int(a["lcounter"]) == 8 and int(a["counter"]) == 12 and int(a["cursor"]) == 3
     # the sampled windows include wrapped ones
     es, ix = a["ep_start"].cpu().numpy().astype(np.int64), a["idx"].cpu().numpy()
