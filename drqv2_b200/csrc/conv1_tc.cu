@@ -876,6 +876,8 @@ int drq_pack_conv1_w_bf16(const float* w, const float* bias, uint16_t* out, int 
 static int ring_args(Conv1TcArgs& a, const drq_ring_src* src, int B, int N) {
     DRQ_REQUIRE(src && src->frames && src->ep_start && src->idx, "conv1_*_ring: incomplete ring source");
     DRQ_REQUIRE(src->capacity > 0 && src->frame_c > 0 && src->stack > 0 && src->nstep > 0, "conv1_*_ring: bad ring dims");
+    // the row producers compute the ring slot in 32 bits: episode start + row < 2 * capacity
+    DRQ_REQUIRE(src->capacity <= (1ll << 30), "conv1_*_ring: ring capacity above 2^30 slots");
     DRQ_REQUIRE(B > 0 && N > 0 && N <= 2 * B, "conv1_*_ring: N images must be B (obs) or 2B (obs | next_obs)");
     DRQ_REQUIRE(((uintptr_t)src->frames % 16) == 0, "conv1_*_ring: ring frames must be 16-byte aligned");
     a.ring_frames = src->frames; a.ring_ep_start = src->ep_start; a.ring_idx = src->idx;
