@@ -443,9 +443,10 @@ class DrQV2Agent:
         self.ring_direct = os.environ.get("DRQV2_B200_RING_DIRECT", "1") != "0"
         # Linear(hidden, A) + the TruncatedNormal samples in one CUDA-core launch (0: tensor-core tile + sampling launches)
         self.fused_policy_head = os.environ.get("DRQV2_B200_POLICY_HEAD", "1") != "0"
-        # the actor pass' GEMMs in their 66 KB variant, co-resident with the encoder backward's conv CTAs.  Off: measured
-        # 1769 vs 1834 updates/s - the encoder backward is the critical chain after the fork, and GEMM CTAs that share its
-        # SMs slow it down more than their own waiting costs
+        # the actor pass' GEMMs in their 66 KB variant, co-resident with the encoder backward's conv CTAs.  A loss without
+        # stream priorities (1769 vs 1834 updates/s: GEMM CTAs that share the encoder backward's SMs cost it more than their
+        # own waiting costs), a gain with them (1940 -> 2000: the chain's CTAs are placed first and no longer queue behind a
+        # whole conv kernel)
         self.small_gemms_beside_encoder = os.environ.get("DRQV2_B200_SMALL_GEMMS", "1") != "0"
         self._side_stream = None
         self._side_stream2 = None
@@ -963,7 +964,7 @@ class DrQV2Agent:
         return self._side_stream2
 
     def _aux_stream(self):
-        """Fourth stream, at the main chain's priority: the half of critic_opt.step() the actor pass needs second."""
+        """Fourth stream, at the main chain's priority (the split optimiser steps: DRQV2_B200_SPLIT_*_STEP)."""
         if self._aux is None:
             self._aux = torch.cuda.Stream(device=self._dev, priority=self._prio[0])
         return self._aux
