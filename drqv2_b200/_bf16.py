@@ -632,14 +632,15 @@ def critic_pass(agent, ws, bw, encoder_grad=True):
         beside.join()                               # the critic's weight gradients are complete
     side.wait_stream(main)                          # early: the encoder backward needs the trunk's data gradient only
     with torch.cuda.stream(side):
-        lim = agent.encoder_backward_sms
+        prev = _lib.lib().drq_device_sm_count()      # SMs the persistent kernels may use now (a data-parallel reservation lowers it)
+        lim = min(agent.encoder_backward_sms, prev)
         if lim:                                     # leave SMs to the small kernels of the actor pass (grids are fixed at capture)
             call("drq_set_sm_limit", lim)
         try:
             encoder_backward()
         finally:
             if lim:
-                call("drq_set_sm_limit", 148)
+                call("drq_set_sm_limit", prev)
         if not agent.data_parallel:                 # data-parallel: after the join and the encoder's all-reduce (_update_body)
             st.step_encoder()
     if early:
